@@ -1,0 +1,17 @@
+"""colpali_b200 -- B200-native late-interaction hot path behind the colpali_engine API surface.
+
+Public names mirror the reference (illuin-tech/colpali):
+  score_multi_vector / score_single_vector   <- BaseVisualRetrieverProcessor (utils/processing_utils.py)
+"""
+
+from ._lib import ColpaliB200Error
+from .scoring import DocBank, QueryBlock, maxsim, score_multi_vector, score_single_vector
+
+__all__ = [
+    "ColpaliB200Error",
+    "DocBank",
+    "QueryBlock",
+    "maxsim",
+    "score_multi_vector",
+    "score_single_vector",
+]

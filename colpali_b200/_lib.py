@@ -1,0 +1,84 @@
+"""ctypes binding of libcolpali_b200.so (the C ABI declared in include/colpali_b200.h).
+
+There is deliberately no CPU or PyTorch fallback: if the shared library has not been built, or a
+call fails, the product path raises.  Build with ``python -m colpali_b200.build`` (or
+``__graft_entry__.build()``).
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcolpali_b200.so")
+
+# every symbol include/colpali_b200.h declares; tests check the built library exports them all
+EXPORTED_SYMBOLS = (
+    "cpb_abi_version",
+    "cpb_last_error",
+    "cpb_device_info",
+    "cpb_maxsim_fwd",
+    "cpb_maxsim_workspace_bytes",
+)
+
+CPB_FLAG_ROUND_BF16 = 1
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+class ColpaliB200Error(RuntimeError):
+    """A libcolpali_b200 call returned a non-zero status."""
+
+
+def load() -> ctypes.CDLL:
+    """Load (once) and return the shared library.  Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ColpaliB200Error(
+            f"{LIB_PATH} not found: the sm_100a extension is not built. "
+            "Run `python -m colpali_b200.build` (needs nvcc). There is no CPU fallback."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    c_vp, c_i, c_i64, c_u32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_uint32
+
+    lib.cpb_abi_version.restype = c_i
+    lib.cpb_abi_version.argtypes = []
+    lib.cpb_last_error.restype = ctypes.c_char_p
+    lib.cpb_last_error.argtypes = []
+    lib.cpb_device_info.restype = c_i
+    lib.cpb_device_info.argtypes = [c_i, ctypes.POINTER(c_i), ctypes.POINTER(c_i), ctypes.POINTER(c_i)]
+    lib.cpb_maxsim_workspace_bytes.restype = c_i64
+    lib.cpb_maxsim_workspace_bytes.argtypes = [c_i, c_i, c_i]
+    lib.cpb_maxsim_fwd.restype = c_i
+    lib.cpb_maxsim_fwd.argtypes = [
+        c_vp, c_i, c_i,  # d_q, n_queries, nq_pad
+        c_vp, c_i64,  # d_docs, doc_rows
+        c_vp, c_vp, c_vp, c_i,  # d_doc_start, d_doc_len, d_doc_floor, n_docs
+        c_vp, c_vp, c_vp,  # d_scores, d_argmax, d_workspace
+        c_u32, c_vp,  # flags, stream
+    ]
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().cpb_last_error().decode("utf-8", "replace")
+        raise ColpaliB200Error(f"{what} failed (code {rc}): {msg}")
+
+
+def gpu_launches() -> int:
+    """Number of kernels this process launched through the C ABI (bench.py reports it)."""
+    return _launch_count
+
+
+_launch_count = 0
+
+
+def count_launches(n: int) -> None:
+    global _launch_count
+    _launch_count += n

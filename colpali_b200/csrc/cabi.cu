@@ -1,0 +1,173 @@
+// extern "C" surface of libcolpali_b200.so (declared in include/colpali_b200.h).
+// Host-side only: argument validation, TMA tensor-map encoding, grid sizing, launches.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "../../include/colpali_b200.h"
+#include "maxsim_params.h"
+
+namespace cpb {
+cudaError_t maxsim_launch(const CUtensorMap& tq, const CUtensorMap& td, const MaxSimParams& p, int r, bool argmax,
+                          int grid, cudaStream_t stream);
+cudaError_t maxsim_reduce_segments(const float* partial, float* out, int64_t plane, int nseg, int round_ref,
+                                   cudaStream_t stream);
+}  // namespace cpb
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CPB_CUDA(expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) return fail(CPB_E_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// libcuda is not linked: the driver entry point is fetched through the runtime, so the library
+// loads (and its symbols can be checked) on a machine without a GPU driver.
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// bf16 [rows, 128] row-major -> tiles of [box_rows, 64] written with the 128-byte swizzle.
+// Rows past `rows` are zero-filled by the TMA unit.
+int make_bf16_rowmajor_map(CUtensorMap* map, const void* base, int64_t rows, int cols, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(CPB_E_CUDA, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
+  if (reinterpret_cast<uintptr_t>(base) & 15u) return fail(CPB_E_INVALID, "tensor base %p is not 16-byte aligned", base);
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(cols) * 2};
+  cuuint32_t box[2] = {64, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(CPB_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+  return CPB_OK;
+}
+
+struct DevInfo {
+  int sm_count = 0, major = 0, minor = 0;
+};
+
+int current_device_info(DevInfo* out) {
+  int dev = 0;
+  CPB_CUDA(cudaGetDevice(&dev));
+  CPB_CUDA(cudaDeviceGetAttribute(&out->sm_count, cudaDevAttrMultiProcessorCount, dev));
+  CPB_CUDA(cudaDeviceGetAttribute(&out->major, cudaDevAttrComputeCapabilityMajor, dev));
+  CPB_CUDA(cudaDeviceGetAttribute(&out->minor, cudaDevAttrComputeCapabilityMinor, dev));
+  return CPB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cpb_abi_version(void) { return CPB_ABI_VERSION; }
+
+const char* cpb_last_error(void) { return g_err; }
+
+int cpb_device_info(int device, int* sm_count, int* cc_major, int* cc_minor) {
+  int v = 0;
+  if (sm_count) {
+    CPB_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device));
+    *sm_count = v;
+  }
+  if (cc_major) {
+    CPB_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMajor, device));
+    *cc_major = v;
+  }
+  if (cc_minor) {
+    CPB_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMinor, device));
+    *cc_minor = v;
+  }
+  return CPB_OK;
+}
+
+int64_t cpb_maxsim_workspace_bytes(int n_queries, int nq_pad, int n_docs) {
+  if (nq_pad <= 32) return 0;
+  return static_cast<int64_t>(nq_pad / 32) * n_queries * n_docs * 4;
+}
+
+int cpb_maxsim_fwd(const void* d_q, int n_queries, int nq_pad, const void* d_docs, int64_t doc_rows,
+                   const int32_t* d_doc_start, const int32_t* d_doc_len, const float* d_doc_floor, int n_docs,
+                   float* d_scores, int32_t* d_argmax, float* d_workspace, uint32_t flags, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n_queries <= 0 || n_docs <= 0) return fail(CPB_E_INVALID, "n_queries=%d and n_docs=%d must be positive", n_queries, n_docs);
+  if (nq_pad <= 0 || (nq_pad % 32) != 0) return fail(CPB_E_INVALID, "nq_pad=%d must be a positive multiple of 32", nq_pad);
+  if (!d_q || !d_docs || !d_doc_start || !d_doc_len || !d_scores) return fail(CPB_E_INVALID, "null device pointer");
+  if (doc_rows <= 0 || doc_rows > 0x7fffffffLL) return fail(CPB_E_INVALID, "doc_rows=%lld out of range (1..2^31-1)", static_cast<long long>(doc_rows));
+  const int nseg = nq_pad / 32;
+  if (nseg > 1 && !d_workspace) return fail(CPB_E_INVALID, "nq_pad=%d needs a workspace (cpb_maxsim_workspace_bytes)", nq_pad);
+  const int64_t q_rows64 = static_cast<int64_t>(n_queries) * nq_pad;
+  if (q_rows64 > 0x7fffffffLL) return fail(CPB_E_INVALID, "too many query rows");
+
+  DevInfo di;
+  int rc = current_device_info(&di);
+  if (rc != CPB_OK) return rc;
+  if (di.major != 10) return fail(CPB_E_DEVICE, "device is sm_%d%d; this library needs sm_100 (B200)", di.major, di.minor);
+
+  cpb::MaxSimParams p{};
+  p.doc_start = d_doc_start;
+  p.doc_len = d_doc_len;
+  p.doc_floor = d_doc_floor;
+  p.argmax = d_argmax;
+  p.plane_stride = static_cast<int64_t>(n_queries) * n_docs;
+  p.n_queries = n_queries;
+  p.nq_pad = nq_pad;
+  p.q_rows = static_cast<int>(q_rows64);
+  p.n_docs = n_docs;
+  p.num_qtiles = (p.q_rows + 127) / 128;
+  p.flags = flags;
+  p.scores = (nseg == 1) ? d_scores : d_workspace;
+
+  // Two resident query tiles per CTA halve the L2->SMEM traffic per flop; a single tile only
+  // when there is just one.
+  const int R = (p.num_qtiles >= 2) ? 2 : 1;
+  p.q_groups = (p.num_qtiles + R - 1) / R;
+  int parts = di.sm_count / p.q_groups;
+  if (parts < 1) parts = 1;
+  if (parts > n_docs) parts = n_docs;
+  p.doc_parts = parts;
+  const int grid = p.q_groups * p.doc_parts;
+
+  CUtensorMap tq, td;
+  rc = make_bf16_rowmajor_map(&tq, d_q, q_rows64, 128, 128);
+  if (rc != CPB_OK) return rc;
+  rc = make_bf16_rowmajor_map(&td, d_docs, doc_rows, 128, 256);
+  if (rc != CPB_OK) return rc;
+
+  CPB_CUDA(cpb::maxsim_launch(tq, td, p, R, d_argmax != nullptr, grid, stream));
+  if (nseg > 1)
+    CPB_CUDA(cpb::maxsim_reduce_segments(d_workspace, d_scores, p.plane_stride, nseg,
+                                         (flags & CPB_FLAG_ROUND_BF16) ? 1 : 0, stream));
+  return CPB_OK;
+}
+
+}  // extern "C"

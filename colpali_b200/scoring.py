@@ -1,0 +1,206 @@
+"""Late-interaction (MaxSim) scoring on B200 behind the reference's scorer API.
+
+Mirrors ``BaseVisualRetrieverProcessor.score_multi_vector``
+(/root/reference/colpali_engine/utils/processing_utils.py:132-187): same signature, same
+``ValueError``s, returns a CPU fp32 ``[n_queries, n_passages]`` tensor.  The arithmetic of
+line 179 (``einsum("bnd,csd->bcns").max(dim=3)[0].sum(dim=2)``) runs in ONE fused sm_100a kernel
+(csrc/maxsim_sm100.cu) over a flat, device-resident document bank; the reference's re-padding and
+re-upload of every 128-document batch for every 128-query batch (:170-180) disappears.
+
+Zero-padding semantics are kept: the reference pads each 128-document batch with zero rows up to
+that batch's longest document, and those rows take part in the max (a shorter document's
+per-token maximum is ``max(real, 0)``).  ``DocBank`` records that as a per-document floor.
+"""
+
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Union
+
+import torch
+
+from . import _lib
+
+EMBED_DIM = 128  # embedding dim one kernel pass contracts over (smaller dims are zero-padded)
+TensorOrList = Union[torch.Tensor, List[torch.Tensor]]
+
+
+def _require_cuda(device: torch.device) -> None:
+    if device.type != "cuda":
+        raise _lib.ColpaliB200Error(
+            f"colpali_b200 computes on CUDA sm_100a only (got device '{device}'); there is no CPU path. "
+            "Use the reference implementation for CPU scoring."
+        )
+
+
+def _resolve_device(device: Optional[Union[str, torch.device]]) -> torch.device:
+    # processing_utils.py:161 / utils/torch_utils.py:22-29: None -> "cuda:0" when available.
+    if device is None or (isinstance(device, str) and device == "auto"):
+        if not torch.cuda.is_available():
+            raise _lib.ColpaliB200Error("no CUDA device available; colpali_b200 has no CPU path")
+        return torch.device("cuda:0")
+    device = torch.device(device)
+    if device.type == "cuda" and device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    return device
+
+
+def _pad_dim(x: torch.Tensor) -> torch.Tensor:
+    """bf16, last dim zero-padded to EMBED_DIM (zero columns add nothing to a dot product)."""
+    d = x.shape[-1]
+    if d > EMBED_DIM:
+        raise _lib.ColpaliB200Error(f"embedding dim {d} > {EMBED_DIM} is not supported by this build")
+    if x.dtype != torch.bfloat16:
+        x = x.to(torch.bfloat16)
+    if d < EMBED_DIM:
+        x = torch.nn.functional.pad(x, (0, EMBED_DIM - d))
+    return x
+
+
+class QueryBlock:
+    """Queries laid out for the kernel: ``[n * nq_pad, 128]`` bf16, each query padded with zero
+    rows to ``nq_pad`` (multiple of 32) rows, so that one epilogue warp == one query segment."""
+
+    def __init__(self, qs: TensorOrList, device: torch.device):
+        _require_cuda(device)
+        if isinstance(qs, torch.Tensor):
+            if qs.dim() != 3:
+                raise ValueError(f"query tensor must be [n, len, dim], got {tuple(qs.shape)}")
+            n, nq, _ = qs.shape
+            lens = [nq] * n
+        else:
+            n = len(qs)
+            lens = [int(q.shape[0]) for q in qs]
+            nq = max(lens) if n else 0
+        if n == 0:
+            raise ValueError("No queries provided")
+        self.n = n
+        self.nq_pad = max(32, (nq + 31) // 32 * 32)
+        flat = torch.zeros(n, self.nq_pad, EMBED_DIM, dtype=torch.bfloat16, device=device)
+        if isinstance(qs, torch.Tensor):
+            flat[:, :nq] = _pad_dim(qs.to(device, non_blocking=True))
+        else:
+            for i, q in enumerate(qs):
+                if lens[i]:
+                    flat[i, : lens[i]] = _pad_dim(q.to(device, non_blocking=True))
+        self.flat = flat.view(n * self.nq_pad, EMBED_DIM)
+        self.device = device
+
+
+class DocBank:
+    """Device-resident document bank: flat ``[rows, 128]`` bf16 tokens + (start, len, floor) per doc.
+
+    ``floor[j]`` is 0 where the reference would have zero-padded document ``j`` inside its
+    128-document batch (processing_utils.py:176-178) and -inf elsewhere.  Build once, score many
+    query batches against it.
+    """
+
+    def __init__(self, flat: torch.Tensor, start: torch.Tensor, length: torch.Tensor,
+                 floor: Optional[torch.Tensor]):
+        self.flat, self.start, self.length, self.floor = flat, start, length, floor
+        self.n_docs = int(start.numel())
+        self.device = flat.device
+
+    @staticmethod
+    def from_passages(ps: TensorOrList, device: torch.device, batch_size: int = 128,
+                      reference_padding: bool = True) -> "DocBank":
+        _require_cuda(device)
+        if len(ps) == 0:
+            raise ValueError("No passages provided")
+        if isinstance(ps, torch.Tensor):
+            if ps.dim() != 3:
+                raise ValueError(f"passage tensor must be [n, len, dim], got {tuple(ps.shape)}")
+            n, L, _ = ps.shape
+            flat = _pad_dim(ps.to(device, non_blocking=True)).reshape(n * L, EMBED_DIM).contiguous()
+            start = torch.arange(0, n * L, L, dtype=torch.int32, device=device)
+            length = torch.full((n,), L, dtype=torch.int32, device=device)
+            return DocBank(flat, start, length, None)  # equal lengths: the reference pads nothing
+        lens = [int(p.shape[0]) for p in ps]
+        n = len(ps)
+        # one pass over the bank: device-side cat of the per-document uploads
+        flat = _pad_dim(torch.cat([p.to(device, non_blocking=True) for p in ps], dim=0)).contiguous()
+        if flat.shape[0] == 0:
+            flat = torch.zeros(1, EMBED_DIM, dtype=torch.bfloat16, device=device)
+        lens_t = torch.tensor(lens, dtype=torch.int64)
+        start = (torch.cumsum(lens_t, 0) - lens_t).to(torch.int32).to(device)
+        length = lens_t.to(torch.int32).to(device)
+        floor = None
+        if reference_padding:
+            fl = torch.full((n,), float("-inf"), dtype=torch.float32)
+            any_pad = False
+            for j in range(0, n, batch_size):
+                chunk = lens_t[j : j + batch_size]
+                padded = chunk < chunk.max()
+                if bool(padded.any()):
+                    any_pad = True
+                    fl[j : j + batch_size][padded] = 0.0
+            floor = fl.to(device) if any_pad else None
+        return DocBank(flat, start, length, floor)
+
+
+def maxsim(q: QueryBlock, bank: DocBank, *, round_bf16: bool = False, want_argmax: bool = False):
+    """Run the fused kernel.  Returns device fp32 ``[n_queries, n_docs]`` (and int32 argmax
+    ``[n_docs, n_queries * nq_pad]`` when asked)."""
+    lib = _lib.load()
+    dev = bank.device
+    scores = torch.empty(q.n, bank.n_docs, dtype=torch.float32, device=dev)
+    argmax = torch.empty(bank.n_docs, q.n * q.nq_pad, dtype=torch.int32, device=dev) if want_argmax else None
+    ws_bytes = lib.cpb_maxsim_workspace_bytes(q.n, q.nq_pad, bank.n_docs)
+    ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev) if ws_bytes else None
+    flags = _lib.CPB_FLAG_ROUND_BF16 if round_bf16 else 0
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = lib.cpb_maxsim_fwd(
+            q.flat.data_ptr(), q.n, q.nq_pad,
+            bank.flat.data_ptr(), bank.flat.shape[0],
+            bank.start.data_ptr(), bank.length.data_ptr(),
+            bank.floor.data_ptr() if bank.floor is not None else None, bank.n_docs,
+            scores.data_ptr(), argmax.data_ptr() if argmax is not None else None,
+            ws.data_ptr() if ws is not None else None,
+            flags, stream,
+        )
+    _lib.check(rc, "cpb_maxsim_fwd")
+    _lib.count_launches(2 if ws is not None else 1)
+    return (scores, argmax) if want_argmax else scores
+
+
+def score_multi_vector(
+    qs: TensorOrList,
+    ps: TensorOrList,
+    batch_size: int = 128,
+    device: Optional[Union[str, torch.device]] = None,
+    *,
+    round_bf16: bool = False,
+) -> torch.Tensor:
+    """Drop-in for ``BaseVisualRetrieverProcessor.score_multi_vector`` (processing_utils.py:132-187).
+
+    ``batch_size`` no longer bounds memory (no score tensor is materialised); it is kept because it
+    defines the reference's zero-padding groups, hence the result for ragged list inputs.
+    Extra keyword ``round_bf16`` reproduces the reference's bf16-rounded scores for bf16 inputs.
+    """
+    dev = _resolve_device(device)
+    if len(qs) == 0:
+        raise ValueError("No queries provided")
+    if len(ps) == 0:
+        raise ValueError("No passages provided")
+    _require_cuda(dev)
+    bank = ps if isinstance(ps, DocBank) else DocBank.from_passages(ps, dev, batch_size=batch_size)
+    q = QueryBlock(qs, dev)
+    scores = maxsim(q, bank, round_bf16=round_bf16)
+    out = scores.cpu()  # the reference contract: scores live on the CPU (:180)
+    assert out.shape[0] == len(qs), f"Expected {len(qs)} scores, got {out.shape[0]}"
+    return out.to(torch.float32)
+
+
+def score_single_vector(qs: TensorOrList, ps: TensorOrList,
+                        device: Optional[Union[str, torch.device]] = None) -> torch.Tensor:
+    """Dense dot-product scorer (processing_utils.py:103-130) as the N_q = N_d = 1 case of MaxSim."""
+    dev = _resolve_device(device)
+    if isinstance(qs, list) and isinstance(ps, list):
+        if len(qs) == 0:
+            raise ValueError("No queries provided")
+        if len(ps) == 0:
+            raise ValueError("No passages provided")
+        qs, ps = torch.stack(qs), torch.stack(ps)
+    q = QueryBlock(qs.unsqueeze(1), dev)
+    bank = DocBank.from_passages(ps.unsqueeze(1), dev)
+    return maxsim(q, bank).to(torch.float32)

@@ -1,0 +1,85 @@
+/*
+ * colpali_b200 -- C ABI of the B200-native late-interaction hot path.
+ *
+ * The reference (illuin-tech/colpali, `colpali_engine`) is pure Python and has no FFI of its own:
+ * the seams this library sits behind are three Python attributes.  Each
+ * entry point below names the reference code it replaces.  The Python host side
+ * (colpali_b200/*.py) binds these symbols with ctypes and keeps the reference signatures.
+ *
+ * Conventions
+ *   - every pointer named `d_*` is a DEVICE pointer owned by the caller (PyTorch's caching
+ *     allocator in practice); the library allocates nothing and never synchronises the device;
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued on it and the call returns;
+ *   - bf16 tensors are raw uint16 storage, row-major, rows of `dim` elements;
+ *   - return value: 0 on success, negative CPB_E_* on error; cpb_last_error() returns a
+ *     thread-local human-readable message for the most recent failure on the calling thread;
+ *   - functions are re-entrant and keep no global mutable state besides a cached driver
+ *     entry point.
+ */
+#ifndef COLPALI_B200_H_
+#define COLPALI_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CPB_ABI_VERSION 1
+
+/* error codes */
+#define CPB_OK 0
+#define CPB_E_INVALID (-1)   /* bad argument (shape, alignment, null pointer)      */
+#define CPB_E_UNSUPPORTED (-2) /* valid request this build cannot serve (e.g. dim) */
+#define CPB_E_CUDA (-3)      /* a CUDA runtime / driver call failed                 */
+#define CPB_E_DEVICE (-4)    /* device is not sm_100 (tcgen05 / TMEM required)      */
+
+/* flags for cpb_maxsim_fwd */
+#define CPB_FLAG_ROUND_BF16 1u /* emulate the reference's bf16 result rounding: each per-token
+                                  maximum and the final score are rounded to bf16 (what
+                                  torch.einsum(...).max().sum() yields for bf16 inputs,
+                                  processing_utils.py:179) instead of staying fp32. */
+
+int cpb_abi_version(void);
+const char* cpb_last_error(void);
+
+/* Number of SMs / compute capability of `device` (for grid sizing on the host side). */
+int cpb_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
+
+/*
+ * Fused MaxSim forward.
+ *   replaces: torch.einsum("bnd,csd->bcns", q, d).max(dim=3)[0].sum(dim=2)
+ *             colpali_engine/utils/processing_utils.py:179  (score_multi_vector inner loop)
+ *             colpali_engine/loss/late_interaction_losses.py:153-154 (ColbertLoss scores),
+ *             :297-298 (ColbertPairwiseCELoss), :444-445 (ColbertSigmoidLoss)
+ *
+ *   d_q          bf16 [n_queries * nq_pad, 128]; every query occupies nq_pad rows (nq_pad a
+ *                multiple of 32), zero rows after its real tokens (a zero row adds 0, exactly
+ *                like the reference's zero padding of queries, processing_utils.py:172).
+ *   d_docs       bf16 [doc_rows, 128]: flat token bank.
+ *   d_doc_start  int32 [n_docs]: first bank row of each document.
+ *   d_doc_len    int32 [n_docs]: number of rows of each document (0 allowed).
+ *   d_doc_floor  fp32 [n_docs] or NULL: initial value of every per-token maximum of that
+ *                document; -inf = plain max, 0 = the document had zero-padding rows in the
+ *                reference batch (processing_utils.py:176-178: pad rows score exactly 0 and take
+ *                part in the max).  NULL means -inf everywhere.
+ *   d_scores     fp32 [n_queries, n_docs] out.
+ *   d_argmax     int32 [n_docs, n_queries * nq_pad] out, or NULL.  Row index (relative to the
+ *                document start) of the first maximal token for every (document, query row);
+ *                -1 when the maximum is the floor.  Needed by cpb_maxsim_bwd.
+ *   d_workspace  fp32 [(nq_pad/32) * n_queries * n_docs] scratch, only read when nq_pad > 32
+ *                (may be NULL otherwise).
+ */
+int cpb_maxsim_fwd(const void* d_q, int n_queries, int nq_pad,
+                   const void* d_docs, int64_t doc_rows,
+                   const int32_t* d_doc_start, const int32_t* d_doc_len, const float* d_doc_floor, int n_docs,
+                   float* d_scores, int32_t* d_argmax, float* d_workspace,
+                   uint32_t flags, void* stream);
+
+/* Bytes of d_workspace cpb_maxsim_fwd needs for this shape (0 when nq_pad == 32). */
+int64_t cpb_maxsim_workspace_bytes(int n_queries, int nq_pad, int n_docs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COLPALI_B200_H_ */
