@@ -1,0 +1,280 @@
+#!/usr/bin/env python
+"""Benchmark of the late-interaction hot path (BASELINE.json metric: MaxSim queries/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A *step* is one pass of the hot path over one batch: 32 queries (N_q = 32) scored against a
+1000-document bank (N_d = 1030, dim 128, bf16) = BASELINE.json configs[1].  Under torchrun (N > 1)
+every rank scores the same 32 queries against ITS OWN 1000-document shard of an N*1000-document
+corpus (weak scaling) and the [32, 1000] score slabs are all-gathered (NCCL) inside the timed region,
+so "queries/sec" counts query x 1000-document-shard units across all ranks.
+
+Prints ONE JSON line (rank 0).  Keys: see the contract in DESIGN.md section "Measurement".
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_QUERIES, N_Q, N_DOCS, N_D, DIM = 32, 32, 1000, 1030, 128
+FLOPS_PER_STEP = 2.0 * N_QUERIES * N_Q * N_DOCS * N_D * DIM  # 2*Bq*Nq*Bd*Nd*D
+MIN_BYTES_PER_STEP = 2 * (N_DOCS * N_D * DIM + N_QUERIES * N_Q * DIM) + 4 * N_QUERIES * N_DOCS
+METRIC = "maxsim_queries_per_sec"
+UNIT = "queries/s"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p.get("bf16_tflops_sustained"),
+                "hbm_gbs": p["hbm_gbs"], "source": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self._stop = [], set(), threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    _NAMES = {
+        0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+        0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost",
+        0x100: "display_clock_setting",
+    }
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self._NAMES.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.002)
+
+    def __enter__(self):
+        if self.ok:
+            self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self.ok:
+            self.t.join(timeout=1)
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": getattr(self, "max_mhz", None), "reasons": [], "samples": 0}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def cpu_reference_arm(steps: int, warmup: int, threads: int):
+    """Times the oracle port of score_multi_vector (the reference's torch.einsum CPU path,
+    processing_utils.py:170-187) on the host cores.  Returns (queries/s, seconds/step, sample)."""
+    from oracle import li_oracle as O  # bench.py's CPU-baseline leg is allowed to execute oracle/
+
+    torch.set_num_threads(threads)
+    q, d = O.cfg2_inputs()
+    for _ in range(max(1, min(warmup, 1))):
+        O.score_multi_vector_port(q, d, batch_size=128, device="cpu")
+    times = []
+    for _ in range(steps):
+        t = time.perf_counter()
+        O.score_multi_vector_port(q, d, batch_size=128, device="cpu")
+        times.append(time.perf_counter() - t)
+    times.sort()
+    med = times[len(times) // 2]
+    return N_QUERIES / med, med, f"full step (32 queries x 1000 docs x 1030 x 128 bf16) x {steps}, median"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    steps = max(3, min(args.steps, 9))
+    qps, sec, sample = cpu_reference_arm(steps, args.warmup, threads)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "score_multi_vector 32q x 1000d x 1030p x 128d bf16 (BASELINE configs[1])",
+                   "path": "oracle port of colpali_engine score_multi_vector (torch.einsum, CPU, batch_size=128)"},
+        "cpu_baseline": {"value": qps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args):
+    import torch.distributed as dist
+
+    import colpali_b200 as cb
+    from colpali_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # synthetic unit-norm bf16 embeddings generated on device; each rank owns a different shard
+    g = torch.Generator(device=dev).manual_seed(1000 + rank)
+    gq = torch.Generator(device=dev).manual_seed(0)
+    q = torch.nn.functional.normalize(torch.randn(N_QUERIES, N_Q, DIM, device=dev, generator=gq), dim=-1).bfloat16()
+    d = torch.nn.functional.normalize(torch.randn(N_DOCS, N_D, DIM, device=dev, generator=g), dim=-1).bfloat16()
+    bank = cb.DocBank.from_passages(d, dev)
+    qb = cb.QueryBlock(q, dev)
+    gathered = torch.empty(world, N_QUERIES, N_DOCS, dtype=torch.float32, device=dev) if world > 1 else None
+
+    def step():
+        s = cb.maxsim(qb, bank)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered.view(world * N_QUERIES, N_DOCS), s)
+        return s
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sync_all()
+
+    # ---- kernel-resident throughput: K steps, CUDA events on the launching stream ----------------
+    l0 = _lib.gpu_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        sync_all()
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        sync_all()
+    launches = _lib.gpu_launches() - l0
+    ms_total = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
+    ms_step = float(ms_total) / args.steps
+    value = world * N_QUERIES / (ms_step * 1e-3)
+
+    # ---- the dominant kernel alone (no collective): roofline numerator --------------------------
+    k_steps = max(10, min(args.steps, 200))
+    sync_all()
+    e0.record()
+    for _ in range(k_steps):
+        cb.maxsim(qb, bank)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_kernel = e0.elapsed_time(e1) / k_steps
+
+    # ---- end to end through the reference-facing API, host buffers in, host scores out ----------
+    q_host = q.cpu().pin_memory()
+    d_host = d.cpu().pin_memory()
+    e2e_steps = max(3, min(args.steps, 10))
+    cb.score_multi_vector(q_host, d_host, device=dev)
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        out = cb.score_multi_vector(q_host, d_host, device=dev)
+    torch.cuda.synchronize()
+    e2e_s = torch.tensor([(time.perf_counter() - t0) / e2e_steps], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * N_QUERIES / float(e2e_s)
+    assert out.shape == (N_QUERIES, N_DOCS) and out.device.type == "cpu"
+
+    if rank == 0:
+        pk = peaks()
+        achieved = FLOPS_PER_STEP / (ms_kernel * 1e-3) / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "maxsim_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {
+                "workload": "score_multi_vector 32q x 1000d x 1030p x 128d bf16 (BASELINE configs[1]) per GPU",
+                "parallelism": f"corpus-sharded x{world}: 1000 docs/rank, all_gather of [32,1000] fp32 slabs" if world > 1 else "single GPU",
+                "l2": "document bank (264 MB) exceeds L2 (126 MB); no explicit flush",
+                "timing": "CUDA events on the launching stream, max over ranks",
+            },
+            "roofline": {
+                "bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": achieved / pk["bf16_tflops"], "traffic": traffic, "peak_source": pk["source"] + " burst",
+                "kernel_ms": ms_kernel, "algorithmic_flops_per_launch": FLOPS_PER_STEP,
+                "algorithmic_bytes_per_launch": MIN_BYTES_PER_STEP,
+                "hbm_gbs_achieved": MIN_BYTES_PER_STEP / (ms_kernel * 1e-3) / 1e9,
+            },
+            "e2e": {"value": e2e_value, "unit": UNIT,
+                    "h2d_bytes_per_step": q_host.numel() * 2 + d_host.numel() * 2,
+                    "d2h_bytes_per_step": N_QUERIES * N_DOCS * 4, "steps": e2e_steps,
+                    "api": "colpali_b200.score_multi_vector(pinned host q, pinned host docs) -> CPU fp32"},
+            "gpu_launches": launches,
+            "clocks": clk.summary(),
+        }
+        if not args.no_cpu and world == 1:
+            threads = os.cpu_count() or 1
+            qps, sec, sample = cpu_reference_arm(5, 1, threads)
+            line["cpu_baseline"] = {"value": qps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                                    "seconds_per_step": sec}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

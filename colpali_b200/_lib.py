@@ -19,6 +19,7 @@ EXPORTED_SYMBOLS = (
     "cpb_abi_version",
     "cpb_last_error",
     "cpb_device_info",
+    "cpb_set_option",
     "cpb_maxsim_fwd",
     "cpb_maxsim_workspace_bytes",
 )
@@ -51,6 +52,8 @@ def load() -> ctypes.CDLL:
     lib.cpb_last_error.argtypes = []
     lib.cpb_device_info.restype = c_i
     lib.cpb_device_info.argtypes = [c_i, ctypes.POINTER(c_i), ctypes.POINTER(c_i), ctypes.POINTER(c_i)]
+    lib.cpb_set_option.restype = c_i
+    lib.cpb_set_option.argtypes = [ctypes.c_char_p, c_i]
     lib.cpb_maxsim_workspace_bytes.restype = c_i64
     lib.cpb_maxsim_workspace_bytes.argtypes = [c_i, c_i, c_i]
     lib.cpb_maxsim_fwd.restype = c_i
@@ -69,6 +72,11 @@ def check(rc: int, what: str) -> None:
     if rc != 0:
         msg = load().cpb_last_error().decode("utf-8", "replace")
         raise ColpaliB200Error(f"{what} failed (code {rc}): {msg}")
+
+
+def set_option(name: str, value: int) -> None:
+    """Tuning knob passthrough (cpb_set_option): 'cluster', 'qtiles_per_cta', 'debug_flags'."""
+    check(load().cpb_set_option(name.encode(), int(value)), f"cpb_set_option({name})")
 
 
 def gpu_launches() -> int:

@@ -12,8 +12,10 @@
 #include "maxsim_params.h"
 
 namespace cpb {
-cudaError_t maxsim_launch(const CUtensorMap& tq, const CUtensorMap& td, const MaxSimParams& p, int r, bool argmax,
+cudaError_t maxsim_launch(const CUtensorMap& td, const CUtensorMap& tt, const MaxSimParams& p, int r, bool argmax,
                           int grid, cudaStream_t stream);
+int maxsim_max_clusters(int cluster);
+int maxsim_tile_n();
 cudaError_t maxsim_reduce_segments(const float* partial, float* out, int64_t plane, int nseg, int round_ref,
                                    cudaStream_t stream);
 }  // namespace cpb
@@ -21,6 +23,11 @@ cudaError_t maxsim_reduce_segments(const float* partial, float* out, int64_t pla
 namespace {
 
 thread_local char g_err[512] = "";
+
+// tuning knobs (cpb_set_option); 0 = choose automatically
+int g_opt_cluster = 0;
+int g_opt_qtiles_per_cta = 0;
+unsigned g_opt_debug_flags = 0;
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -110,6 +117,22 @@ int cpb_device_info(int device, int* sm_count, int* cc_major, int* cc_minor) {
   return CPB_OK;
 }
 
+int cpb_set_option(const char* name, int value) {
+  if (!name) return fail(CPB_E_INVALID, "null option name");
+  if (!strcmp(name, "cluster")) {
+    if (value != 0 && value != 1 && value != 2 && value != 4) return fail(CPB_E_INVALID, "cluster must be 0, 1, 2 or 4");
+    g_opt_cluster = value;
+  } else if (!strcmp(name, "qtiles_per_cta")) {
+    if (value < 0 || value > 2) return fail(CPB_E_INVALID, "qtiles_per_cta must be 0, 1 or 2");
+    g_opt_qtiles_per_cta = value;
+  } else if (!strcmp(name, "debug_flags")) {
+    g_opt_debug_flags = static_cast<unsigned>(value) & 0xffff0000u;
+  } else {
+    return fail(CPB_E_INVALID, "unknown option '%s'", name);
+  }
+  return CPB_OK;
+}
+
 int64_t cpb_maxsim_workspace_bytes(int n_queries, int nq_pad, int n_docs) {
   if (nq_pad <= 32) return 0;
   return static_cast<int64_t>(nq_pad / 32) * n_queries * n_docs * 4;
@@ -121,6 +144,7 @@ int cpb_maxsim_fwd(const void* d_q, int n_queries, int nq_pad, const void* d_doc
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (n_queries <= 0 || n_docs <= 0) return fail(CPB_E_INVALID, "n_queries=%d and n_docs=%d must be positive", n_queries, n_docs);
   if (nq_pad <= 0 || (nq_pad % 32) != 0) return fail(CPB_E_INVALID, "nq_pad=%d must be a positive multiple of 32", nq_pad);
+  if (reinterpret_cast<uintptr_t>(d_q) & 15u) return fail(CPB_E_INVALID, "d_q is not 16-byte aligned");
   if (!d_q || !d_docs || !d_doc_start || !d_doc_len || !d_scores) return fail(CPB_E_INVALID, "null device pointer");
   if (doc_rows <= 0 || doc_rows > 0x7fffffffLL) return fail(CPB_E_INVALID, "doc_rows=%lld out of range (1..2^31-1)", static_cast<long long>(doc_rows));
   const int nseg = nq_pad / 32;
@@ -134,6 +158,7 @@ int cpb_maxsim_fwd(const void* d_q, int n_queries, int nq_pad, const void* d_doc
   if (di.major != 10) return fail(CPB_E_DEVICE, "device is sm_%d%d; this library needs sm_100 (B200)", di.major, di.minor);
 
   cpb::MaxSimParams p{};
+  p.q = d_q;
   p.doc_start = d_doc_start;
   p.doc_len = d_doc_len;
   p.doc_floor = d_doc_floor;
@@ -149,21 +174,37 @@ int cpb_maxsim_fwd(const void* d_q, int n_queries, int nq_pad, const void* d_doc
 
   // Two resident query tiles per CTA halve the L2->SMEM traffic per flop; a single tile only
   // when there is just one.
-  const int R = (p.num_qtiles >= 2) ? 2 : 1;
+  int R = (p.num_qtiles >= 2) ? 2 : 1;
+  if (g_opt_qtiles_per_cta == 1 || g_opt_qtiles_per_cta == 2) R = g_opt_qtiles_per_cta;
   p.q_groups = (p.num_qtiles + R - 1) / R;
-  int parts = di.sm_count / p.q_groups;
+  // CTAs of a cluster hold different query-tile groups and share every document tile through TMA
+  // multicast.  Pairs tile the 148 SMs exactly; clusters of 4 strand SMs in GPCs whose SM count is
+  // not a multiple of 4, so they are opt-in.
+  int cluster = (p.q_groups >= 2) ? 2 : 1;
+  if (g_opt_cluster == 1 || g_opt_cluster == 2 || g_opt_cluster == 4) cluster = g_opt_cluster;
+  int max_clusters = cpb::maxsim_max_clusters(cluster);
+  if (max_clusters <= 0) {
+    if (cluster == 1) return fail(CPB_E_CUDA, "kernel cannot be resident on this device (shared memory?)");
+    cluster = 1;
+    max_clusters = cpb::maxsim_max_clusters(1);
+    if (max_clusters <= 0) return fail(CPB_E_CUDA, "kernel cannot be resident on this device (shared memory?)");
+  }
+  p.cluster = cluster;
+  p.group_sets = (p.q_groups + cluster - 1) / cluster;
+  int parts = max_clusters / p.group_sets;
   if (parts < 1) parts = 1;
   if (parts > n_docs) parts = n_docs;
   p.doc_parts = parts;
-  const int grid = p.q_groups * p.doc_parts;
+  p.flags = flags | g_opt_debug_flags;
+  const int grid = p.group_sets * p.doc_parts * cluster;
 
-  CUtensorMap tq, td;
-  rc = make_bf16_rowmajor_map(&tq, d_q, q_rows64, 128, 128);
+  CUtensorMap td, tt;
+  rc = make_bf16_rowmajor_map(&td, d_docs, doc_rows, 128, cpb::maxsim_tile_n() / cluster);
   if (rc != CPB_OK) return rc;
-  rc = make_bf16_rowmajor_map(&td, d_docs, doc_rows, 128, 256);
+  rc = make_bf16_rowmajor_map(&tt, d_docs, doc_rows, 128, 32);
   if (rc != CPB_OK) return rc;
 
-  CPB_CUDA(cpb::maxsim_launch(tq, td, p, R, d_argmax != nullptr, grid, stream));
+  CPB_CUDA(cpb::maxsim_launch(td, tt, p, R, d_argmax != nullptr, grid, stream));
   if (nseg > 1)
     CPB_CUDA(cpb::maxsim_reduce_segments(d_workspace, d_scores, p.plane_stride, nseg,
                                          (flags & CPB_FLAG_ROUND_BF16) ? 1 : 0, stream));

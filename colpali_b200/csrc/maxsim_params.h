@@ -4,9 +4,15 @@
 
 #include "../../include/colpali_b200.h"
 
+// internal (profiling only) flag bits, never set through the public header
+#define CPB_DBG_SKIP_EPILOGUE 0x10000u
+#define CPB_DBG_NO_TMA 0x20000u   /* producer signals 'full' without loading (MMA re-reads stale smem) */
+#define CPB_DBG_CLOCKS 0x40000u   /* CTA b writes (SM cycles, ns) of its main loop to scores[2b], scores[2b+1] */
+
 namespace cpb {
 
 struct MaxSimParams {
+  const void* q;             // bf16 [q_rows, 128] padded queries
   const int32_t* doc_start;  // [n_docs] first bank row of each document
   const int32_t* doc_len;    // [n_docs] rows per document
   const float* doc_floor;    // [n_docs] or nullptr (-inf)
@@ -19,7 +25,9 @@ struct MaxSimParams {
   int n_docs;
   int num_qtiles;  // ceil(q_rows / 128)
   int q_groups;    // ceil(num_qtiles / R)
-  int doc_parts;   // CTAs per query group; grid = q_groups * doc_parts
+  int cluster;     // CTAs per cluster (1, 2 or 4); they share a document partition via TMA multicast
+  int group_sets;  // ceil(q_groups / cluster)
+  int doc_parts;   // document partitions; grid = group_sets * doc_parts * cluster
   uint32_t flags;
 };
 

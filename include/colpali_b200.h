@@ -47,6 +47,14 @@ const char* cpb_last_error(void);
 int cpb_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
 
 /*
+ * Tuning knobs for experiments (process-wide, not thread-safe against concurrent launches):
+ *   "cluster"         0 = auto, 1 / 2 / 4 = CTAs per cluster sharing document tiles by TMA multicast
+ *   "qtiles_per_cta"  0 = auto, 1 / 2     = resident 128-row query tiles per CTA
+ *   "debug_flags"     profiling-only bits (upper 16), 0 in production
+ */
+int cpb_set_option(const char* name, int value);
+
+/*
  * Fused MaxSim forward.
  *   replaces: torch.einsum("bnd,csd->bcns", q, d).max(dim=3)[0].sum(dim=2)
  *             colpali_engine/utils/processing_utils.py:179  (score_multi_vector inner loop)

@@ -1,0 +1,223 @@
+"""Generate tests/golden/*.npz by executing the UNMODIFIED reference (/root/reference) on CPU.
+
+TEST INFRASTRUCTURE.  Run in the build container only (the GPU box has no /root/reference):
+
+    python oracle/make_golden.py
+
+Every fixture stores the reference's outputs; inputs are either stored (small cases) or re-created
+from the seeded generators in oracle/li_oracle.py with a checksum to detect RNG drift.  The same
+script asserts that the oracle port agrees with the reference on every case, which is what pins the
+oracle ("parity pinned against reference outputs").
+"""
+
+from __future__ import annotations
+
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+sys.dont_write_bytecode = True
+
+from colpali_engine.loss import ColbertLoss, ColbertPairwiseCELoss  # noqa: E402  (reference)
+from colpali_engine.utils.processing_utils import BaseVisualRetrieverProcessor as RefProc  # noqa: E402
+
+from oracle import li_oracle as O  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+os.makedirs(GOLD, exist_ok=True)
+
+
+def bits(x: torch.Tensor) -> np.ndarray:
+    """bf16 tensor -> uint16 bit patterns (npz has no bf16)."""
+    return x.contiguous().view(torch.int16).numpy().view(np.uint16)
+
+
+def checksum(x: torch.Tensor) -> float:
+    return float(x.double().sum())
+
+
+def ref_score(qs, ps, **kw):
+    return RefProc.score_multi_vector(qs, ps, device="cpu", **kw)
+
+
+def scorer_small():
+    out = {}
+    # (1) the reference's own unit test shapes, tests/utils/test_processing_utils.py:15-35
+    g = torch.Generator().manual_seed(7)
+    qs = [torch.randn(2, 32, generator=g), torch.randn(4, 32, generator=g)]
+    ps = [torch.randn(8, 32, generator=g), torch.randn(4, 32, generator=g), torch.randn(16, 32, generator=g)]
+    out["t1_q"] = torch.nn.utils.rnn.pad_sequence(qs, batch_first=True).numpy()
+    out["t1_qlen"] = np.array([2, 4])
+    out["t1_p"] = torch.nn.utils.rnn.pad_sequence(ps, batch_first=True).numpy()
+    out["t1_plen"] = np.array([8, 4, 16])
+    out["t1_list"] = ref_score(qs, ps).numpy()
+    out["t1_tensor"] = ref_score(torch.nn.utils.rnn.pad_sequence(qs, batch_first=True),
+                                 torch.nn.utils.rnn.pad_sequence(ps, batch_first=True)).numpy()
+    assert np.allclose(out["t1_list"], out["t1_tensor"])
+    assert torch.allclose(O.score_multi_vector_port(qs, ps), torch.from_numpy(out["t1_list"]))
+
+    # (2) the zero-padding trap of SURVEY.md section 8 a1' (4)
+    q = [torch.tensor([[1.0, 0.0]])]
+    a = torch.tensor([[-1.0, 0.0], [-0.5, 0.0]])
+    b3 = torch.tensor([[-0.2, 0.0], [-0.3, 0.0], [-0.9, 0.0]])
+    out["t2_alone"] = ref_score(q, [a]).numpy()
+    out["t2_batched"] = ref_score(q, [a, b3]).numpy()
+    out["t2_bs1"] = ref_score(q, [a, b3], batch_size=1).numpy()
+    assert out["t2_alone"][0, 0] == -0.5 and out["t2_batched"][0, 0] == 0.0 and out["t2_bs1"][0, 0] == -0.5
+
+    # (3) ragged bf16, several padding groups (batch_size=3) and the default grouping
+    g = torch.Generator().manual_seed(11)
+    qlen = [5, 32, 17, 1, 40]
+    plen = [1, 16, 17, 255, 256, 257, 600, 1030, 7, 64]
+    qs = [torch.nn.functional.normalize(torch.randn(n, 128, generator=g), dim=-1).bfloat16() for n in qlen]
+    ps = [torch.nn.functional.normalize(torch.randn(n, 128, generator=g), dim=-1).bfloat16() for n in plen]
+    out["t3_q"] = bits(torch.cat(qs))
+    out["t3_qlen"] = np.array(qlen)
+    out["t3_p"] = bits(torch.cat(ps))
+    out["t3_plen"] = np.array(plen)
+    out["t3_bf16"] = ref_score(qs, ps).numpy()
+    out["t3_fp32"] = ref_score([x.float() for x in qs], [x.float() for x in ps]).numpy()
+    out["t3_fp32_bs3"] = ref_score([x.float() for x in qs], [x.float() for x in ps], batch_size=3).numpy()
+    for bs, key in ((128, "t3_fp32"), (3, "t3_fp32_bs3")):
+        port = O.score_multi_vector_port([x.float() for x in qs], [x.float() for x in ps], batch_size=bs)
+        assert torch.equal(port, torch.from_numpy(out[key])), key
+        f64 = O.maxsim_f64(qs, ps, O.reference_floors(plen, bs))
+        assert np.allclose(f64, out[key], rtol=1e-5, atol=1e-5), key
+    assert torch.equal(O.score_multi_vector_port(qs, ps), torch.from_numpy(out["t3_bf16"]))
+    np.savez_compressed(os.path.join(GOLD, "scorer_small.npz"), **out)
+    print("scorer_small ok")
+
+
+def scorer_cfg(name, q, d):
+    t = time.time()
+    bf = ref_score(q, d)
+    t_bf = time.time() - t
+    t = time.time()
+    fp = ref_score(q.float(), d.float())
+    t_fp = time.time() - t
+    assert torch.equal(O.score_multi_vector_port(q, d), bf)
+    port_fp = O.score_multi_vector_port(q.float(), d.float())
+    assert torch.equal(port_fp, fp)
+    sub = slice(0, 16)
+    f64 = O.maxsim_f64(list(q), list(d[sub]))
+    assert np.allclose(f64, fp[:, sub].numpy(), rtol=2e-6, atol=2e-5)
+    np.savez_compressed(
+        os.path.join(GOLD, f"scorer_{name}.npz"),
+        ref_bf16=bf.numpy(), ref_fp32=fp.numpy(),
+        q_checksum=checksum(q), d_checksum=checksum(d),
+        q_shape=np.array(q.shape), d_shape=np.array(d.shape),
+        ref_seconds=np.array([t_bf, t_fp]), threads=torch.get_num_threads(),
+    )
+    print(f"scorer_{name} ok (reference CPU {t_bf:.2f}s bf16, {t_fp:.2f}s fp32)")
+
+
+def loss_small():
+    """B=4, C=6, N_q=5, N_d=9, fp32, offset=1, zero query rows and zero doc rows."""
+    g = torch.Generator().manual_seed(5)
+    q = torch.nn.functional.normalize(torch.randn(4, 5, 16, generator=g), dim=-1)
+    d = torch.nn.functional.normalize(torch.randn(6, 9, 16, generator=g), dim=-1)
+    q[1, 3:] = 0
+    q[3, 4:] = 0
+    d[0, :2] = 0
+    d[4, :1] = 0
+    out = {"q": q.numpy().copy(), "d": d.numpy().copy()}
+    for name, mod, kw in (
+        ("colbert", ColbertLoss(), {}),
+        ("colbert_nonorm_t1", ColbertLoss(temperature=1.0, normalize_scores=False), {}),
+        ("colbert_filter", ColbertLoss(pos_aware_negative_filtering=True), {}),
+        ("pairwise", ColbertPairwiseCELoss(), {}),
+        ("pairwise_filter", ColbertPairwiseCELoss(pos_aware_negative_filtering=True), {}),
+    ):
+        qq, dd = q.clone().requires_grad_(True), d.clone().requires_grad_(True)
+        loss = mod(qq, dd, offset=1)
+        loss.backward()
+        out[f"{name}_loss"] = loss.detach().numpy()
+        out[f"{name}_dq"] = qq.grad.numpy()
+        out[f"{name}_dd"] = dd.grad.numpy()
+    # port agreement
+    assert torch.allclose(O.colbert_loss_port(q, d, offset=1), torch.from_numpy(out["colbert_loss"]))
+    assert torch.allclose(O.colbert_loss_port(q, d, offset=1, pos_aware_negative_filtering=True),
+                          torch.from_numpy(out["colbert_filter_loss"]))
+    assert torch.allclose(O.colbert_pairwise_ce_loss_port(q, d, offset=1), torch.from_numpy(out["pairwise_loss"]))
+    np.savez_compressed(os.path.join(GOLD, "loss_small.npz"), **out)
+    print("loss_small ok")
+
+
+def loss_cfg3():
+    q, d, lens = O.cfg3_inputs()
+    out = {"q_checksum": checksum(q), "d_checksum": checksum(d), "lens": lens.numpy()}
+    for name, cls in (("colbert", ColbertLoss), ("pairwise", ColbertPairwiseCELoss)):
+        out[f"{name}_bf16"] = cls()(q, d).float().numpy()
+        qq, dd = q.float().requires_grad_(True), d.float().requires_grad_(True)
+        t = time.time()
+        loss = cls()(qq, dd)
+        out[f"{name}_fwd_seconds"] = time.time() - t
+        loss.backward()
+        out[f"{name}_fp32"] = loss.detach().numpy()
+        out[f"{name}_dq"] = qq.grad.numpy()
+        out[f"{name}_dd_first2"] = dd.grad[:2].numpy()
+        out[f"{name}_dd_abs_sum"] = float(dd.grad.abs().sum())
+        out[f"{name}_dd_rownorm"] = dd.grad.norm(dim=-1).numpy().astype(np.float32)
+        print(f"  {name}: bf16 {float(out[name + '_bf16']):.5f} fp32 {float(out[name + '_fp32']):.5f}")
+    assert torch.allclose(O.colbert_loss_port(q.float(), d.float()), torch.from_numpy(out["colbert_fp32"]))
+    assert torch.allclose(O.colbert_pairwise_ce_loss_port(q.float(), d.float()), torch.from_numpy(out["pairwise_fp32"]))
+    np.savez_compressed(os.path.join(GOLD, "loss_cfg3.npz"), **out)
+    print("loss_cfg3 ok")
+
+
+def head_small():
+    """Run the reference ColQwen2 (tiny random-init config) and capture the head's input/output."""
+    from transformers.models.qwen2_vl import Qwen2VLConfig
+
+    from colpali_engine.models import ColQwen2
+
+    torch.manual_seed(0)
+    cfg = Qwen2VLConfig(
+        text_config=dict(hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=4,
+                         num_key_value_heads=2, vocab_size=512, rope_scaling={"type": "mrope", "mrope_section": [8, 12, 12]}),
+        vision_config=dict(depth=1, embed_dim=32, hidden_size=256, num_heads=2, patch_size=14),
+    )
+    out = {}
+    for dtype, tag in ((torch.bfloat16, "bf16"), (torch.float32, "fp32")):
+        torch.manual_seed(0)
+        model = ColQwen2(cfg).to(dtype).eval()
+        captured = {}
+        model.custom_text_proj.register_forward_hook(lambda m, i, o: captured.__setitem__("h", i[0].detach()))
+        ids = torch.randint(0, 500, (3, 24))
+        mask = torch.ones(3, 24, dtype=torch.long)
+        mask[0, :7] = 0  # left padding (processing_colqwen2.py:43)
+        mask[2, :3] = 0
+        with torch.no_grad():
+            emb = model(input_ids=ids, attention_mask=mask)
+        h = captured["h"]
+        w, b = model.custom_text_proj.weight.detach(), model.custom_text_proj.bias.detach()
+        port = O.head_port(h, w, b, mask)
+        assert torch.equal(port, emb), tag
+        conv = bits if dtype == torch.bfloat16 else (lambda x: x.numpy())
+        out[f"{tag}_h"], out[f"{tag}_w"], out[f"{tag}_b"], out[f"{tag}_out"] = conv(h), conv(w), conv(b), conv(emb)
+        out[f"{tag}_mask"] = mask.numpy()
+    np.savez_compressed(os.path.join(GOLD, "head_small.npz"), **out)
+    print("head_small ok")
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(os.cpu_count())
+    which = set(sys.argv[1:]) or {"scorer_small", "cfg1", "cfg2", "loss_small", "loss_cfg3", "head_small"}
+    if "scorer_small" in which:
+        scorer_small()
+    if "cfg1" in which:
+        scorer_cfg("cfg1", *O.cfg1_inputs())
+    if "cfg2" in which:
+        scorer_cfg("cfg2", *O.cfg2_inputs())
+    if "loss_small" in which:
+        loss_small()
+    if "loss_cfg3" in which:
+        loss_cfg3()
+    if "head_small" in which:
+        head_small()

@@ -1,0 +1,42 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA sm_100 device (run on the B200 box)")
+
+
+def pytest_collection_modifyitems(config, items):
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+def load_golden(name):
+    return dict(np.load(os.path.join(GOLDEN, name), allow_pickle=False))
+
+
+def from_bits(a: np.ndarray, shape=None) -> torch.Tensor:
+    """uint16 bit patterns -> bf16 tensor."""
+    t = torch.from_numpy(a.view(np.int16).copy()).view(torch.bfloat16)
+    return t.reshape(shape) if shape is not None else t
+
+
+def split_rows(flat: torch.Tensor, lens):
+    out, o = [], 0
+    for n in lens:
+        out.append(flat[o : o + int(n)])
+        o += int(n)
+    return out

@@ -1,0 +1,182 @@
+"""GPU parity: the fused sm_100a MaxSim kernel, called through the C ABI, against the CPU oracle, the
+reference-generated golden vectors, and size-independent properties at the full BASELINE size."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import from_bits, load_golden, split_rows
+
+import colpali_b200 as cb
+from oracle import li_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+REL_TOL = 1e-2  # north_star: MaxSim score within 1e-2 rel-tol (observed ~1e-6: fp32 accumulate of exact bf16 products)
+
+
+def rel_err(got, want):
+    return ((got - want).abs() / want.abs().clamp_min(1e-3)).max().item()
+
+
+def test_reference_unit_test_shapes_list_equals_tensor():
+    g = load_golden("scorer_small.npz")
+    q_pad, p_pad = torch.from_numpy(g["t1_q"]), torch.from_numpy(g["t1_p"])
+    qs = [q_pad[i, : int(n)] for i, n in enumerate(g["t1_qlen"])]
+    ps = [p_pad[j, : int(n)] for j, n in enumerate(g["t1_plen"])]
+    s_list = cb.score_multi_vector(qs, ps, device=DEV)
+    s_tensor = cb.score_multi_vector(q_pad, p_pad, device=DEV)
+    assert s_list.shape == (2, 3) and s_list.dtype == torch.float32 and s_list.device.type == "cpu"
+    assert torch.allclose(s_list, s_tensor)  # tests/utils/test_processing_utils.py:26-35
+    # the kernel contracts bf16: compare tightly with the oracle on bf16-rounded inputs, loosely with fp32 golden
+    want = O.score_multi_vector_port([x.bfloat16().float() for x in qs], [x.bfloat16().float() for x in ps])
+    assert torch.allclose(s_list, want, rtol=1e-5, atol=1e-4)
+    assert torch.allclose(s_list, torch.from_numpy(g["t1_list"]), rtol=2e-2, atol=0.15)
+
+
+def test_zero_padding_semantics():
+    g = load_golden("scorer_small.npz")
+    q = [torch.tensor([[1.0, 0.0]])]
+    a = torch.tensor([[-1.0, 0.0], [-0.5, 0.0]])
+    b3 = torch.tensor([[-0.2, 0.0], [-0.3, 0.0], [-0.9, 0.0]])
+    # -0.2 / -0.3 / -0.9 are not bf16-representable: the kernel contracts bf16, hence the 2e-3 slack
+    close = lambda x, y: torch.allclose(x, y, rtol=0, atol=2e-3)  # noqa: E731
+    assert close(cb.score_multi_vector(q, [a], device=DEV), torch.from_numpy(g["t2_alone"]))            # -0.5
+    assert close(cb.score_multi_vector(q, [a, b3], device=DEV), torch.from_numpy(g["t2_batched"]))       # 0.0, -0.2
+    assert cb.score_multi_vector(q, [a, b3], device=DEV)[0, 0] == 0.0  # shorter doc: zero pad row wins the max
+    assert close(cb.score_multi_vector(q, [a, b3], batch_size=1, device=DEV), torch.from_numpy(g["t2_bs1"]))
+
+
+@pytest.mark.parametrize("batch_size,key", [(128, "t3_fp32"), (3, "t3_fp32_bs3")])
+def test_ragged_against_reference_golden(batch_size, key):
+    g = load_golden("scorer_small.npz")
+    qs = split_rows(from_bits(g["t3_q"], (-1, 128)), g["t3_qlen"])  # N_q in {5,32,17,1,40}: nq_pad = 64
+    ps = split_rows(from_bits(g["t3_p"], (-1, 128)), g["t3_plen"])  # N_d in {1..1030}
+    got = cb.score_multi_vector(qs, ps, batch_size=batch_size, device=DEV)
+    want = torch.from_numpy(g[key])
+    assert rel_err(got, want) < 1e-4
+    assert torch.equal(got.argmax(1), want.argmax(1))
+
+
+def test_ragged_bf16_rounding_mode_matches_native_bf16_reference():
+    g = load_golden("scorer_small.npz")
+    qs = split_rows(from_bits(g["t3_q"], (-1, 128)), g["t3_qlen"])
+    ps = split_rows(from_bits(g["t3_p"], (-1, 128)), g["t3_plen"])
+    got = cb.score_multi_vector(qs, ps, device=DEV, round_bf16=True)
+    want = torch.from_numpy(g["t3_bf16"])
+    # identical up to one bf16 ulp (the reference rounds every dot product, we round the per-token maximum)
+    ulp = want.abs().clamp_min(1e-3) * 2.0 ** -7
+    assert ((got - want).abs() <= ulp).all()
+    assert (got == want).float().mean() > 0.9
+
+
+def test_cfg1_scores_and_argmax():
+    g = load_golden("scorer_cfg1.npz")
+    q, d = O.cfg1_inputs()
+    got = cb.score_multi_vector(q, d, device=DEV)
+    want = torch.from_numpy(g["ref_fp32"])
+    assert rel_err(got, want) < 1e-5
+    assert torch.equal(got.argmax(1), want.argmax(1))
+    assert rel_err(got, torch.from_numpy(g["ref_bf16"])) < REL_TOL
+
+
+def test_cfg2_headline_scores_argmax_and_ties():
+    """32 queries x 1000 docs x 1030 x 128 bf16 (BASELINE configs[1]) against the reference's outputs."""
+    g = load_golden("scorer_cfg2.npz")
+    q, d = O.cfg2_inputs()
+    got = cb.score_multi_vector(q, d, device=DEV)
+    ref32 = torch.from_numpy(g["ref_fp32"])
+    ref16 = torch.from_numpy(g["ref_bf16"])
+    assert got.shape == (32, 1000)
+    assert rel_err(got, ref32) < 1e-5 < REL_TOL
+    assert torch.equal(got.argmax(1), ref32.argmax(1))  # bit-exact argmax-doc agreement (fp32 reference)
+    assert rel_err(got, ref16) < REL_TOL
+    # native-bf16 reference rounds scores -> ties; our argmax must sit inside its tied-max set
+    am = got.argmax(1)
+    assert (ref16[torch.arange(32), am] == ref16.max(1).values).all()
+    # rounding mode reproduces the bf16 reference to within one bf16 ulp
+    got16 = cb.score_multi_vector(q, d, device=DEV, round_bf16=True)
+    assert ((got16 - ref16).abs() <= ref16.abs() * 2.0 ** -7).all()
+    assert (got16 == ref16).float().mean() > 0.9
+
+
+def test_full_size_properties():
+    """Size-independent checks at the full cfg2 size, no oracle needed."""
+    q, d = O.cfg2_inputs()
+    dev = torch.device(DEV)
+    qd, dd = q.to(dev), d.to(dev)
+    bank = cb.DocBank.from_passages(dd, dev)
+    base = cb.maxsim(cb.QueryBlock(qd, dev), bank)
+    # (1) permuting documents permutes columns, bit-exactly
+    perm = torch.randperm(1000, generator=torch.Generator().manual_seed(3)).to(dev)
+    s_perm = cb.maxsim(cb.QueryBlock(qd, dev), cb.DocBank.from_passages(dd[perm], dev))
+    assert torch.equal(s_perm, base[:, perm])
+    # (2) scaling queries by 2 scales scores by exactly 2 (power-of-two scaling is exact in bf16/fp32)
+    s2 = cb.maxsim(cb.QueryBlock(qd * 2, dev), bank)
+    assert torch.equal(s2, base * 2)
+    # (3) splitting a query's tokens splits its score additively
+    sa = cb.maxsim(cb.QueryBlock(qd[:, :16], dev), bank)
+    sb = cb.maxsim(cb.QueryBlock(qd[:, 16:], dev), bank)
+    assert torch.allclose(sa + sb, base, rtol=1e-6, atol=1e-5)
+    # (4) a document split in two: per-token max of the halves combines by max -> score(whole) <= sum, >= each
+    h1 = cb.maxsim(cb.QueryBlock(qd, dev), cb.DocBank.from_passages(dd[:, :515], dev))
+    h2 = cb.maxsim(cb.QueryBlock(qd, dev), cb.DocBank.from_passages(dd[:, 515:], dev))
+    assert (base >= torch.maximum(h1, h2) - 1e-5).all() and (base <= h1 + h2 + 1e-5).all()
+    # (5) query order does not matter; different query-tile grouping (R) gives identical bits
+    s_one = torch.cat([cb.maxsim(cb.QueryBlock(qd[i : i + 4], dev), bank) for i in range(0, 32, 4)])
+    assert torch.equal(s_one, base)
+    # (6) argmax variant returns the same scores and indices that reproduce them
+    s_arg, am = cb.maxsim(cb.QueryBlock(qd, dev), bank, want_argmax=True)
+    assert torch.equal(s_arg, base)
+    assert am.shape == (1000, 32 * 32) and int(am.min()) >= 0 and int(am.max()) < 1030
+    j = 123
+    sim = qd.float().reshape(-1, 128) @ dd[j].float().T  # [1024, 1030]
+    assert torch.equal(am[j].long(), sim.argmax(1))
+    assert torch.allclose(sim.gather(1, am[j].long()[:, None]).view(32, 32).sum(1), base[:, j], rtol=1e-6, atol=1e-5)
+
+
+def test_argmax_on_ragged_with_floor():
+    g = load_golden("scorer_small.npz")
+    dev = torch.device(DEV)
+    qs = [x.to(dev) for x in split_rows(from_bits(g["t3_q"], (-1, 128)), g["t3_qlen"])]
+    ps = [x.to(dev) for x in split_rows(from_bits(g["t3_p"], (-1, 128)), g["t3_plen"])]
+    bank = cb.DocBank.from_passages(ps, dev)
+    qb = cb.QueryBlock(qs, dev)
+    s, am = cb.maxsim(qb, bank, want_argmax=True)
+    assert torch.equal(s, cb.maxsim(qb, bank))
+    for j, p in enumerate(ps):
+        for i, q in enumerate(qs):
+            sim = q.float() @ p.float().T
+            mx, ix = sim.max(1)
+            rows = am[j, i * qb.nq_pad : i * qb.nq_pad + q.shape[0]].long()
+            floor_hit = rows < 0
+            assert torch.equal(floor_hit, mx <= 0) or bank.floor is None
+            assert torch.equal(rows[~floor_hit], ix[~floor_hit])
+
+
+def test_many_query_tiles_and_wide_queries():
+    dev = torch.device(DEV)
+    g = torch.Generator().manual_seed(9)
+    qs = [torch.nn.functional.normalize(torch.randn(n, 128, generator=g), dim=-1).bfloat16() for n in [70] * 7 + [96, 33]]
+    ps = [torch.nn.functional.normalize(torch.randn(n, 128, generator=g), dim=-1).bfloat16() for n in [300, 511, 513, 64, 1]]
+    got = cb.score_multi_vector(qs, ps, device=dev)
+    want = torch.from_numpy(O.maxsim_f64(qs, ps, O.reference_floors([300, 511, 513, 64, 1]))).float()
+    assert rel_err(got, want) < 1e-4
+
+
+def test_single_vector_scorer():
+    g = torch.Generator().manual_seed(2)
+    qs = [torch.randn(32, generator=g) for _ in range(4)]
+    ps = [torch.randn(32, generator=g) for _ in range(8)]
+    got = cb.score_single_vector(qs, ps, device=DEV)
+    want = torch.einsum("bd,cd->bc", torch.stack(qs).bfloat16().float(), torch.stack(ps).bfloat16().float())
+    assert got.shape == (4, 8)
+    assert torch.allclose(got.cpu(), want, rtol=1e-5, atol=1e-4)
+
+
+def test_errors():
+    with pytest.raises(ValueError, match="No queries"):
+        cb.score_multi_vector([], [torch.randn(3, 128)], device=DEV)
+    with pytest.raises(ValueError, match="No passages"):
+        cb.score_multi_vector([torch.randn(3, 128)], [], device=DEV)
+    with pytest.raises(cb.ColpaliB200Error):
+        cb.score_multi_vector([torch.randn(3, 256)], [torch.randn(3, 256)], device=DEV)
