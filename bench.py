@@ -99,6 +99,42 @@ class ClockSampler:
                 "samples": len(s)}
 
 
+def host_cores() -> int:
+    """CPU cores this process may really use: min(cpu_count, affinity, cgroup quota).  The GPU boxes show 128
+    logical CPUs but cap the container at 16 (cpu.max); oversubscribing oneDNN with 128 threads is ~80x slower."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        pass
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        pass
+    return n
+
+
+def pick_cpu_threads() -> int:
+    """Give the reference arm its best thread count: calibrate {cores, 2*cores} on a 1/16-size sample."""
+    from oracle import li_oracle as O
+
+    cores = host_cores()
+    q, d = O.cfg2_inputs(64)
+    best, best_t = cores, float("inf")
+    for t in sorted({cores, min(2 * cores, os.cpu_count() or cores)}):
+        torch.set_num_threads(t)
+        O.score_multi_vector_port(q, d)
+        t0 = time.perf_counter()
+        O.score_multi_vector_port(q, d)
+        dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = t, dt
+    return best
+
+
 def cpu_reference_arm(steps: int, warmup: int, threads: int):
     """Times the oracle port of score_multi_vector (the reference's torch.einsum CPU path,
     processing_utils.py:170-187) on the host cores.  Returns (queries/s, seconds/step, sample)."""
@@ -122,7 +158,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = pick_cpu_threads()
     steps = max(3, min(args.steps, 9))
     qps, sec, sample = cpu_reference_arm(steps, args.warmup, threads)
     line = {
@@ -131,7 +167,8 @@ def run_reference(args):
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "score_multi_vector 32q x 1000d x 1030p x 128d bf16 (BASELINE configs[1])",
                    "path": "oracle port of colpali_engine score_multi_vector (torch.einsum, CPU, batch_size=128)"},
-        "cpu_baseline": {"value": qps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": qps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "host_cores": host_cores()},
         "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -252,10 +289,10 @@ def run_b200(args):
             "clocks": clk.summary(),
         }
         if not args.no_cpu and world == 1:
-            threads = os.cpu_count() or 1
+            threads = pick_cpu_threads()
             qps, sec, sample = cpu_reference_arm(5, 1, threads)
             line["cpu_baseline"] = {"value": qps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
-                                    "seconds_per_step": sec}
+                                    "seconds_per_step": sec, "host_cores": host_cores()}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -25,6 +25,7 @@ EXPORTED_SYMBOLS = (
 )
 
 CPB_FLAG_ROUND_BF16 = 1
+CPB_FLAG_CONTIGUOUS = 2
 
 _lib: Optional[ctypes.CDLL] = None
 

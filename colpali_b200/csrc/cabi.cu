@@ -12,9 +12,9 @@
 #include "maxsim_params.h"
 
 namespace cpb {
-cudaError_t maxsim_launch(const CUtensorMap& td, const CUtensorMap& tt, const MaxSimParams& p, int r, bool argmax,
-                          int grid, cudaStream_t stream);
-int maxsim_max_clusters(int cluster);
+cudaError_t maxsim_launch(const CUtensorMap& tq, const CUtensorMap& td, const CUtensorMap& tt, const MaxSimParams& p,
+                          int r, bool argmax, int grid, cudaStream_t stream);
+int maxsim_max_clusters(int r, int cluster);
 int maxsim_tile_n();
 cudaError_t maxsim_reduce_segments(const float* partial, float* out, int64_t plane, int nseg, int round_ref,
                                    cudaStream_t stream);
@@ -182,11 +182,11 @@ int cpb_maxsim_fwd(const void* d_q, int n_queries, int nq_pad, const void* d_doc
   // not a multiple of 4, so they are opt-in.
   int cluster = (p.q_groups >= 2) ? 2 : 1;
   if (g_opt_cluster == 1 || g_opt_cluster == 2 || g_opt_cluster == 4) cluster = g_opt_cluster;
-  int max_clusters = cpb::maxsim_max_clusters(cluster);
+  int max_clusters = cpb::maxsim_max_clusters(R, cluster);
   if (max_clusters <= 0) {
     if (cluster == 1) return fail(CPB_E_CUDA, "kernel cannot be resident on this device (shared memory?)");
     cluster = 1;
-    max_clusters = cpb::maxsim_max_clusters(1);
+    max_clusters = cpb::maxsim_max_clusters(R, 1);
     if (max_clusters <= 0) return fail(CPB_E_CUDA, "kernel cannot be resident on this device (shared memory?)");
   }
   p.cluster = cluster;
@@ -198,13 +198,15 @@ int cpb_maxsim_fwd(const void* d_q, int n_queries, int nq_pad, const void* d_doc
   p.flags = flags | g_opt_debug_flags;
   const int grid = p.group_sets * p.doc_parts * cluster;
 
-  CUtensorMap td, tt;
+  CUtensorMap tq, td, tt;
+  rc = make_bf16_rowmajor_map(&tq, d_q, q_rows64, 128, 128);
+  if (rc != CPB_OK) return rc;
   rc = make_bf16_rowmajor_map(&td, d_docs, doc_rows, 128, cpb::maxsim_tile_n() / cluster);
   if (rc != CPB_OK) return rc;
   rc = make_bf16_rowmajor_map(&tt, d_docs, doc_rows, 128, 32);
   if (rc != CPB_OK) return rc;
 
-  CPB_CUDA(cpb::maxsim_launch(td, tt, p, R, d_argmax != nullptr, grid, stream));
+  CPB_CUDA(cpb::maxsim_launch(tq, td, tt, p, R, d_argmax != nullptr, grid, stream));
   if (nseg > 1)
     CPB_CUDA(cpb::maxsim_reduce_segments(d_workspace, d_scores, p.plane_stride, nseg,
                                          (flags & CPB_FLAG_ROUND_BF16) ? 1 : 0, stream));

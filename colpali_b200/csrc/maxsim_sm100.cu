@@ -11,20 +11,18 @@
 //     Query tokens sit on TMEM lanes, so max-over-document-tokens is a per-thread running
 //     FMNMX3 over accumulator columns and the sum over a query's tokens is one warp reduction
 //     (queries are padded to a multiple of 32 rows: one warp == one query segment).
-//   * One persistent CTA per SM.  A CTA keeps R (1 or 2) 128-row query tiles RESIDENT IN TENSOR MEMORY
-//     (bf16 pairs, 64 columns per tile, written once with tcgen05.st) and feeds them to the tensor core
-//     as the TMEM A operand (tcgen05.mma ... [d], [a], b_desc): only the document operand crosses the
-//     shared-memory read port.  (The first version read A from shared memory and ran at 86% of the MMA
-//     rate with TMA and epilogue switched off -- profiles/r01_notes.md.)
-//   * The CTA streams its share of the document bank through a 4-deep ring of 192-token tiles that TMA
-//     writes with the 128-byte swizzle.  Each document tile is multiplied against all R resident query
-//     tiles (tcgen05.mma 128 x N x 16, 8 K-steps) into two 192-column fp32 TMEM accumulators used as a
-//     ping-pong, so the epilogue of job j overlaps the MMAs of job j+1.
-//     TMEM columns: [0,128) query tiles, [128,320) accumulator 0, [320,512) accumulator 1.
-//   * Documents are addressed as (start row, length) in a flat [tokens, 128] bf16 bank, so ragged
-//     banks, left/right padded batches and dense [B_d, N_d, 128] tensors are all the same kernel.
-//     The last tile of a document is fetched in 32-row boxes, issued with a smaller MMA N (multiple
-//     of 16) and its unused columns are masked in the epilogue.
+//   * One persistent CTA per SM.  A CTA keeps R (1 or 2) 128-row query tiles resident in shared
+//     memory and streams its share of the document bank through a ring of 256-token tiles that
+//     TMA writes with the 128-byte swizzle.  Each document tile is multiplied against all R
+//     resident query tiles (tcgen05.mma 128 x 256 x 16, 8 K-steps) into two 256-column fp32 TMEM
+//     accumulators used as a ping-pong, so the epilogue of job j overlaps the MMAs of job j+1.
+//   * Documents are (start row, length) intervals of a flat [tokens, 128] bf16 bank, so ragged banks,
+//     left/right padded batches and dense [B_d, N_d, 128] tensors are all the same kernel.  Tiles cover
+//     the bank in 256-row steps across document boundaries: back-to-back documents form a "run" that is
+//     tiled without gaps, and the epilogue walks the document boundaries inside each accumulator tile
+//     (a measured ~22-cycle fixed cost per tcgen05.mma makes short per-document tail MMAs expensive:
+//     profiles/r01_notes.md).  Only the last tile of a run is short: it is fetched in 32-row boxes and
+//     issued with a smaller MMA N (multiple of 16).
 //   * CTAs are launched as clusters of C (1, 2 or 4): the C CTAs of a cluster hold different query tiles,
 //     walk the same document partition in lock-step and each fetches 1/C of every document tile with a
 //     TMA multicast, so a bank byte crosses the L2->SM fabric once per C*R query tiles.
@@ -41,25 +39,46 @@
 namespace cpb {
 
 constexpr int kTileM = 128;
-constexpr int kTileN = 192;
+constexpr int kTileN = 256;
 constexpr int kDim = 128;                       // embedding dim handled per pass (2 swizzle panels of 64)
-constexpr int kDTileBytes = kTileN * kDim * 2;  // 48 KiB
-constexpr int kDPanelBytes = kTileN * 64 * 2;   // 24 KiB
-constexpr int kStages = 4;
+constexpr int kQTileBytes = kTileM * kDim * 2;  // 32 KiB
+constexpr int kQPanelBytes = kTileM * 64 * 2;   // 16 KiB
+constexpr int kDTileBytes = kTileN * kDim * 2;  // 64 KiB
+constexpr int kDPanelBytes = kTileN * 64 * 2;   // 32 KiB
 constexpr int kThreads = 192;
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kTmemQCols = 64;     // one 128 x 128 bf16 query tile = 64 32-bit columns
-constexpr uint32_t kTmemAccBase = 128;  // accumulators start after two query tiles
 
+template <int R>
 struct SmemLayout {
-  static constexpr int kDOff = 0;
-  static constexpr int kBarOff = kStages * kDTileBytes;
-  // barriers: q_ready, full[S], empty[S], tmem_full[2], tmem_empty[2]
+  static constexpr int kStages = (R == 1) ? 3 : 2;
+  static constexpr int kQOff = 0;
+  static constexpr int kDOff = R * kQTileBytes;
+  static constexpr int kBarOff = kDOff + kStages * kDTileBytes;
+  // barriers: q_full, full[S], empty[S], tmem_full[2], tmem_empty[2]
   static constexpr int kNumBars = 1 + 2 * kStages + 4;
   static constexpr int kTmemPtrOff = kBarOff + kNumBars * 8;
   static constexpr int kBytes = kTmemPtrOff + 16;
   static constexpr int kAlloc = kBytes + 1024;  // slack for manual 1024-B alignment
 };
+
+// A run = documents [d, e) stored back to back in the bank, rows [row0, row1): tiled without gaps.
+// With CPB_FLAG_CONTIGUOUS the caller guarantees start[j+1] == start[j] + len[j] for the whole bank, so a
+// CTA's partition is ONE run (two loads, no scan); otherwise every document is its own run.
+struct Run {
+  int e, row0, row1;
+};
+__device__ __forceinline__ Run next_run(const MaxSimParams& p, int d, int d1) {
+  Run r;
+  r.row0 = __ldg(p.doc_start + d);
+  if (p.flags & CPB_FLAG_CONTIGUOUS) {
+    r.e = d1;
+    r.row1 = __ldg(p.doc_start + d1 - 1) + __ldg(p.doc_len + d1 - 1);
+  } else {
+    r.e = d + 1;
+    r.row1 = r.row0 + __ldg(p.doc_len + d);
+  }
+  return r;
+}
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 
@@ -79,24 +98,40 @@ __device__ __forceinline__ float max32(const uint32_t (&v)[32], float m) {
   return fmax3(x0, u3, m);
 }
 
-__device__ __forceinline__ float max32_masked(const uint32_t (&v)[32], float m, int nvalid) {
+// max of 32 accumulator columns (15 FMNMX3)
+__device__ __forceinline__ float tree32(const uint32_t (&v)[32]) {
+  float t[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    t[i] = fmax3(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]));
+  float u0 = fmax3(t[0], t[1], __uint_as_float(v[3]));
+  float u1 = fmax3(t[2], t[3], __uint_as_float(v[7]));
+  float u2 = fmax3(t[4], t[5], __uint_as_float(v[11]));
+  float u3 = fmax3(t[6], t[7], __uint_as_float(v[15]));
+  float w0 = fmax3(u0, __uint_as_float(v[19]), __uint_as_float(v[23]));
+  float w1 = fmax3(u1, __uint_as_float(v[27]), __uint_as_float(v[31]));
+  return fmax3(fmax3(w0, w1, u2), u3, u3);
+}
+
+// max over columns lo <= i < hi of a 32-column chunk
+__device__ __forceinline__ float max32_range(const uint32_t (&v)[32], float m, int lo, int hi) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) {
-    float x = (i < nvalid) ? __uint_as_float(v[i]) : -INFINITY;
+    float x = (i >= lo && i < hi) ? __uint_as_float(v[i]) : -INFINITY;
     m = fmaxf(m, x);
   }
   return m;
 }
 
-// running (value, first index) argmax over 32 columns; strict '>' keeps the earliest maximum,
-// which is what torch.max(dim) returns on ties.
-__device__ __forceinline__ void argmax32(const uint32_t (&v)[32], float& m, int& idx, int col0, int nvalid) {
+// running (value, first index) argmax over columns lo <= i < hi; strict '>' keeps the earliest maximum,
+// which is what torch.max(dim) returns on ties.  idx0 = document-relative index of column 0 of the chunk.
+__device__ __forceinline__ void argmax32_range(const uint32_t (&v)[32], float& m, int& idx, int idx0, int lo, int hi) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) {
     float x = __uint_as_float(v[i]);
-    bool take = (i < nvalid) && (x > m);
+    bool take = (i >= lo) && (i < hi) && (x > m);
     m = take ? x : m;
-    idx = take ? (col0 + i) : idx;
+    idx = take ? (idx0 + i) : idx;
   }
 }
 
@@ -110,16 +145,17 @@ __device__ __forceinline__ float warp_sum(float x) {
 
 template <int R, bool kArgmax>
 __global__ void __launch_bounds__(kThreads, 1)
-maxsim_fwd_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_tail,
-                  const MaxSimParams p) {
-  using L = SmemLayout;
-  constexpr int S = kStages;
+maxsim_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_d,
+                  const __grid_constant__ CUtensorMap tmap_tail, const MaxSimParams p) {
+  using L = SmemLayout<R>;
+  constexpr int S = L::kStages;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* q_smem = smem + L::kQOff;
   uint8_t* d_smem = smem + L::kDOff;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
-  uint64_t* q_ready = bars;
+  uint64_t* q_full = bars;
   uint64_t* full = bars + 1;
   uint64_t* empty = bars + 1 + S;
   uint64_t* tmem_full = bars + 1 + 2 * S;
@@ -144,9 +180,10 @@ maxsim_fwd_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_const
 
   // ---- one-time setup ---------------------------------------------------------------------
   if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_d);
     tma_prefetch_desc(&tmap_tail);
-    mbar_init(q_ready, 4);  // one arrive per epilogue warp once its query rows are in TMEM
+    mbar_init(q_full, 1);
     for (int s = 0; s < S; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], static_cast<uint32_t>(C));  // every CTA of the cluster releases the slot
@@ -171,22 +208,28 @@ maxsim_fwd_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_const
   if (warp == 0) {
     // ================================ TMA producer ==========================================
     if (lane == 0) {
+      if (r_cnt > 0) {
+        mbar_expect_tx(q_full, static_cast<uint32_t>(r_cnt) * kQTileBytes);
+        for (int r = 0; r < r_cnt; ++r) {
+          const int row = (g * R + r) * kTileM;
+          tma_load_2d(q_smem + r * kQTileBytes, &tmap_q, 0, row, q_full);
+          tma_load_2d(q_smem + r * kQTileBytes + kQPanelBytes, &tmap_q, 64, row, q_full);
+        }
+      }
       const int rows_per_cta = kTileN / C;
       int stage = 0;
       uint32_t phase = 0;
-      for (int d = d0; d < d1; ++d) {
-        const int start = __ldg(p.doc_start + d);
-        const int len = __ldg(p.doc_len + d);
-        const int nch = max(1, (len + kTileN - 1) / kTileN);
-        for (int c = 0; c < nch; ++c) {
-          const int n_valid = min(kTileN, len - c * kTileN);
+      for (int d = d0; d < d1;) {
+        const Run run = next_run(p, d, d1);
+        d = run.e;
+        for (int row = run.row0; row < run.row1; row += kTileN) {
+          const int n_valid = min(kTileN, run.row1 - row);
           mbar_wait(&empty[stage], phase ^ 1u);
           uint8_t* dst = d_smem + stage * kDTileBytes;
-          const int row = start + c * kTileN;
           if (p.flags & CPB_DBG_NO_TMA) {
             mbar_arrive(&full[stage]);
           } else if (n_valid == kTileN) {
-            // full tile: this CTA fetches rows [crank*192/C, (crank+1)*192/C) for the whole cluster
+            // full tile: this CTA fetches rows [crank*256/C, (crank+1)*256/C) for the whole cluster
             mbar_expect_tx(&full[stage], kDTileBytes);
             const int r0 = static_cast<int>(crank) * rows_per_cta;
             if (C > 1) {
@@ -197,8 +240,8 @@ maxsim_fwd_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_const
               tma_load_2d(dst + kDPanelBytes, &tmap_d, 64, row, &full[stage]);
             }
           } else {
-            // tail of a document: 32-row boxes, fetched by rank 0 only
-            const int nbox = max(1, (n_valid + 31) >> 5);
+            // last tile of a run: 32-row boxes, fetched by rank 0 only
+            const int nbox = (n_valid + 31) >> 5;
             mbar_expect_tx(&full[stage], static_cast<uint32_t>(nbox) * 32u * 256u);
             if (crank == 0) {
               for (int b = 0; b < nbox; ++b) {
@@ -222,34 +265,42 @@ maxsim_fwd_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_const
   } else if (warp == 1) {
     // ================================ MMA issuer ============================================
     if (lane == 0) {
-      mbar_wait(q_ready, 0);  // query tiles are in TMEM
+      if (r_cnt > 0) mbar_wait(q_full, 0);
       tc_fence_after();
+      const uint32_t q_addr = smem_u32(q_smem);
       const uint32_t d_addr = smem_u32(d_smem);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t job = 0;
-      for (int d = d0; d < d1; ++d) {
-        const int len = __ldg(p.doc_len + d);
-        const int nch = max(1, (len + kTileN - 1) / kTileN);
-        for (int c = 0; c < nch; ++c) {
-          const int n_valid = min(kTileN, len - c * kTileN);
-          const uint32_t n_mma = static_cast<uint32_t>(max(16, (n_valid + 15) & ~15));
+      const bool dbg = (p.flags & CPB_DBG_CLOCKS) != 0;
+      long long w_full = 0, w_tmem = 0;
+      for (int d = d0; d < d1;) {
+        const Run run = next_run(p, d, d1);
+        d = run.e;
+        for (int row = run.row0; row < run.row1; row += kTileN) {
+          const int n_valid = min(kTileN, run.row1 - row);
+          const uint32_t n_mma = static_cast<uint32_t>((n_valid + 15) & ~15);
           const uint32_t idesc = make_idesc_bf16_f32(kTileM, n_mma);
+          long long t0 = dbg ? clock64() : 0;
           mbar_wait(&full[stage], phase);
+          if (dbg) w_full += clock64() - t0;
           tc_fence_after();
           for (int r = 0; r < r_cnt; ++r) {
             const uint32_t a = job & 1u;
             const uint32_t aphase = (job >> 1) & 1u;
+            t0 = dbg ? clock64() : 0;
             mbar_wait(&tmem_empty[a], aphase ^ 1u);
+            if (dbg) w_tmem += clock64() - t0;
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + kTmemAccBase + a * kTileN;
-            const uint32_t a_tmem = tmem_base + r * kTmemQCols;
+            const uint32_t d_tmem = tmem_base + a * kTileN;
 #pragma unroll
             for (int k = 0; k < kDim / 16; ++k) {
               const int kp = k >> 2, kk = k & 3;
+              const uint64_t adesc =
+                  make_sw128_kmajor_desc(q_addr + r * kQTileBytes + kp * kQPanelBytes) + static_cast<uint64_t>(kk * 2);
               const uint64_t bdesc =
                   make_sw128_kmajor_desc(d_addr + stage * kDTileBytes + kp * kDPanelBytes) + static_cast<uint64_t>(kk * 2);
-              umma_bf16_ts(d_tmem, a_tmem + k * 8, bdesc, idesc, k > 0 ? 1u : 0u);
+              umma_bf16(d_tmem, adesc, bdesc, idesc, k > 0 ? 1u : 0u);
             }
             umma_commit(&tmem_full[a]);
             ++job;
@@ -262,117 +313,244 @@ maxsim_fwd_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_const
           }
         }
       }
+      if (dbg) {  // cycles the issuer spent blocked on TMA data / on the epilogue
+        p.scores[512 + 8 * blockIdx.x + 0] = static_cast<float>(w_full);
+        p.scores[512 + 8 * blockIdx.x + 1] = static_cast<float>(w_tmem);
+      }
     }
   } else {
     // ================================ epilogue ==============================================
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may read
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
+    const bool round_ref = (p.flags & CPB_FLAG_ROUND_BF16) != 0;
+    const bool skip = (p.flags & CPB_DBG_SKIP_EPILOGUE) != 0;
 
-    // ---- stage the resident query tiles: global -> registers -> TMEM (row = lane, 2 bf16 per column)
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      if (r < r_cnt) {
-        const int row = (g * R + r) * kTileM + quad * 32 + lane;
-        const uint4* src = reinterpret_cast<const uint4*>(p.q) + static_cast<int64_t>(row) * (kDim * 2 / 16);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t v[32];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            uint4 x = (row < p.q_rows) ? __ldg(src + h * 8 + i) : make_uint4(0u, 0u, 0u, 0u);
-            v[4 * i] = x.x;
-            v[4 * i + 1] = x.y;
-            v[4 * i + 2] = x.z;
-            v[4 * i + 3] = x.w;
-          }
-          tmem_st_x32(tmem_base + lane_base + r * kTmemQCols + h * 32, v);
-        }
-      }
-    }
-    tmem_st_wait();
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(q_ready);
+    // document `doc` is complete for resident query tile r: fold this query segment's 32 token maxima
+    auto finalize = [&](int doc, int r, float mm, int ai) {
+      const int row0 = (g * R + r) * kTileM + quad * 32;  // first padded query row of this warp
+      const int q = row0 / p.nq_pad;
+      const int seg = (row0 % p.nq_pad) >> 5;
+      if (kArgmax && p.argmax != nullptr && row0 + lane < p.q_rows)
+        p.argmax[static_cast<int64_t>(doc) * p.q_rows + row0 + lane] = ai;
+      float x = round_ref ? round_bf16(mm) : mm;
+      x = warp_sum(x);
+      if (round_ref && p.nq_pad == 32) x = round_bf16(x);
+      if (lane == 0 && q < p.n_queries && !(p.flags & CPB_DBG_CLOCKS))
+        p.scores[static_cast<int64_t>(seg) * p.plane_stride + static_cast<int64_t>(q) * p.n_docs + doc] = x;
+    };
+    auto doc_init = [&](int doc) { return (p.doc_floor != nullptr) ? __ldg(p.doc_floor + doc) : -INFINITY; };
 
     float m[R];
     int am[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      m[r] = -INFINITY;
-      am[r] = -1;
-    }
-    const bool round_ref = (p.flags & CPB_FLAG_ROUND_BF16) != 0;
     uint32_t job = 0;
-    for (int d = d0; d < d1; ++d) {
-      const int len = __ldg(p.doc_len + d);
-      const int nch = max(1, (len + kTileN - 1) / kTileN);
-      const float init = (p.doc_floor != nullptr) ? __ldg(p.doc_floor + d) : -INFINITY;
-      for (int c = 0; c < nch; ++c) {
-        const int n_valid = min(kTileN, len - c * kTileN);
+    const bool dbg = (p.flags & CPB_DBG_CLOCKS) != 0;
+    long long e_wait = 0, e_hold = 0, e_post = 0, e_hold2 = 0;
+    int n_path2 = 0;
+    for (int d = d0; d < d1;) {
+      const Run run = next_run(p, d, d1);
+      if (run.row1 == run.row0) {
+        // nothing but empty documents: their score is the sum of the floors
+        for (int e = d; e < run.e; ++e)
+          for (int r = 0; r < r_cnt; ++r) finalize(e, r, doc_init(e), -1);
+        d = run.e;
+        continue;
+      }
+      // state at the start of each tile: current document, its first/last bank row, running maxima
+      int cur = d;
+      int cur_row0 = run.row0;
+      int cur_end = cur_row0 + __ldg(p.doc_len + cur);
+      {
+        const float init = doc_init(cur);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          m[r] = init;
+          am[r] = -1;
+        }
+      }
+      for (int row = run.row0; row < run.row1; row += kTileN) {
+        const int n_valid = min(kTileN, run.row1 - row);
+        const int tile_end = row + n_valid;
+        int nxt = cur, nxt_row0 = cur_row0, nxt_end = cur_end;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           if (r < r_cnt) {
             const uint32_t a = job & 1u;
             const uint32_t aphase = (job >> 1) & 1u;
+            const long long t0 = dbg ? clock64() : 0;
             mbar_wait(&tmem_full[a], aphase);
+            const long long t1 = dbg ? clock64() : 0;
+            long long t2 = 0;
             tc_fence_after();
-            const uint32_t taddr = tmem_base + lane_base + kTmemAccBase + a * kTileN;
-            float mm = (c == 0) ? init : m[r];
-            int ai = (c == 0) ? -1 : am[r];
-            if (p.flags & CPB_DBG_SKIP_EPILOGUE) {
-              // profiling aid: leave the accumulator unread (results are garbage)
-            } else if constexpr (!kArgmax) {
-              if (n_valid == kTileN) {
-#pragma unroll
-                for (int cc = 0; cc < kTileN / 64; ++cc) {
-                  uint32_t v0[32], v1[32];
-                  tmem_ld_x32(taddr + cc * 64, v0);
-                  tmem_ld_x32(taddr + cc * 64 + 32, v1);
-                  tmem_ld_wait();
-                  mm = max32(v0, mm);
-                  mm = max32(v1, mm);
-                }
-              } else {
-                for (int col = 0; col < n_valid; col += 32) {
-                  uint32_t v[32];
-                  tmem_ld_x32(taddr + col, v);
-                  tmem_ld_wait();
-                  const int nv = n_valid - col;
-                  mm = (nv >= 32) ? max32(v, mm) : max32_masked(v, mm, nv);
-                }
+            const uint32_t taddr = tmem_base + lane_base + a * kTileN;
+            float mm = m[r];
+            int ai = am[r];
+            int doc = cur, doc_row0 = cur_row0, doc_end = cur_end;
+
+            // the current document is complete: emit it and step to the next one of the run
+            auto finish_doc = [&]() {
+              finalize(doc, r, mm, ai);
+              ++doc;
+              if (doc >= run.e) {
+                doc_end = 0x7fffffff;  // run exhausted
+                return;
               }
-            } else {
-              for (int col = 0; col < n_valid; col += 32) {
-                uint32_t v[32];
-                tmem_ld_x32(taddr + col, v);
-                tmem_ld_wait();
-                argmax32(v, mm, ai, c * kTileN + col, n_valid - col);
+              doc_row0 = doc_end;
+              doc_end = doc_row0 + __ldg(p.doc_len + doc);
+              mm = doc_init(doc);
+              ai = -1;
+            };
+            auto release_acc = [&]() {  // accumulator drained: hand the TMEM stage back to the MMA warp
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tmem_empty[a]);
+              if (dbg) t2 = clock64();
+            };
+
+            // Three warp-uniform cases.  (1) the whole 256-column tile belongs to one document: FMNMX3 trees.
+            // (2) exactly one document boundary inside a full tile: the same trees, routed to the old or the
+            // new document per 32-column chunk, plus one masked pass over the chunk that holds the boundary.
+            // (3) anything else (short documents, last tile of a run, argmax): generic masked walk.
+            int path = 3;
+            int next_len = 0;
+            if (!kArgmax && n_valid == kTileN) {
+              if (doc_end >= tile_end) {
+                path = 1;
+              } else if (doc_end > row && doc + 1 < run.e) {
+                next_len = __ldg(p.doc_len + doc + 1);
+                if (doc_end + next_len >= tile_end) path = 2;
               }
             }
-            // accumulator drained: hand the TMEM stage back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[a]);
+            if (skip) {
+              release_acc();
+              while (doc_end <= tile_end) {  // advance the cursor without reading the accumulator
+                ++doc;
+                if (doc >= run.e) { doc_end = 0x7fffffff; break; }
+                doc_row0 = doc_end;
+                doc_end = doc_row0 + __ldg(p.doc_len + doc);
+              }
+            } else if (path == 1) {
+              // software pipeline: the loads of columns [64k+64, 64k+128) are in flight while [64k, 64k+64) fold
+              uint32_t va[32], vb[32], vc[32], vd[32];
+              tmem_ld_x32(taddr, va);
+              tmem_ld_x32(taddr + 32, vb);
+              tmem_ld_wait();
+              reg_fence32(va);
+              reg_fence32(vb);
+              tmem_ld_x32(taddr + 64, vc);
+              tmem_ld_x32(taddr + 96, vd);
+              mm = max32(va, mm);
+              mm = max32(vb, mm);
+              tmem_ld_wait();
+              reg_fence32(vc);
+              reg_fence32(vd);
+              tmem_ld_x32(taddr + 128, va);
+              tmem_ld_x32(taddr + 160, vb);
+              mm = max32(vc, mm);
+              mm = max32(vd, mm);
+              tmem_ld_wait();
+              reg_fence32(va);
+              reg_fence32(vb);
+              tmem_ld_x32(taddr + 192, vc);
+              tmem_ld_x32(taddr + 224, vd);
+              mm = max32(va, mm);
+              mm = max32(vb, mm);
+              tmem_ld_wait();
+              reg_fence32(vc);
+              reg_fence32(vd);
+              // all accumulator reads have landed in registers: release before the last fold
+              release_acc();
+              mm = max32(vc, mm);
+              mm = max32(vd, mm);
+              while (doc_end <= tile_end) finish_doc();  // document (and empty followers) ending at the tile end
+            } else if (path == 2) {
+              const int b = doc_end - row;  // first column of the next document, 0 < b < 256
+              const int kb = b >> 5;
+              float ma = mm, mb = doc_init(doc + 1);
+#pragma unroll
+              for (int cc = 0; cc < kTileN / 64; ++cc) {
+                uint32_t v0[32], v1[32];
+                tmem_ld_x32(taddr + cc * 64, v0);
+                tmem_ld_x32(taddr + cc * 64 + 32, v1);
+                tmem_ld_wait();
+                reg_fence32(v0);
+                reg_fence32(v1);
+                const float t0 = tree32(v0), t1 = tree32(v1);
+                ma = (2 * cc < kb) ? fmaxf(ma, t0) : ma;
+                mb = (2 * cc > kb) ? fmaxf(mb, t0) : mb;
+                ma = (2 * cc + 1 < kb) ? fmaxf(ma, t1) : ma;
+                mb = (2 * cc + 1 > kb) ? fmaxf(mb, t1) : mb;
+              }
+              {
+                uint32_t v[32];
+                tmem_ld_x32(taddr + kb * 32, v);
+                tmem_ld_wait();
+                reg_fence32(v);
+                release_acc();
+                const int bl = b & 31;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                  const float x = __uint_as_float(v[i]);
+                  if (i < bl) ma = fmaxf(ma, x); else mb = fmaxf(mb, x);
+                }
+              }
+              mm = ma;
+              finish_doc();  // old document; cursor moves to the new one (its running max is mb)
+              mm = mb;
+              while (doc_end <= tile_end) finish_doc();
+            } else {
+#pragma unroll 1
+              for (int cb = 0; cb < n_valid; cb += 32) {
+                uint32_t v[32];
+                tmem_ld_x32(taddr + cb, v);
+                tmem_ld_wait();
+                reg_fence32(v);
+                const int abs0 = row + cb;
+                const int abs1 = min(abs0 + 32, tile_end);
+                int pos = abs0;
+                while (true) {
+                  const int seg_end = min(doc_end, abs1);
+                  if (seg_end > pos) {
+                    if constexpr (kArgmax) {
+                      argmax32_range(v, mm, ai, abs0 - doc_row0, pos - abs0, seg_end - abs0);
+                    } else {
+                      mm = max32_range(v, mm, pos - abs0, seg_end - abs0);
+                    }
+                  }
+                  pos = seg_end;
+                  if (doc_end > abs1) break;  // the current document continues past this chunk
+                  finish_doc();
+                }
+              }
+              release_acc();
+            }
+            if (dbg) {
+              const long long t3 = clock64();
+              e_wait += t1 - t0;
+              e_post += t3 - t2;
+              if (path == 2) { e_hold2 += t2 - t1; ++n_path2; } else { e_hold += t2 - t1; }
+            }
             m[r] = mm;
             am[r] = ai;
-
-            if (c == nch - 1) {
-              // document finished: fold this query segment's 32 token maxima into one score
-              const int row0 = (g * R + r) * kTileM + quad * 32;  // first padded query row of this warp
-              const int q = row0 / p.nq_pad;
-              const int seg = (row0 % p.nq_pad) >> 5;
-              if (kArgmax && p.argmax != nullptr && row0 + lane < p.q_rows)
-                p.argmax[static_cast<int64_t>(d) * p.q_rows + row0 + lane] = ai;
-              float x = round_ref ? round_bf16(mm) : mm;
-              x = warp_sum(x);
-              if (round_ref && p.nq_pad == 32) x = round_bf16(x);
-              if (lane == 0 && q < p.n_queries)
-                p.scores[static_cast<int64_t>(seg) * p.plane_stride + static_cast<int64_t>(q) * p.n_docs + d] = x;
-            }
+            nxt = doc;
+            nxt_row0 = doc_row0;
+            nxt_end = doc_end;
             ++job;
           }
         }
+        cur = nxt;
+        cur_row0 = nxt_row0;
+        cur_end = nxt_end;
       }
+      d = run.e;
+    }
+    if (dbg && warp == 2 && lane == 0) {  // epilogue: blocked on MMA / holding the accumulator / after release
+      float* o = p.scores + 512 + 8 * blockIdx.x;
+      o[2] = static_cast<float>(e_wait);
+      o[3] = static_cast<float>(e_hold);
+      o[4] = static_cast<float>(e_post);
+      o[5] = static_cast<float>(e_hold2);
+      o[6] = static_cast<float>(n_path2);
+      o[7] = static_cast<float>(job);
     }
   }
 
@@ -400,11 +578,12 @@ __global__ void maxsim_reduce_segments_kernel(const float* __restrict__ partial,
   out[i] = round_ref ? round_bf16(s) : s;
 }
 
+template <int R>
 static void fill_cluster_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int grid, int cluster,
                              cudaStream_t stream) {
   cfg.gridDim = dim3(static_cast<unsigned>(grid));
   cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = SmemLayout::kAlloc;
+  cfg.dynamicSmemBytes = SmemLayout<R>::kAlloc;
   cfg.stream = stream;
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = static_cast<unsigned>(cluster);
@@ -415,34 +594,41 @@ static void fill_cluster_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr,
 }
 
 template <int R, bool kArgmax>
-static cudaError_t launch_variant(const CUtensorMap& td, const CUtensorMap& tt, const MaxSimParams& p, int grid,
-                                  cudaStream_t stream) {
+static cudaError_t launch_variant(const CUtensorMap& tq, const CUtensorMap& td, const CUtensorMap& tt,
+                                  const MaxSimParams& p, int grid, cudaStream_t stream) {
   auto kern = maxsim_fwd_kernel<R, kArgmax>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout::kAlloc);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<R>::kAlloc);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg{};
   cudaLaunchAttribute attr[1];
-  fill_cluster_cfg(cfg, attr, grid, p.cluster, stream);
-  return cudaLaunchKernelEx(&cfg, kern, td, tt, p);
+  fill_cluster_cfg<R>(cfg, attr, grid, p.cluster, stream);
+  return cudaLaunchKernelEx(&cfg, kern, tq, td, tt, p);
 }
 
-cudaError_t maxsim_launch(const CUtensorMap& td, const CUtensorMap& tt, const MaxSimParams& p, int r, bool argmax,
-                          int grid, cudaStream_t stream) {
+cudaError_t maxsim_launch(const CUtensorMap& tq, const CUtensorMap& td, const CUtensorMap& tt, const MaxSimParams& p,
+                          int r, bool argmax, int grid, cudaStream_t stream) {
   if (r == 1)
-    return argmax ? launch_variant<1, true>(td, tt, p, grid, stream) : launch_variant<1, false>(td, tt, p, grid, stream);
-  return argmax ? launch_variant<2, true>(td, tt, p, grid, stream) : launch_variant<2, false>(td, tt, p, grid, stream);
+    return argmax ? launch_variant<1, true>(tq, td, tt, p, grid, stream)
+                  : launch_variant<1, false>(tq, td, tt, p, grid, stream);
+  return argmax ? launch_variant<2, true>(tq, td, tt, p, grid, stream)
+                : launch_variant<2, false>(tq, td, tt, p, grid, stream);
 }
 
 // How many clusters of `cluster` CTAs can be co-resident (persistent-grid sizing).
-int maxsim_max_clusters(int cluster) {
-  auto kern = maxsim_fwd_kernel<2, false>;
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout::kAlloc) != cudaSuccess) return 0;
+template <int R>
+static int max_clusters_variant(int cluster) {
+  auto kern = maxsim_fwd_kernel<R, false>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<R>::kAlloc) != cudaSuccess)
+    return 0;
   cudaLaunchConfig_t cfg{};
   cudaLaunchAttribute attr[1];
-  fill_cluster_cfg(cfg, attr, cluster, cluster, nullptr);
+  fill_cluster_cfg<R>(cfg, attr, cluster, cluster, nullptr);
   int n = 0;
   if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) return 0;
   return n;
+}
+int maxsim_max_clusters(int r, int cluster) {
+  return r == 1 ? max_clusters_variant<1>(cluster) : max_clusters_variant<2>(cluster);
 }
 
 int maxsim_tile_n() { return kTileN; }

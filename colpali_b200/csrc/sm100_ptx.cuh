@@ -235,6 +235,18 @@ __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// tcgen05.ld is asynchronous: its destination registers are valid only after tcgen05.wait::ld.  The wait
+// has no register operands, so nothing stops the compiler from scheduling a consumer of `r` above it.
+// This empty asm "rewrites" the 32 registers after the wait and thereby pins every consumer below it.
+__device__ __forceinline__ void reg_fence32(uint32_t (&r)[32]) {
+  asm volatile(""
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]),
+                 "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]),
+                 "+r"(r[30]), "+r"(r[31]));
+}
+
 // registers -> TMEM, 32 lanes x 32 consecutive 32-bit columns (thread i writes lane lane_base + i)
 __device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(

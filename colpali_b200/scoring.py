@@ -95,8 +95,9 @@ class DocBank:
     """
 
     def __init__(self, flat: torch.Tensor, start: torch.Tensor, length: torch.Tensor,
-                 floor: Optional[torch.Tensor]):
+                 floor: Optional[torch.Tensor], contiguous: bool = False):
         self.flat, self.start, self.length, self.floor = flat, start, length, floor
+        self.contiguous = contiguous  # documents stored back to back (start[j+1] == start[j] + len[j])
         self.n_docs = int(start.numel())
         self.device = flat.device
 
@@ -113,7 +114,7 @@ class DocBank:
             flat = _pad_dim(ps.to(device, non_blocking=True)).reshape(n * L, EMBED_DIM).contiguous()
             start = torch.arange(0, n * L, L, dtype=torch.int32, device=device)
             length = torch.full((n,), L, dtype=torch.int32, device=device)
-            return DocBank(flat, start, length, None)  # equal lengths: the reference pads nothing
+            return DocBank(flat, start, length, None, contiguous=True)  # equal lengths: the reference pads nothing
         lens = [int(p.shape[0]) for p in ps]
         n = len(ps)
         # one pass over the bank: device-side cat of the per-document uploads
@@ -134,7 +135,7 @@ class DocBank:
                     any_pad = True
                     fl[j : j + batch_size][padded] = 0.0
             floor = fl.to(device) if any_pad else None
-        return DocBank(flat, start, length, floor)
+        return DocBank(flat, start, length, floor, contiguous=True)
 
 
 def maxsim(q: QueryBlock, bank: DocBank, *, round_bf16: bool = False, want_argmax: bool = False):
@@ -146,7 +147,7 @@ def maxsim(q: QueryBlock, bank: DocBank, *, round_bf16: bool = False, want_argma
     argmax = torch.empty(bank.n_docs, q.n * q.nq_pad, dtype=torch.int32, device=dev) if want_argmax else None
     ws_bytes = lib.cpb_maxsim_workspace_bytes(q.n, q.nq_pad, bank.n_docs)
     ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev) if ws_bytes else None
-    flags = _lib.CPB_FLAG_ROUND_BF16 if round_bf16 else 0
+    flags = (_lib.CPB_FLAG_ROUND_BF16 if round_bf16 else 0) | (_lib.CPB_FLAG_CONTIGUOUS if bank.contiguous else 0)
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
         rc = lib.cpb_maxsim_fwd(
