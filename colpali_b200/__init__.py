@@ -2,12 +2,17 @@
 
 Public names mirror the reference (illuin-tech/colpali):
   score_multi_vector / score_single_vector   <- BaseVisualRetrieverProcessor (utils/processing_utils.py)
+  ColbertLoss / ColbertPairwiseCELoss        <- colpali_engine.loss (loss/late_interaction_losses.py)
 """
 
 from ._lib import ColpaliB200Error
+from .losses import ColbertLoss, ColbertModule, ColbertPairwiseCELoss
 from .scoring import DocBank, QueryBlock, maxsim, score_multi_vector, score_single_vector
 
 __all__ = [
+    "ColbertLoss",
+    "ColbertModule",
+    "ColbertPairwiseCELoss",
     "ColpaliB200Error",
     "DocBank",
     "QueryBlock",

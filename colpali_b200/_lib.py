@@ -22,10 +22,14 @@ EXPORTED_SYMBOLS = (
     "cpb_set_option",
     "cpb_maxsim_fwd",
     "cpb_maxsim_workspace_bytes",
+    "cpb_colbert_loss_fwd",
+    "cpb_maxsim_bwd",
 )
 
 CPB_FLAG_ROUND_BF16 = 1
 CPB_FLAG_CONTIGUOUS = 2
+CPB_LOSS_CE = 0
+CPB_LOSS_PAIRWISE = 1
 
 _lib: Optional[ctypes.CDLL] = None
 
@@ -64,6 +68,20 @@ def load() -> ctypes.CDLL:
         c_vp, c_vp, c_vp, c_i,  # d_doc_start, d_doc_len, d_doc_floor, n_docs
         c_vp, c_vp, c_vp,  # d_scores, d_argmax, d_workspace
         c_u32, c_vp,  # flags, stream
+    ]
+    c_f = ctypes.c_float
+    lib.cpb_colbert_loss_fwd.restype = c_i
+    lib.cpb_colbert_loss_fwd.argtypes = [
+        c_vp, c_vp, c_i, c_i, c_i, c_i,  # d_scores, d_q, n_queries, nq_pad, n_docs, mode
+        c_f, c_i, c_i, c_f, c_f, c_i,  # temperature, normalize, filter, threshold, factor, offset
+        c_vp, c_vp, c_vp, c_vp,  # d_loss, d_grad_scores, d_bounds, stream
+    ]
+    lib.cpb_maxsim_bwd.restype = c_i
+    lib.cpb_maxsim_bwd.argtypes = [
+        c_vp, c_vp, c_vp,  # d_grad_scores, d_grad_out, d_argmax
+        c_vp, c_i, c_i,  # d_q, n_queries, nq_pad
+        c_vp, c_i64, c_vp, c_i,  # d_docs, doc_rows, d_doc_start, n_docs
+        c_vp, c_vp, c_vp,  # d_dq, d_dd, stream
     ]
     _lib = lib
     return lib

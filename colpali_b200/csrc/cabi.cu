@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/colpali_b200.h"
+#include "loss_params.h"
 #include "maxsim_params.h"
 
 namespace cpb {
@@ -210,6 +211,64 @@ int cpb_maxsim_fwd(const void* d_q, int n_queries, int nq_pad, const void* d_doc
   if (nseg > 1)
     CPB_CUDA(cpb::maxsim_reduce_segments(d_workspace, d_scores, p.plane_stride, nseg,
                                          (flags & CPB_FLAG_ROUND_BF16) ? 1 : 0, stream));
+  return CPB_OK;
+}
+
+int cpb_colbert_loss_fwd(const float* d_scores, const void* d_q, int n_queries, int nq_pad, int n_docs, int mode,
+                         float temperature, int normalize_scores, int pos_aware_negative_filtering,
+                         float filter_threshold, float filter_factor, int offset, float* d_loss, float* d_grad_scores,
+                         float* d_bounds, void* stream_) {
+  if (n_queries <= 0 || n_docs <= 0) return fail(CPB_E_INVALID, "n_queries=%d and n_docs=%d must be positive", n_queries, n_docs);
+  if (nq_pad <= 0 || (nq_pad % 32) != 0) return fail(CPB_E_INVALID, "nq_pad=%d must be a positive multiple of 32", nq_pad);
+  if (mode != CPB_LOSS_CE && mode != CPB_LOSS_PAIRWISE) return fail(CPB_E_INVALID, "unknown loss mode %d", mode);
+  if (offset < 0 || offset + n_queries > n_docs)
+    return fail(CPB_E_INVALID, "positive index out of range: offset=%d + n_queries=%d > n_docs=%d", offset, n_queries, n_docs);
+  if (!(temperature > 0.f)) return fail(CPB_E_INVALID, "temperature must be positive");
+  if (!d_scores || !d_q || !d_loss) return fail(CPB_E_INVALID, "null device pointer");
+  cpb::LossParams p{};
+  p.scores = d_scores;
+  p.q = static_cast<const __nv_bfloat16*>(d_q);
+  p.loss = d_loss;
+  p.grad = d_grad_scores;
+  p.bounds = d_bounds;
+  p.B = n_queries;
+  p.C = n_docs;
+  p.nq_pad = nq_pad;
+  p.offset = offset;
+  p.mode = mode;
+  p.normalize = normalize_scores;
+  p.filter = pos_aware_negative_filtering;
+  p.temperature = temperature;
+  p.filter_threshold = filter_threshold;
+  p.filter_factor = filter_factor;
+  CPB_CUDA(cpb::colbert_loss_launch(p, static_cast<cudaStream_t>(stream_)));
+  return CPB_OK;
+}
+
+int cpb_maxsim_bwd(const float* d_grad_scores, const float* d_grad_out, const int32_t* d_argmax, const void* d_q,
+                   int n_queries, int nq_pad, const void* d_docs, int64_t doc_rows, const int32_t* d_doc_start,
+                   int n_docs, float* d_dq, float* d_dd, void* stream_) {
+  if (n_queries <= 0 || n_docs <= 0) return fail(CPB_E_INVALID, "n_queries=%d and n_docs=%d must be positive", n_queries, n_docs);
+  if (nq_pad <= 0 || (nq_pad % 32) != 0) return fail(CPB_E_INVALID, "nq_pad=%d must be a positive multiple of 32", nq_pad);
+  if (!d_grad_scores || !d_argmax || !d_q || !d_docs || !d_doc_start) return fail(CPB_E_INVALID, "null device pointer");
+  if (doc_rows <= 0) return fail(CPB_E_INVALID, "doc_rows must be positive");
+  if ((reinterpret_cast<uintptr_t>(d_dq) | reinterpret_cast<uintptr_t>(d_dd) | reinterpret_cast<uintptr_t>(d_q) |
+       reinterpret_cast<uintptr_t>(d_docs)) & 15u)
+    return fail(CPB_E_INVALID, "tensor pointers must be 16-byte aligned");
+  cpb::BwdParams p{};
+  p.g = d_grad_scores;
+  p.grad_out = d_grad_out;
+  p.argmax = d_argmax;
+  p.q = static_cast<const __nv_bfloat16*>(d_q);
+  p.docs = static_cast<const __nv_bfloat16*>(d_docs);
+  p.doc_start = d_doc_start;
+  p.dq = d_dq;
+  p.dd = d_dd;
+  p.B = n_queries;
+  p.C = n_docs;
+  p.nq_pad = nq_pad;
+  p.q_rows = n_queries * nq_pad;
+  CPB_CUDA(cpb::maxsim_bwd_launch(p, static_cast<cudaStream_t>(stream_)));
   return CPB_OK;
 }
 

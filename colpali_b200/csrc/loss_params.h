@@ -1,0 +1,36 @@
+// Parameter blocks of the loss / backward kernels (loss_sm100.cu), filled by cabi.cu.
+#pragma once
+#include <cstdint>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace cpb {
+
+struct LossParams {
+  const float* scores;        // [B, C] raw sums of per-token maxima
+  const __nv_bfloat16* q;     // [B * nq_pad, 128] padded queries (lengths are counted from column 0)
+  float* loss;                // [1]
+  float* grad;                // [B, C] dLoss/dScores (raw), or nullptr
+  float* bounds;              // [2] min / max of the normalised scores, or nullptr
+  int B, C, nq_pad, offset;
+  int mode;                   // 0 = cross entropy (ColbertLoss), 1 = pairwise softplus (ColbertPairwiseCELoss)
+  int normalize, filter;
+  float temperature, filter_threshold, filter_factor;
+};
+
+struct BwdParams {
+  const float* g;             // [B, C]
+  const float* grad_out;      // scalar upstream gradient, or nullptr (= 1)
+  const int32_t* argmax;      // [C, q_rows] document-relative token index, -1 = floor (no gradient)
+  const __nv_bfloat16* q;     // [q_rows, 128]
+  const __nv_bfloat16* docs;  // [doc_rows, 128]
+  const int32_t* doc_start;   // [C]
+  float* dq;                  // [q_rows, 128]
+  float* dd;                  // [doc_rows, 128], pre-zeroed
+  int B, C, nq_pad, q_rows;
+};
+
+cudaError_t colbert_loss_launch(const LossParams& p, cudaStream_t stream);
+cudaError_t maxsim_bwd_launch(const BwdParams& p, cudaStream_t stream);
+
+}  // namespace cpb

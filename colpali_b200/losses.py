@@ -1,0 +1,188 @@
+"""ColBERT in-batch-negative losses on B200 behind the reference's loss-module API.
+
+Mirrors ``colpali_engine/loss/late_interaction_losses.py`` (reference @ 9be8f19):
+
+* ``ColbertModule``           :6-107   (hyper-parameters + the small helper methods, kept for API parity)
+* ``ColbertLoss``             :110-164 (InfoNCE over in-batch documents)
+* ``ColbertPairwiseCELoss``   :255-313 (softplus(hardest in-batch negative - positive))
+
+Same constructor keyword arguments, same ``forward(query_embeddings, doc_embeddings, offset=0)``.  The
+``einsum("bnd,csd->bcns")`` / ``amax`` / ``sum`` of :153-154 and everything after it run as
+
+1. the fused sm_100a MaxSim kernel (csrc/maxsim_sm100.cu), which also records, per (document, query token),
+   the index of the winning document token (int32 ``[C, B*N_q]`` instead of the reference's saved
+   ``[B, C, N_q, N_d]`` similarity tensor);
+2. one small kernel (csrc/loss_sm100.cu) that turns the ``[B, C]`` sums into the scalar loss *and* its gradient
+   with respect to the sums;
+3. in backward, a gather kernel for ``dQ`` and a scatter-add kernel for ``dD``.
+
+Differences from the reference that a caller can observe, all documented in DESIGN.md:
+the loss is returned in fp32 whatever the embedding dtype (the reference returns the embedding dtype);
+embeddings are contracted in bf16 with fp32 accumulation; ``use_smooth_max=True`` is not implemented yet and
+raises; where several document tokens tie for the maximum the gradient goes to the first one (``amax`` splits
+it evenly) -- this only differs on all-zero (padding) rows, whose gradients the model masks anyway.
+"""
+
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .scoring import EMBED_DIM, DocBank, QueryBlock, maxsim
+
+
+class _InBatchLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, d, offset, mode, temperature, normalize, filt, thr, factor, bounds_out):
+        if q.dim() != 3 or d.dim() != 3:
+            raise ValueError(f"expected [B, N_q, D] and [C, N_d, D] embeddings, got {tuple(q.shape)} / {tuple(d.shape)}")
+        dev = q.device
+        if dev.type != "cuda" or d.device != dev:
+            raise _lib.ColpaliB200Error("colpali_b200 losses need query and document embeddings on the same CUDA device")
+        lib = _lib.load()
+        qb = QueryBlock(q.detach(), dev)
+        bank = DocBank.from_passages(d.detach(), dev)  # dense [C, L, D]: zero (padding) rows are ordinary tokens,
+        # they score exactly 0 and take part in the max, as in the reference
+        need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        if need_grad:
+            scores, argmax = maxsim(qb, bank, want_argmax=True)
+        else:
+            scores, argmax = maxsim(qb, bank), None
+        b, c = qb.n, bank.n_docs
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        g = torch.empty(b, c, dtype=torch.float32, device=dev) if need_grad else None
+        with torch.cuda.device(dev):
+            rc = lib.cpb_colbert_loss_fwd(
+                scores.data_ptr(), qb.flat.data_ptr(), b, qb.nq_pad, c, mode,
+                float(temperature), int(normalize), int(filt), float(thr), float(factor), int(offset),
+                loss.data_ptr(), g.data_ptr() if g is not None else None,
+                bounds_out.data_ptr() if bounds_out is not None else None,
+                torch.cuda.current_stream(dev).cuda_stream,
+            )
+        _lib.check(rc, "cpb_colbert_loss_fwd")
+        _lib.count_launches(1)
+        if need_grad:
+            ctx.save_for_backward(qb.flat, bank.flat, bank.start, argmax, g)
+            ctx.meta = (qb.n, qb.nq_pad, c, tuple(q.shape), tuple(d.shape), q.dtype, d.dtype)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        q_flat, d_flat, d_start, argmax, g = ctx.saved_tensors
+        b, nq_pad, c, q_shape, d_shape, q_dtype, d_dtype = ctx.meta
+        dev = q_flat.device
+        lib = _lib.load()
+        want_q, want_d = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        dq = torch.empty(b * nq_pad, EMBED_DIM, dtype=torch.float32, device=dev) if want_q else None
+        dd = torch.zeros(d_flat.shape[0], EMBED_DIM, dtype=torch.float32, device=dev) if want_d else None
+        go = grad_out.detach().to(torch.float32).reshape(1).contiguous()
+        with torch.cuda.device(dev):
+            rc = lib.cpb_maxsim_bwd(
+                g.data_ptr(), go.data_ptr(), argmax.data_ptr(),
+                q_flat.data_ptr(), b, nq_pad,
+                d_flat.data_ptr(), d_flat.shape[0], d_start.data_ptr(), c,
+                dq.data_ptr() if dq is not None else None, dd.data_ptr() if dd is not None else None,
+                torch.cuda.current_stream(dev).cuda_stream,
+            )
+        _lib.check(rc, "cpb_maxsim_bwd")
+        _lib.count_launches(int(want_q) + int(want_d))
+        grad_q = grad_d = None
+        if want_q:
+            grad_q = dq.view(b, nq_pad, EMBED_DIM)[:, : q_shape[1], : q_shape[2]].to(q_dtype)
+        if want_d:
+            grad_d = dd.view(d_shape[0], d_shape[1], EMBED_DIM)[:, :, : d_shape[2]].to(d_dtype)
+        return grad_q, grad_d, None, None, None, None, None, None, None, None
+
+
+class ColbertModule(torch.nn.Module):
+    """late_interaction_losses.py:6-107 -- hyper-parameters and helper methods of the ColBERT losses."""
+
+    def __init__(self, max_batch_size: int = 1024, tau: float = 0.1, norm_tol: float = 1e-3,
+                 filter_threshold: float = 0.95, filter_factor: float = 0.5):
+        super().__init__()
+        self.register_buffer("idx_buffer", torch.arange(max_batch_size), persistent=False)
+        self.tau = tau
+        self.norm_tol = norm_tol
+        self.filter_threshold = filter_threshold
+        self.filter_factor = filter_factor
+        # set True to reproduce the reference's "Scores out of bounds after normalization" print (:64-70);
+        # it costs a host sync per step, which is why it is off by default here
+        self.check_bounds = False
+
+    # -- helpers kept for drop-in parity with the reference's own unit tests (tests/loss/test_li_losses.py) --
+    def _get_idx(self, batch_size: int, offset: int, device: torch.device):
+        idx = self.idx_buffer[:batch_size].to(device)
+        return idx, idx + offset
+
+    def _smooth_max(self, scores: torch.Tensor, dim: int) -> torch.Tensor:
+        return self.tau * torch.logsumexp(scores / self.tau, dim=dim)
+
+    def _apply_normalization(self, scores: torch.Tensor, lengths: torch.Tensor) -> torch.Tensor:
+        normalized = scores / lengths.unsqueeze(1) if scores.ndim == 2 else scores / lengths
+        mn, mx = torch.aminmax(normalized)
+        if mn < -self.norm_tol or mx > 1 + self.norm_tol:
+            print(f"Scores out of bounds after normalization: min={mn.item():.4f}, max={mx.item():.4f}, tol={self.norm_tol}")
+        return normalized
+
+    def _aggregate(self, scores_raw: torch.Tensor, use_smooth_max: bool, dim_max: int, dim_sum: int) -> torch.Tensor:
+        if use_smooth_max:
+            return self._smooth_max(scores_raw, dim=dim_max).sum(dim=dim_sum)
+        return scores_raw.amax(dim=dim_max).sum(dim=dim_sum)
+
+    def _filter_high_negatives(self, scores: torch.Tensor, pos_idx: torch.Tensor) -> None:
+        batch_size = scores.size(0)
+        idx = self.idx_buffer[:batch_size].to(scores.device)
+        pos_scores = scores[idx, pos_idx]
+        thresh = self.filter_threshold * pos_scores.unsqueeze(1)
+        mask = scores > thresh
+        mask[idx, pos_idx] = False
+        scores[mask] *= self.filter_factor
+
+    # -- shared fused path ------------------------------------------------------------------------------
+    def _fused_in_batch_loss(self, mode: int, q: torch.Tensor, d: torch.Tensor, offset: int) -> torch.Tensor:
+        if self.use_smooth_max:
+            raise NotImplementedError(
+                "use_smooth_max=True (tau * logsumexp instead of amax, late_interaction_losses.py:40-44) is not "
+                "implemented in the fused sm_100a path yet; use the reference module for it."
+            )
+        bounds = torch.empty(2, dtype=torch.float32, device=q.device) if (self.check_bounds and self.normalize_scores) else None
+        loss = _InBatchLossFn.apply(q, d, int(offset), mode, self.temperature, self.normalize_scores,
+                                    self.pos_aware_negative_filtering, self.filter_threshold, self.filter_factor, bounds)
+        if bounds is not None:
+            mn, mx = bounds.tolist()
+            if mn < -self.norm_tol or mx > 1 + self.norm_tol:
+                print(f"Scores out of bounds after normalization: min={mn:.4f}, max={mx:.4f}, tol={self.norm_tol}")
+        return loss
+
+
+class ColbertLoss(ColbertModule):
+    """InfoNCE loss for late interaction without explicit negatives (late_interaction_losses.py:110-164)."""
+
+    def __init__(self, temperature: float = 0.02, normalize_scores: bool = True, use_smooth_max: bool = False,
+                 pos_aware_negative_filtering: bool = False, max_batch_size: int = 1024, tau: float = 0.1,
+                 norm_tol: float = 1e-3, filter_threshold: float = 0.95, filter_factor: float = 0.5):
+        super().__init__(max_batch_size, tau, norm_tol, filter_threshold, filter_factor)
+        self.temperature = temperature
+        self.normalize_scores = normalize_scores
+        self.use_smooth_max = use_smooth_max
+        self.pos_aware_negative_filtering = pos_aware_negative_filtering
+        self.ce_loss = torch.nn.CrossEntropyLoss()  # attribute kept for parity (:138); the fused kernel does the work
+
+    def forward(self, query_embeddings: torch.Tensor, doc_embeddings: torch.Tensor, offset: int = 0) -> torch.Tensor:
+        return self._fused_in_batch_loss(_lib.CPB_LOSS_CE, query_embeddings, doc_embeddings, offset)
+
+
+class ColbertPairwiseCELoss(ColbertModule):
+    """Pairwise softplus loss over in-batch documents (late_interaction_losses.py:255-313)."""
+
+    def __init__(self, temperature: float = 1.0, normalize_scores: bool = True, use_smooth_max: bool = False,
+                 pos_aware_negative_filtering: bool = False, max_batch_size: int = 1024, tau: float = 0.1,
+                 norm_tol: float = 1e-3, filter_threshold: float = 0.95, filter_factor: float = 0.5):
+        super().__init__(max_batch_size, tau, norm_tol, filter_threshold, filter_factor)
+        self.temperature = temperature
+        self.normalize_scores = normalize_scores
+        self.use_smooth_max = use_smooth_max
+        self.pos_aware_negative_filtering = pos_aware_negative_filtering
+
+    def forward(self, query_embeddings: torch.Tensor, doc_embeddings: torch.Tensor, offset: int = 0) -> torch.Tensor:
+        return self._fused_in_batch_loss(_lib.CPB_LOSS_PAIRWISE, query_embeddings, doc_embeddings, offset)

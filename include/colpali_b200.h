@@ -91,6 +91,45 @@ int cpb_maxsim_fwd(const void* d_q, int n_queries, int nq_pad,
 /* Bytes of d_workspace cpb_maxsim_fwd needs for this shape (0 when nq_pad == 32). */
 int64_t cpb_maxsim_workspace_bytes(int n_queries, int nq_pad, int n_docs);
 
+/* loss modes of cpb_colbert_loss_fwd */
+#define CPB_LOSS_CE 0       /* ColbertLoss: cross entropy over in-batch documents          */
+#define CPB_LOSS_PAIRWISE 1 /* ColbertPairwiseCELoss: softplus(hardest negative - positive) */
+
+/*
+ * In-batch-negative loss on a [n_queries, n_docs] matrix of raw MaxSim sums, with its gradient.
+ *   replaces: ColbertLoss.forward            colpali_engine/loss/late_interaction_losses.py:152,155-164
+ *             ColbertPairwiseCELoss.forward  colpali_engine/loss/late_interaction_losses.py:296,299-313
+ *             ColbertModule._apply_normalization :46-71, ._filter_high_negatives :93-107
+ *   lengths (late_interaction_losses.py:152) are counted here from column 0 of d_q (same padded
+ *   layout as cpb_maxsim_fwd).  The positive of query b is document b + offset (:33-38).
+ *
+ *   d_loss         fp32 [1] out: mean over queries.
+ *   d_grad_scores  fp32 [n_queries, n_docs] out or NULL: d loss / d raw score.
+ *   d_bounds       fp32 [2] out or NULL: min / max of the length-normalised scores (the reference
+ *                  prints a warning when they leave [-norm_tol, 1 + norm_tol], :64-70).
+ */
+int cpb_colbert_loss_fwd(const float* d_scores, const void* d_q, int n_queries, int nq_pad, int n_docs, int mode,
+                         float temperature, int normalize_scores, int pos_aware_negative_filtering,
+                         float filter_threshold, float filter_factor, int offset,
+                         float* d_loss, float* d_grad_scores, float* d_bounds, void* stream);
+
+/*
+ * Backward of cpb_maxsim_fwd: given g = d loss / d scores and the argmax saved by the forward,
+ *   dq[row]                       = sum_c g[query(row), c] * docs[doc_start[c] + argmax[c, row]]
+ *   dd[doc_start[c] + argmax[..]] += g[query(row), c] * q[row]            (fp32 vector atomics)
+ *   replaces: autograd through torch.einsum / amax / sum (late_interaction_losses.py:153-154); the
+ *   reference keeps the [B, C, N_q, N_d] similarity tensor alive for it, this path keeps [C, rows] int32.
+ *
+ *   d_grad_out  fp32 [1] upstream gradient of the loss, or NULL for 1.
+ *   d_dq        fp32 [n_queries * nq_pad, 128] out, or NULL to skip.
+ *   d_dd        fp32 [doc_rows, 128] in/out, MUST be zero-initialised by the caller, or NULL to skip.
+ *   Rows whose argmax is -1 (the floor won) receive no gradient.
+ */
+int cpb_maxsim_bwd(const float* d_grad_scores, const float* d_grad_out, const int32_t* d_argmax,
+                   const void* d_q, int n_queries, int nq_pad,
+                   const void* d_docs, int64_t doc_rows, const int32_t* d_doc_start, int n_docs,
+                   float* d_dq, float* d_dd, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -120,8 +120,9 @@ def scorer_cfg(name, q, d):
 def loss_small():
     """B=4, C=6, N_q=5, N_d=9, fp32, offset=1, zero query rows and zero doc rows."""
     g = torch.Generator().manual_seed(5)
-    q = torch.nn.functional.normalize(torch.randn(4, 5, 16, generator=g), dim=-1)
-    d = torch.nn.functional.normalize(torch.randn(6, 9, 16, generator=g), dim=-1)
+    # values are rounded to bf16 so that a bf16-contracting implementation sees exactly the same numbers
+    q = torch.nn.functional.normalize(torch.randn(4, 5, 16, generator=g), dim=-1).bfloat16().float()
+    d = torch.nn.functional.normalize(torch.randn(6, 9, 16, generator=g), dim=-1).bfloat16().float()
     q[1, 3:] = 0
     q[3, 4:] = 0
     d[0, :2] = 0

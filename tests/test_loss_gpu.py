@@ -1,0 +1,135 @@
+"""GPU parity: fused ColbertLoss / ColbertPairwiseCELoss (forward and backward) against the reference's own
+outputs (tests/golden/loss_*.npz) and the CPU oracle."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+import colpali_b200 as cb
+from oracle import li_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+LOSS_TOL = 1e-3  # BASELINE configs[2]: loss within 1e-3
+
+
+def _run(mod, q, d, offset=0):
+    qq = q.to(DEV).requires_grad_(True)
+    dd = d.to(DEV).requires_grad_(True)
+    loss = mod(qq, dd, offset=offset)
+    loss.backward()
+    torch.cuda.synchronize()
+    return loss.detach().cpu(), qq.grad.cpu(), dd.grad.cpu()
+
+
+CASES = (
+    ("colbert", lambda: cb.ColbertLoss()),
+    ("colbert_nonorm_t1", lambda: cb.ColbertLoss(temperature=1.0, normalize_scores=False)),
+    ("colbert_filter", lambda: cb.ColbertLoss(pos_aware_negative_filtering=True)),
+    ("pairwise", lambda: cb.ColbertPairwiseCELoss()),
+    ("pairwise_filter", lambda: cb.ColbertPairwiseCELoss(pos_aware_negative_filtering=True)),
+)
+
+
+@pytest.mark.parametrize("name,make", CASES)
+def test_small_losses_and_grads_match_reference(name, make):
+    """B=4, C=6, N_q=5, N_d=9, D=16, offset=1, zero query rows and zero document rows; inputs are
+    bf16-representable so the bf16 contraction is exact and the reference's fp32 numbers apply directly."""
+    g = load_golden("loss_small.npz")
+    q, d = torch.from_numpy(g["q"]), torch.from_numpy(g["d"])
+    loss, dq, dd = _run(make(), q, d, offset=1)
+    assert loss.dtype == torch.float32 and loss.dim() == 0
+    assert abs(float(loss) - float(g[f"{name}_loss"])) < 2e-5, (float(loss), float(g[f"{name}_loss"]))
+    # gradients: exclude all-zero (padding) rows, where amax's tie-splitting differs by construction
+    real_q = q.abs().sum(-1) > 0
+    real_d = d.abs().sum(-1) > 0
+    ref_dq, ref_dd = torch.from_numpy(g[f"{name}_dq"]), torch.from_numpy(g[f"{name}_dd"])
+    assert torch.allclose(dq[real_q], ref_dq[real_q], rtol=1e-4, atol=2e-6), name
+    assert torch.allclose(dd[real_d], ref_dd[real_d], rtol=1e-4, atol=2e-6), name
+
+
+def test_zero_embedding_known_answers():
+    """The reference's own KATs (tests/loss/test_li_losses.py:76-100, :166-181): all-zero inputs."""
+    b, nq, dim = 3, 1, 4
+    q = torch.zeros(b, nq, dim, device=DEV)
+    d = torch.zeros(b, nq, dim, device=DEV)
+    ce = cb.ColbertLoss(temperature=1.0, normalize_scores=False)
+    assert math.isclose(float(ce(q, d)), math.log(b), rel_tol=1e-6)
+    filt = cb.ColbertLoss(temperature=1.0, normalize_scores=False, pos_aware_negative_filtering=True)
+    assert math.isclose(float(filt(q, d)), float(ce(q, d)), rel_tol=1e-6)
+    pw = cb.ColbertPairwiseCELoss(temperature=1.0, normalize_scores=False)
+    assert math.isclose(float(pw(q, d)), math.log(2.0), rel_tol=1e-6)
+
+
+def test_helper_methods_known_answers():
+    """ColbertModule helpers, same KATs as tests/loss/test_li_losses.py:16-74."""
+    m = cb.ColbertModule(max_batch_size=5)
+    idx, pos = m._get_idx(3, 2, torch.device("cpu"))
+    assert idx.tolist() == [0, 1, 2] and pos.tolist() == [2, 3, 4]
+    raw = torch.tensor([[[1.0, 2.0], [3.0, 4.0]], [[5.0, 6.0], [7.0, 8.0]]])
+    assert torch.allclose(m._aggregate(raw, False, 2, 1), torch.tensor([6.0, 14.0]))
+    m2 = cb.ColbertModule(tau=1.0)
+    assert torch.allclose(m2._aggregate(torch.zeros(1, 2, 2), True, 2, 1), 2 * torch.log(torch.tensor(2.0)))
+    s = torch.tensor([[1.0, 0.96], [0.5, 1.0]])
+    cb.ColbertModule()._filter_high_negatives(s, torch.tensor([0, 1]))
+    assert s[0, 1] == pytest.approx(0.48) and s[0, 0] == 1.0 and s[1, 0] == 0.5
+
+
+def test_cfg3_loss_and_gradients():
+    """B=64 pairs, N_q=32, documents 768..1030 tokens left-padded to 1030 (BASELINE configs[2])."""
+    g = load_golden("loss_cfg3.npz")
+    q, d, lens = O.cfg3_inputs()
+    for name, mod in (("colbert", cb.ColbertLoss()), ("pairwise", cb.ColbertPairwiseCELoss())):
+        loss, dq, dd = _run(mod, q, d)
+        ref = float(g[f"{name}_fp32"])
+        assert abs(float(loss) - ref) < LOSS_TOL, (name, float(loss), ref)
+        ref_dq = torch.from_numpy(g[f"{name}_dq"])
+        # grads come back in the embedding dtype (bf16): compare direction and scale
+        cos = torch.nn.functional.cosine_similarity(dq.float().flatten(), ref_dq.flatten(), dim=0)
+        assert cos > 0.9999, (name, float(cos))
+        assert torch.allclose(dq.float(), ref_dq, rtol=2e-2, atol=ref_dq.abs().max().item() * 1e-2)
+        ref_dd2 = torch.from_numpy(g[f"{name}_dd_first2"])
+        real = d[:2].float().abs().sum(-1) > 0
+        assert torch.allclose(dd[:2].float()[real], ref_dd2[real], rtol=2e-2, atol=ref_dd2.abs().max().item() * 1e-2)
+        rn = dd.float().norm(dim=-1)
+        ref_rn = torch.from_numpy(g[f"{name}_dd_rownorm"])
+        realall = d.float().abs().sum(-1) > 0
+        assert torch.allclose(rn[realall], ref_rn[realall], rtol=3e-2, atol=ref_rn.max().item() * 1e-2)
+
+
+def test_gathered_documents_offset_and_no_grad_path():
+    """C > B with a rank offset (contrastive_trainer.py:143-150 gathers documents across ranks)."""
+    g = torch.Generator().manual_seed(4)
+    q = O.unit_rows((8, 20, 128), 10)
+    d = O.unit_rows((24, 70, 128), 11)
+    d[:, :5] = 0
+    for offset in (0, 8, 16):
+        want = O.colbert_loss_port(q.float(), d.float(), offset=offset)
+        got = cb.ColbertLoss()(q.to(DEV), d.to(DEV), offset=offset)  # no grad required: argmax-free kernel
+        assert abs(float(got) - float(want)) < 1e-4
+        want_p = O.colbert_pairwise_ce_loss_port(q.float(), d.float(), offset=offset)
+        got_p = cb.ColbertPairwiseCELoss()(q.to(DEV), d.to(DEV), offset=offset)
+        assert abs(float(got_p) - float(want_p)) < 1e-4
+    with pytest.raises(cb.ColpaliB200Error):
+        cb.ColbertLoss()(q.to(DEV), d.to(DEV), offset=17)  # positive index past the last document
+
+
+def test_upstream_gradient_scaling_and_autograd_of_oracle():
+    """d(2.5 * loss) = 2.5 * d(loss); gradients agree with torch autograd through the oracle port."""
+    q = O.unit_rows((6, 32, 128), 20)
+    d = O.unit_rows((6, 300, 128), 21)
+    qq, dd = q.to(DEV).requires_grad_(True), d.to(DEV).requires_grad_(True)
+    (cb.ColbertLoss()(qq, dd) * 2.5).backward()
+    qo, do = q.float().requires_grad_(True), d.float().requires_grad_(True)
+    (O.colbert_loss_port(qo, do) * 2.5).backward()
+    assert torch.allclose(qq.grad.float().cpu(), qo.grad, rtol=2e-2, atol=qo.grad.abs().max().item() * 1e-2)
+    assert torch.allclose(dd.grad.float().cpu(), do.grad, rtol=2e-2, atol=do.grad.abs().max().item() * 1e-2)
+
+
+def test_smooth_max_is_refused_loudly():
+    q = O.unit_rows((2, 4, 128), 1).to(DEV)
+    with pytest.raises(NotImplementedError):
+        cb.ColbertLoss(use_smooth_max=True)(q, q)
