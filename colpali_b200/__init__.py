@@ -3,9 +3,11 @@
 Public names mirror the reference (illuin-tech/colpali):
   score_multi_vector / score_single_vector   <- BaseVisualRetrieverProcessor (utils/processing_utils.py)
   ColbertLoss / ColbertPairwiseCELoss        <- colpali_engine.loss (loss/late_interaction_losses.py)
+  fused_head                                 <- custom_text_proj + norm + mask tail of every Col* model forward
 """
 
 from ._lib import ColpaliB200Error
+from .head import fused_head
 from .losses import ColbertLoss, ColbertModule, ColbertPairwiseCELoss
 from .scoring import DocBank, QueryBlock, maxsim, score_multi_vector, score_single_vector
 
@@ -15,6 +17,7 @@ __all__ = [
     "ColbertPairwiseCELoss",
     "ColpaliB200Error",
     "DocBank",
+    "fused_head",
     "QueryBlock",
     "maxsim",
     "score_multi_vector",

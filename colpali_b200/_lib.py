@@ -24,10 +24,13 @@ EXPORTED_SYMBOLS = (
     "cpb_maxsim_workspace_bytes",
     "cpb_colbert_loss_fwd",
     "cpb_maxsim_bwd",
+    "cpb_head_fwd",
 )
 
 CPB_FLAG_ROUND_BF16 = 1
 CPB_FLAG_CONTIGUOUS = 2
+CPB_HEAD_CLAMP_NORM = 1
+CPB_HEAD_SINGLE_ROUNDING = 2
 CPB_LOSS_CE = 0
 CPB_LOSS_PAIRWISE = 1
 
@@ -82,6 +85,13 @@ def load() -> ctypes.CDLL:
         c_vp, c_i, c_i,  # d_q, n_queries, nq_pad
         c_vp, c_i64, c_vp, c_i,  # d_docs, doc_rows, d_doc_start, n_docs
         c_vp, c_vp, c_vp,  # d_dq, d_dd, stream
+    ]
+    lib.cpb_head_fwd.restype = c_i
+    lib.cpb_head_fwd.argtypes = [
+        c_vp, c_i64, c_i,  # d_hidden, n_tokens, hidden
+        c_vp, c_vp, c_i,  # d_weight, d_bias, dim
+        c_vp, c_vp,  # d_attention_mask, d_extra_mask
+        c_vp, c_u32, c_vp,  # d_out, flags, stream
     ]
     _lib = lib
     return lib

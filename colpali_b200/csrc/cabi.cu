@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/colpali_b200.h"
+#include "head_params.h"
 #include "loss_params.h"
 #include "maxsim_params.h"
 
@@ -269,6 +270,38 @@ int cpb_maxsim_bwd(const float* d_grad_scores, const float* d_grad_out, const in
   p.nq_pad = nq_pad;
   p.q_rows = n_queries * nq_pad;
   CPB_CUDA(cpb::maxsim_bwd_launch(p, static_cast<cudaStream_t>(stream_)));
+  return CPB_OK;
+}
+
+int cpb_head_fwd(const void* d_hidden, int64_t n_tokens, int hidden, const void* d_weight, const void* d_bias, int dim,
+                 const int64_t* d_attention_mask, const uint8_t* d_extra_mask, void* d_out, uint32_t flags,
+                 void* stream_) {
+  if (n_tokens <= 0) return fail(CPB_E_INVALID, "n_tokens=%lld must be positive", static_cast<long long>(n_tokens));
+  if (n_tokens > 0x7fffff00LL) return fail(CPB_E_INVALID, "n_tokens too large");
+  if (dim != 128) return fail(CPB_E_UNSUPPORTED, "projection dim %d is not supported by this build (128 only)", dim);
+  if (hidden <= 0 || (hidden % 64) != 0) return fail(CPB_E_UNSUPPORTED, "hidden size %d must be a positive multiple of 64", hidden);
+  if (!d_hidden || !d_weight || !d_out) return fail(CPB_E_INVALID, "null device pointer");
+  if (reinterpret_cast<uintptr_t>(d_out) & 15u) return fail(CPB_E_INVALID, "d_out is not 16-byte aligned");
+  DevInfo di;
+  int rc = current_device_info(&di);
+  if (rc != CPB_OK) return rc;
+  if (di.major != 10) return fail(CPB_E_DEVICE, "device is sm_%d%d; this library needs sm_100 (B200)", di.major, di.minor);
+  CUtensorMap th, tw;
+  rc = make_bf16_rowmajor_map(&th, d_hidden, n_tokens, hidden, 128);
+  if (rc != CPB_OK) return rc;
+  rc = make_bf16_rowmajor_map(&tw, d_weight, dim, hidden, 128);
+  if (rc != CPB_OK) return rc;
+  cpb::HeadParams p{};
+  p.bias = static_cast<const __nv_bfloat16*>(d_bias);
+  p.attention_mask = d_attention_mask;
+  p.extra_mask = d_extra_mask;
+  p.out = static_cast<__nv_bfloat16*>(d_out);
+  p.n_tokens = n_tokens;
+  p.hidden = hidden;
+  p.flags = flags;
+  const int64_t pairs = (n_tokens + 255) / 256;
+  const int grid = static_cast<int>(pairs < di.sm_count ? pairs : di.sm_count);
+  CPB_CUDA(cpb::head_launch(th, tw, p, grid, static_cast<cudaStream_t>(stream_)));
   return CPB_OK;
 }
 

@@ -1,0 +1,22 @@
+// Parameter block of the fused projection-head kernel (head_sm100.cu), filled by cabi.cu.
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace cpb {
+
+struct HeadParams {
+  const __nv_bfloat16* bias;       // [128] or nullptr
+  const int64_t* attention_mask;   // [n_tokens] or nullptr
+  const uint8_t* extra_mask;       // [n_tokens] or nullptr (image-token mask)
+  __nv_bfloat16* out;              // [n_tokens, 128]
+  int64_t n_tokens;
+  int hidden;
+  uint32_t flags;
+};
+
+cudaError_t head_launch(const CUtensorMap& th, const CUtensorMap& tw, const HeadParams& p, int grid, cudaStream_t stream);
+
+}  // namespace cpb

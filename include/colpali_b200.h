@@ -130,6 +130,32 @@ int cpb_maxsim_bwd(const float* d_grad_scores, const float* d_grad_out, const in
                    const void* d_docs, int64_t doc_rows, const int32_t* d_doc_start, int n_docs,
                    float* d_dq, float* d_dd, void* stream);
 
+/* flags for cpb_head_fwd */
+#define CPB_HEAD_CLAMP_NORM 1u      /* norm = max(norm, 1e-12): ColModernVBert variant (modeling_colmodernvbert.py:59) */
+#define CPB_HEAD_SINGLE_ROUNDING 2u /* keep fp32 until the final store instead of emulating the reference's
+                                       three bf16 roundings (Linear output, norm, quotient) */
+
+/*
+ * Fused multi-vector projection head.
+ *   replaces: proj = self.custom_text_proj(h); proj = proj / proj.norm(dim=-1, keepdim=True);
+ *             proj = proj * attention_mask.unsqueeze(-1) [; proj = proj * image_mask]
+ *             colpali_engine/models/qwen2/colqwen2/modeling_colqwen2.py:65-74 (ctor :34-35) and the identical
+ *             tails of ColPali :67-77, ColQwen2.5 :67-76, ColQwen3.5 :67-76, ColQwen2.5-Omni :64-73,
+ *             ColGemma3 :84-93, ColIdefics3 :38-46, ColModernVBert :57-65 (CPB_HEAD_CLAMP_NORM).
+ *
+ *   d_hidden          bf16 [n_tokens, hidden]   last_hidden_state, flattened over (batch, sequence)
+ *   d_weight          bf16 [dim, hidden]        custom_text_proj.weight (nn.Linear layout)
+ *   d_bias            bf16 [dim] or NULL        custom_text_proj.bias
+ *   d_attention_mask  int64 [n_tokens] or NULL  multiplied in as a value (0/1 in practice)
+ *   d_extra_mask      uint8 [n_tokens] or NULL  non-zero keeps the row (input_ids == image_token_id)
+ *   d_out             bf16 [n_tokens, dim]
+ *   dim must be 128 and hidden a multiple of 64 in this build (CPB_E_UNSUPPORTED otherwise).
+ */
+int cpb_head_fwd(const void* d_hidden, int64_t n_tokens, int hidden,
+                 const void* d_weight, const void* d_bias, int dim,
+                 const int64_t* d_attention_mask, const uint8_t* d_extra_mask,
+                 void* d_out, uint32_t flags, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
