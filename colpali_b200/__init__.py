@@ -8,6 +8,7 @@ Public names mirror the reference (illuin-tech/colpali):
 
 from ._lib import ColpaliB200Error
 from .head import fused_head
+from .install import install, uninstall
 from .losses import ColbertLoss, ColbertModule, ColbertPairwiseCELoss
 from .scoring import DocBank, QueryBlock, maxsim, score_multi_vector, score_single_vector
 
@@ -18,6 +19,8 @@ __all__ = [
     "ColpaliB200Error",
     "DocBank",
     "fused_head",
+    "install",
+    "uninstall",
     "QueryBlock",
     "maxsim",
     "score_multi_vector",

@@ -1,0 +1,51 @@
+"""Drop the B200 hot path into an importable ``colpali_engine`` (the reference) by attribute patching.
+
+The reference has no plugin registry; its seams are plain Python attributes:
+
+* the staticmethod ``BaseVisualRetrieverProcessor.score_multi_vector`` that every ``Col*Processor.score`` forwards
+  to (colpali_engine/utils/processing_utils.py:132, e.g. models/qwen2/colqwen2/processing_colqwen2.py:115-125);
+* the loss classes referenced by dotted path from training configs (scripts/configs/qwen2/train_colqwen2_model.yaml:25)
+  and re-exported by ``colpali_engine.loss`` (loss/__init__.py:9-16).
+
+``install()`` swaps those attributes; ``uninstall()`` restores the originals.  Model heads are patched per model
+file (three lines) because each ``forward`` owns its backbone call.
+"""
+
+from __future__ import annotations
+
+import importlib
+from typing import Dict, Tuple
+
+_saved: Dict[Tuple[str, str], object] = {}
+
+_LOSS_NAMES = ("ColbertModule", "ColbertLoss", "ColbertPairwiseCELoss")
+
+
+def _swap(obj, name: str, new) -> None:
+    key = (f"{getattr(obj, '__module__', '')}.{getattr(obj, '__qualname__', getattr(obj, '__name__', repr(obj)))}", name)
+    if key not in _saved:
+        _saved[key] = (obj, obj.__dict__.get(name, getattr(obj, name)))
+    setattr(obj, name, new)
+
+
+def install(scorer: bool = True, losses: bool = True) -> None:
+    """Patch ``colpali_engine`` in this process.  Raises ImportError if the reference is not importable."""
+    from . import losses as _losses
+    from . import scoring as _scoring
+
+    if scorer:
+        pu = importlib.import_module("colpali_engine.utils.processing_utils")
+        _swap(pu.BaseVisualRetrieverProcessor, "score_multi_vector", staticmethod(_scoring.score_multi_vector))
+        _swap(pu.BaseVisualRetrieverProcessor, "score_single_vector", staticmethod(_scoring.score_single_vector))
+    if losses:
+        for modname in ("colpali_engine.loss.late_interaction_losses", "colpali_engine.loss"):
+            mod = importlib.import_module(modname)
+            for n in _LOSS_NAMES:
+                if hasattr(mod, n):
+                    _swap(mod, n, getattr(_losses, n))
+
+
+def uninstall() -> None:
+    for (_, name), (obj, old) in list(_saved.items()):
+        setattr(obj, name, old)
+    _saved.clear()

@@ -1,0 +1,61 @@
+"""CPU: install()/uninstall() swap exactly the reference's seams (exercised on a stub package that has the
+reference's attribute layout; the real colpali_engine is not present on the GPU box)."""
+import sys
+import textwrap
+
+import colpali_b200 as cb
+
+
+def _make_stub(tmp_path):
+    root = tmp_path / "colpali_engine"
+    (root / "utils").mkdir(parents=True)
+    (root / "loss").mkdir()
+    (root / "__init__.py").write_text("")
+    (root / "utils" / "__init__.py").write_text("")
+    (root / "utils" / "processing_utils.py").write_text(textwrap.dedent("""
+        class BaseVisualRetrieverProcessor:
+            @staticmethod
+            def score_multi_vector(qs, ps, batch_size=128, device=None):
+                return "reference-multi"
+            @staticmethod
+            def score_single_vector(qs, ps, device=None):
+                return "reference-single"
+        class ColStubProcessor(BaseVisualRetrieverProcessor):
+            def score(self, qs, ps, device=None, **kw):
+                return self.score_multi_vector(qs, ps, device=device, **kw)
+    """))
+    (root / "loss" / "late_interaction_losses.py").write_text(textwrap.dedent("""
+        class ColbertModule: pass
+        class ColbertLoss(ColbertModule): pass
+        class ColbertPairwiseCELoss(ColbertModule): pass
+        class ColbertSigmoidLoss(ColbertModule): pass
+    """))
+    (root / "loss" / "__init__.py").write_text(
+        "from .late_interaction_losses import ColbertLoss, ColbertModule, ColbertPairwiseCELoss, ColbertSigmoidLoss\n")
+
+
+def test_install_and_uninstall(tmp_path, monkeypatch):
+    _make_stub(tmp_path)
+    monkeypatch.syspath_prepend(str(tmp_path))
+    for k in [k for k in sys.modules if k.startswith("colpali_engine")]:
+        monkeypatch.delitem(sys.modules, k)
+    import colpali_engine.loss as L
+    import colpali_engine.utils.processing_utils as pu
+
+    proc = pu.ColStubProcessor()
+    assert proc.score(1, 2) == "reference-multi"
+    cb.install()
+    try:
+        assert pu.BaseVisualRetrieverProcessor.score_multi_vector is cb.score_multi_vector
+        assert pu.ColStubProcessor.score_multi_vector is cb.score_multi_vector          # subclasses inherit the patch
+        assert L.ColbertLoss is cb.ColbertLoss and L.ColbertPairwiseCELoss is cb.ColbertPairwiseCELoss
+        assert L.late_interaction_losses.ColbertLoss is cb.ColbertLoss                   # dotted-path configs resolve to it
+        assert L.ColbertSigmoidLoss.__module__.startswith("colpali_engine")              # untouched
+        # constructible with the reference's keyword arguments (scripts/configs/**/*.yaml)
+        L.ColbertPairwiseCELoss(temperature=0.02, normalize_scores=True, use_smooth_max=False,
+                                pos_aware_negative_filtering=False, max_batch_size=1024, tau=0.1, norm_tol=1e-3,
+                                filter_threshold=0.95, filter_factor=0.5)
+    finally:
+        cb.uninstall()
+    assert proc.score(1, 2) == "reference-multi"
+    assert L.ColbertLoss.__module__.startswith("colpali_engine")
