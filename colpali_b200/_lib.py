@@ -12,7 +12,7 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcolpali_b200.so")
+LIB_PATH = os.environ.get("COLPALI_B200_LIB") or os.path.join(_HERE, "libcolpali_b200.so")  # env override: kernel-variant experiments
 
 # every symbol include/colpali_b200.h declares; tests check the built library exports them all
 EXPORTED_SYMBOLS = (

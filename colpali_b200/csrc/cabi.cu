@@ -30,6 +30,7 @@ thread_local char g_err[512] = "";
 int g_opt_cluster = 0;
 int g_opt_qtiles_per_cta = 0;
 unsigned g_opt_debug_flags = 0;
+int g_opt_mma_split = 6;
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -127,6 +128,9 @@ int cpb_set_option(const char* name, int value) {
   } else if (!strcmp(name, "qtiles_per_cta")) {
     if (value < 0 || value > 2) return fail(CPB_E_INVALID, "qtiles_per_cta must be 0, 1 or 2");
     g_opt_qtiles_per_cta = value;
+  } else if (!strcmp(name, "mma_split")) {
+    if (value < 5 || value > 8) return fail(CPB_E_INVALID, "mma_split must be 5..8");
+    g_opt_mma_split = value;
   } else if (!strcmp(name, "debug_flags")) {
     g_opt_debug_flags = static_cast<unsigned>(value) & 0xffff0000u;
   } else {
@@ -198,6 +202,7 @@ int cpb_maxsim_fwd(const void* d_q, int n_queries, int nq_pad, const void* d_doc
   if (parts > n_docs) parts = n_docs;
   p.doc_parts = parts;
   p.flags = flags | g_opt_debug_flags;
+  p.mma_split = g_opt_mma_split;
   const int grid = p.group_sets * p.doc_parts * cluster;
 
   CUtensorMap tq, td, tt;

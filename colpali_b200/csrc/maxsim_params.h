@@ -29,6 +29,7 @@ struct MaxSimParams {
   int group_sets;  // ceil(q_groups / cluster)
   int doc_parts;   // document partitions; grid = group_sets * doc_parts * cluster
   uint32_t flags;
+  int mma_split;   // K-steps of a job issued before the next job's barrier waits (5..8)
 };
 
 }  // namespace cpb

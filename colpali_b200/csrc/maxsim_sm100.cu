@@ -46,6 +46,9 @@ constexpr int kQPanelBytes = kTileM * 64 * 2;   // 16 KiB
 constexpr int kDTileBytes = kTileN * kDim * 2;  // 64 KiB
 constexpr int kDPanelBytes = kTileN * 64 * 2;   // 32 KiB
 constexpr int kThreads = 192;
+#ifndef CPB_MMA_SPLIT
+#define CPB_MMA_SPLIT 6
+#endif
 constexpr uint32_t kTmemCols = 512;
 
 template <int R>
@@ -264,56 +267,110 @@ maxsim_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ============================================
-    if (lane == 0) {
+    // The WHOLE warp runs this loop (waits, descriptor arithmetic) so that every value is provably warp-uniform
+    // and stays in uniform registers; only the tcgen05 instructions themselves are issued by one elected lane.
+    //
+    // The tensor pipe's instruction queue is shallow: whatever the issuer does between the last MMA of one job and
+    // the first MMA of the next (two mbarrier try_waits at ~90 cycles each even when already complete, fences,
+    // descriptor setup) shows up as tensor idle time (measured: ~165 cycles per 1024-cycle job, profiles/r01_notes.md).
+    // So the issue stream is software-pipelined: the waits and set-up of job j+1 are performed after K-step kSplit
+    // of job j, while the previous K-steps are still queued, and the remaining K-steps of job j follow immediately.
+    {
       if (r_cnt > 0) mbar_wait(q_full, 0);
       tc_fence_after();
       const uint32_t q_addr = smem_u32(q_smem);
       const uint32_t d_addr = smem_u32(d_smem);
-      int stage = 0;
-      uint32_t phase = 0;
-      uint32_t job = 0;
       const bool dbg = (p.flags & CPB_DBG_CLOCKS) != 0;
       long long w_full = 0, w_tmem = 0;
-      for (int d = d0; d < d1;) {
-        const Run run = next_run(p, d, d1);
-        d = run.e;
-        for (int row = run.row0; row < run.row1; row += kTileN) {
-          const int n_valid = min(kTileN, run.row1 - row);
-          const uint32_t n_mma = static_cast<uint32_t>((n_valid + 15) & ~15);
-          const uint32_t idesc = make_idesc_bf16_f32(kTileM, n_mma);
-          long long t0 = dbg ? clock64() : 0;
-          mbar_wait(&full[stage], phase);
-          if (dbg) w_full += clock64() - t0;
-          tc_fence_after();
-          for (int r = 0; r < r_cnt; ++r) {
-            const uint32_t a = job & 1u;
-            const uint32_t aphase = (job >> 1) & 1u;
-            t0 = dbg ? clock64() : 0;
-            mbar_wait(&tmem_empty[a], aphase ^ 1u);
-            if (dbg) w_tmem += clock64() - t0;
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + a * kTileN;
-#pragma unroll
-            for (int k = 0; k < kDim / 16; ++k) {
-              const int kp = k >> 2, kk = k & 3;
-              const uint64_t adesc =
-                  make_sw128_kmajor_desc(q_addr + r * kQTileBytes + kp * kQPanelBytes) + static_cast<uint64_t>(kk * 2);
-              const uint64_t bdesc =
-                  make_sw128_kmajor_desc(d_addr + stage * kDTileBytes + kp * kDPanelBytes) + static_cast<uint64_t>(kk * 2);
-              umma_bf16(d_tmem, adesc, bdesc, idesc, k > 0 ? 1u : 0u);
-            }
-            umma_commit(&tmem_full[a]);
-            ++job;
-          }
-          // smem slot is free (in every CTA of the cluster) once these MMAs have read it
-          if (C > 1) umma_commit_mc(&empty[stage], cmask); else umma_commit(&empty[stage]);
-          if (++stage == S) {
-            stage = 0;
-            phase ^= 1u;
+
+      struct Job {
+        bool valid, first_of_tile, last_of_tile;
+        int stage, r;
+        uint32_t phase, job, idesc;
+        uint64_t a_desc0, b_desc0;
+      };
+      // tile cursor over the non-empty runs of this partition
+      int it_d = d0, it_row = 0, it_row1 = 0, it_stage = 0;
+      uint32_t it_phase = 0, it_job = 0;
+      bool it_have_tile = false;
+      auto next_tile = [&]() {  // advance to the next 256-row tile; returns false at the end of the partition
+        if (it_have_tile) {
+          it_row += kTileN;
+          if (++it_stage == S) {
+            it_stage = 0;
+            it_phase ^= 1u;
           }
         }
+        while (!it_have_tile || it_row >= it_row1) {
+          if (it_d >= d1) return false;
+          const Run run = next_run(p, it_d, d1);
+          it_d = run.e;
+          it_row = run.row0;
+          it_row1 = run.row1;
+          it_have_tile = true;
+        }
+        return true;
+      };
+      Job cur{};
+      int r_next = 0;
+      auto advance = [&](Job& j) {  // fill j with the job after the current cursor position
+        if (r_cnt == 0) { j.valid = false; return; }
+        if (r_next == 0) {
+          if (!next_tile()) { j.valid = false; return; }
+        }
+        const int n_valid = min(kTileN, it_row1 - it_row);
+        j.valid = true;
+        j.r = r_next;
+        j.first_of_tile = (r_next == 0);
+        j.last_of_tile = (r_next == r_cnt - 1);
+        j.stage = it_stage;
+        j.phase = it_phase;
+        j.job = it_job++;
+        j.idesc = make_idesc_bf16_f32(kTileM, static_cast<uint32_t>((n_valid + 15) & ~15));
+        r_next = (r_next + 1 == r_cnt) ? 0 : r_next + 1;
+      };
+      auto prepare = [&](Job& j) {  // block until job j's operands and accumulator are available
+        long long t0 = dbg ? clock64() : 0;
+        if (j.first_of_tile) mbar_wait(&full[j.stage], j.phase);
+        if (dbg) { const long long t1 = clock64(); w_full += t1 - t0; t0 = t1; }
+        mbar_wait(&tmem_empty[j.job & 1u], ((j.job >> 1) & 1u) ^ 1u);
+        if (dbg) w_tmem += clock64() - t0;
+        tc_fence_after();
+        j.a_desc0 = make_sw128_kmajor_desc(q_addr + j.r * kQTileBytes);
+        j.b_desc0 = make_sw128_kmajor_desc(d_addr + j.stage * kDTileBytes);
+      };
+      auto issue = [&](const Job& j, int k_lo, int k_hi) {
+        const uint32_t d_tmem = tmem_base + (j.job & 1u) * kTileN;
+#pragma unroll
+        for (int k = 0; k < kDim / 16; ++k) {
+          if (k >= k_lo && k < k_hi) {
+            // K step k: panel k/4 (16 KiB / 32 KiB apart), 32 bytes (2 encoded units) per step inside it
+            const uint64_t adesc = j.a_desc0 + static_cast<uint64_t>((k >> 2) * (kQPanelBytes >> 4) + (k & 3) * 2);
+            const uint64_t bdesc = j.b_desc0 + static_cast<uint64_t>((k >> 2) * (kDPanelBytes >> 4) + (k & 3) * 2);
+            umma_bf16(d_tmem, adesc, bdesc, j.idesc, k > 0 ? 1u : 0u);
+          }
+        }
+      };
+      constexpr int kSplit = CPB_MMA_SPLIT;  // K-steps issued before the next job's waits
+      advance(cur);
+      if (cur.valid) prepare(cur);
+      while (cur.valid) {
+        Job nxt{};
+        advance(nxt);
+        if (elect_one()) issue(cur, 0, kSplit);
+        __syncwarp();
+        if (nxt.valid) prepare(nxt);
+        if (elect_one()) {
+          issue(cur, kSplit, kDim / 16);
+          umma_commit(&tmem_full[cur.job & 1u]);
+          if (cur.last_of_tile) {  // smem slot is free (in every CTA of the cluster) once these MMAs have read it
+            if (C > 1) umma_commit_mc(&empty[cur.stage], cmask); else umma_commit(&empty[cur.stage]);
+          }
+        }
+        __syncwarp();
+        cur = nxt;
       }
-      if (dbg) {  // cycles the issuer spent blocked on TMA data / on the epilogue
+      if (dbg && lane == 0) {  // cycles the issuer spent blocked on TMA data / on the epilogue
         p.scores[512 + 8 * blockIdx.x + 0] = static_cast<float>(w_full);
         p.scores[512 + 8 * blockIdx.x + 1] = static_cast<float>(w_tmem);
       }
@@ -359,6 +416,10 @@ maxsim_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       int cur = d;
       int cur_row0 = run.row0;
       int cur_end = cur_row0 + __ldg(p.doc_len + cur);
+      // length and floor of the FOLLOWING document are fetched when the cursor moves, long before they are needed:
+      // a global load while the accumulator is held costs ~300 cycles of tensor idle time on boundary tiles
+      int cur_nlen = (cur + 1 < run.e) ? __ldg(p.doc_len + cur + 1) : 0;
+      float cur_ninit = (cur + 1 < run.e) ? doc_init(cur + 1) : -INFINITY;
       {
         const float init = doc_init(cur);
 #pragma unroll
@@ -370,7 +431,8 @@ maxsim_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       for (int row = run.row0; row < run.row1; row += kTileN) {
         const int n_valid = min(kTileN, run.row1 - row);
         const int tile_end = row + n_valid;
-        int nxt = cur, nxt_row0 = cur_row0, nxt_end = cur_end;
+        int nxt = cur, nxt_row0 = cur_row0, nxt_end = cur_end, nxt_nlen = cur_nlen;
+        float nxt_ninit = cur_ninit;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           if (r < r_cnt) {
@@ -384,7 +446,8 @@ maxsim_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             const uint32_t taddr = tmem_base + lane_base + a * kTileN;
             float mm = m[r];
             int ai = am[r];
-            int doc = cur, doc_row0 = cur_row0, doc_end = cur_end;
+            int doc = cur, doc_row0 = cur_row0, doc_end = cur_end, doc_nlen = cur_nlen;
+            float doc_ninit = cur_ninit;
 
             // the current document is complete: emit it and step to the next one of the run
             auto finish_doc = [&]() {
@@ -395,9 +458,11 @@ maxsim_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 return;
               }
               doc_row0 = doc_end;
-              doc_end = doc_row0 + __ldg(p.doc_len + doc);
-              mm = doc_init(doc);
+              doc_end = doc_row0 + doc_nlen;
+              mm = doc_ninit;
               ai = -1;
+              doc_nlen = (doc + 1 < run.e) ? __ldg(p.doc_len + doc + 1) : 0;
+              doc_ninit = (doc + 1 < run.e) ? doc_init(doc + 1) : -INFINITY;
             };
             auto release_acc = [&]() {  // accumulator drained: hand the TMEM stage back to the MMA warp
               tc_fence_before();
@@ -411,13 +476,11 @@ maxsim_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             // new document per 32-column chunk, plus one masked pass over the chunk that holds the boundary.
             // (3) anything else (short documents, last tile of a run, argmax): generic masked walk.
             int path = 3;
-            int next_len = 0;
             if (!kArgmax && n_valid == kTileN) {
               if (doc_end >= tile_end) {
                 path = 1;
               } else if (doc_end > row && doc + 1 < run.e) {
-                next_len = __ldg(p.doc_len + doc + 1);
-                if (doc_end + next_len >= tile_end) path = 2;
+                if (doc_end + doc_nlen >= tile_end) path = 2;
               }
             }
             if (skip) {
@@ -426,10 +489,12 @@ maxsim_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 ++doc;
                 if (doc >= run.e) { doc_end = 0x7fffffff; break; }
                 doc_row0 = doc_end;
-                doc_end = doc_row0 + __ldg(p.doc_len + doc);
+                doc_end = doc_row0 + doc_nlen;
+                doc_nlen = (doc + 1 < run.e) ? __ldg(p.doc_len + doc + 1) : 0;
               }
             } else if (path == 1) {
               // software pipeline: the loads of columns [64k+64, 64k+128) are in flight while [64k, 64k+64) fold
+              // (TMEM reads are ~64 B/clk per lane quadrant: ~490 cycles for 128 x 256 fp32 whatever the warp count)
               uint32_t va[32], vb[32], vc[32], vd[32];
               tmem_ld_x32(taddr, va);
               tmem_ld_x32(taddr + 32, vb);
@@ -457,44 +522,64 @@ maxsim_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
               tmem_ld_wait();
               reg_fence32(vc);
               reg_fence32(vd);
-              // all accumulator reads have landed in registers: release before the last fold
-              release_acc();
+              release_acc();  // every accumulator read has landed in registers
               mm = max32(vc, mm);
               mm = max32(vd, mm);
               while (doc_end <= tile_end) finish_doc();  // document (and empty followers) ending at the tile end
             } else if (path == 2) {
-              const int b = doc_end - row;  // first column of the next document, 0 < b < 256
+              // one boundary at column b: per 32-column chunk the FMNMX3 tree goes to the old document (chunk < kb)
+              // or the new one (chunk > kb) through selects; the boundary chunk itself is re-read at the end and split
+              // element-wise after the release (branching per chunk would be if-converted into doing everything).
+              const int b = doc_end - row;
               const int kb = b >> 5;
-              float ma = mm, mb = doc_init(doc + 1);
-#pragma unroll
-              for (int cc = 0; cc < kTileN / 64; ++cc) {
-                uint32_t v0[32], v1[32];
-                tmem_ld_x32(taddr + cc * 64, v0);
-                tmem_ld_x32(taddr + cc * 64 + 32, v1);
-                tmem_ld_wait();
-                reg_fence32(v0);
-                reg_fence32(v1);
-                const float t0 = tree32(v0), t1 = tree32(v1);
-                ma = (2 * cc < kb) ? fmaxf(ma, t0) : ma;
-                mb = (2 * cc > kb) ? fmaxf(mb, t0) : mb;
-                ma = (2 * cc + 1 < kb) ? fmaxf(ma, t1) : ma;
-                mb = (2 * cc + 1 > kb) ? fmaxf(mb, t1) : mb;
-              }
+              float mb = doc_ninit;
+              auto route = [&](const uint32_t (&v)[32], int c) {
+                const float t = tree32(v);
+                mm = (c < kb) ? fmaxf(mm, t) : mm;
+                mb = (c > kb) ? fmaxf(mb, t) : mb;
+              };
+              uint32_t va[32], vb[32], vc[32], vd[32];
+              tmem_ld_x32(taddr, va);
+              tmem_ld_x32(taddr + 32, vb);
+              tmem_ld_wait();
+              reg_fence32(va);
+              reg_fence32(vb);
+              tmem_ld_x32(taddr + 64, vc);
+              tmem_ld_x32(taddr + 96, vd);
+              route(va, 0);
+              route(vb, 1);
+              tmem_ld_wait();
+              reg_fence32(vc);
+              reg_fence32(vd);
+              tmem_ld_x32(taddr + 128, va);
+              tmem_ld_x32(taddr + 160, vb);
+              route(vc, 2);
+              route(vd, 3);
+              tmem_ld_wait();
+              reg_fence32(va);
+              reg_fence32(vb);
+              tmem_ld_x32(taddr + 192, vc);
+              tmem_ld_x32(taddr + 224, vd);
+              route(va, 4);
+              route(vb, 5);
+              tmem_ld_wait();
+              reg_fence32(vc);
+              reg_fence32(vd);
+              tmem_ld_x32(taddr + kb * 32, va);  // the boundary chunk again
+              route(vc, 6);
+              route(vd, 7);
+              tmem_ld_wait();
+              reg_fence32(va);
+              release_acc();
               {
-                uint32_t v[32];
-                tmem_ld_x32(taddr + kb * 32, v);
-                tmem_ld_wait();
-                reg_fence32(v);
-                release_acc();
                 const int bl = b & 31;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                  const float x = __uint_as_float(v[i]);
-                  if (i < bl) ma = fmaxf(ma, x); else mb = fmaxf(mb, x);
+                  const float x = __uint_as_float(va[i]);
+                  if (i < bl) mm = fmaxf(mm, x); else mb = fmaxf(mb, x);
                 }
               }
-              mm = ma;
-              finish_doc();  // old document; cursor moves to the new one (its running max is mb)
+              finish_doc();  // old document (running max mm); the cursor moves to the new one, whose max is mb
               mm = mb;
               while (doc_end <= tile_end) finish_doc();
             } else {
@@ -534,12 +619,16 @@ maxsim_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             nxt = doc;
             nxt_row0 = doc_row0;
             nxt_end = doc_end;
+            nxt_nlen = doc_nlen;
+            nxt_ninit = doc_ninit;
             ++job;
           }
         }
         cur = nxt;
         cur_row0 = nxt_row0;
         cur_end = nxt_end;
+        cur_nlen = nxt_nlen;
+        cur_ninit = nxt_ninit;
       }
       d = run.e;
     }

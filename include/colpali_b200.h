@@ -54,6 +54,7 @@ int cpb_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
  * Tuning knobs for experiments (process-wide, not thread-safe against concurrent launches):
  *   "cluster"         0 = auto, 1 / 2 / 4 = CTAs per cluster sharing document tiles by TMA multicast
  *   "qtiles_per_cta"  0 = auto, 1 / 2     = resident 128-row query tiles per CTA
+ *   "mma_split"       5..8 (default 6): K-steps of a job issued before the next job's barrier waits
  *   "debug_flags"     profiling-only bits (upper 16), 0 in production
  */
 int cpb_set_option(const char* name, int value);

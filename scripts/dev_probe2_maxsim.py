@@ -12,16 +12,16 @@ for nd in (1024, 1030):
     d = F.normalize(torch.randn(1000, nd, 128, device=dev), dim=-1).bfloat16()
     bank = cb.DocBank.from_passages(d, dev); qb = cb.QueryBlock(q, dev)
     for cluster in (1, 2):
+      for name, dbg in (("normal", 0), ("noTMA", 0x20000), ("noEpi", 0x10000), ("noTMA+noEpi", 0x30000)):
         _lib.set_option("cluster", cluster)
-        _lib.set_option("debug_flags", 0x40000)
+        _lib.set_option("debug_flags", 0x40000 | dbg)
         for _ in range(5): s = cb.maxsim(qb, bank)
         torch.cuda.synchronize()
         f = s.flatten().double()
         tot = f[:296].view(148, 2)
         x = f[512:512 + 8 * 148].view(148, 8)
         jobs = x[:, 7]
-        print(f"Nd={nd} C={cluster}: CTA cycles mean {tot[:,0].mean():.0f} max {tot[:,0].max():.0f} clock {(tot[:,0]/tot[:,1]).mean():.3f} GHz; jobs/CTA {jobs.mean():.1f}")
-        print(f"   MMA issuer blocked: on TMA {x[:,0].mean():.0f}  on epilogue {x[:,1].mean():.0f} cycles/CTA")
         n2 = x[:, 6]
-        print(f"   epilogue per job: wait-for-MMA {(x[:,2]/jobs).mean():.0f}  hold(path1/3) {(x[:,3]/(jobs-n2)).mean():.0f}  hold(path2) {(x[:,5]/n2.clamp_min(1)).mean():.0f} (n={n2.mean():.1f})  post-release {(x[:,4]/jobs).mean():.0f}")
+        print(f"Nd={nd} C={cluster} {name:12s}: cycles/job {(tot[:,0]/jobs).mean():6.0f} (CTA mean {tot[:,0].mean():.0f} max {tot[:,0].max():.0f}, {(tot[:,0]/tot[:,1]).mean():.2f} GHz) | "
+              f"issuer blocked/job: TMA {(x[:,0]/jobs).mean():4.0f} epi {(x[:,1]/jobs).mean():4.0f} | epilogue/job: wait {(x[:,2]/jobs).mean():4.0f} hold {(x[:,3]/(jobs-n2)).mean():4.0f} hold2 {(x[:,5]/n2.clamp_min(1)).mean():4.0f} post {(x[:,4]/jobs).mean():4.0f}", flush=True)
 _lib.set_option("cluster", 0); _lib.set_option("debug_flags", 0)
