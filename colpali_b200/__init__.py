@@ -9,13 +9,23 @@ Public names mirror the reference (illuin-tech/colpali):
 from ._lib import ColpaliB200Error
 from .head import fused_head
 from .install import install, uninstall
-from .losses import ColbertLoss, ColbertModule, ColbertPairwiseCELoss
+from .losses import (
+    ColbertLoss,
+    ColbertModule,
+    ColbertNegativeCELoss,
+    ColbertPairwiseCELoss,
+    ColbertPairwiseNegativeCELoss,
+    ColbertSigmoidLoss,
+)
 from .scoring import DocBank, QueryBlock, maxsim, score_multi_vector, score_single_vector
 
 __all__ = [
     "ColbertLoss",
     "ColbertModule",
+    "ColbertNegativeCELoss",
     "ColbertPairwiseCELoss",
+    "ColbertPairwiseNegativeCELoss",
+    "ColbertSigmoidLoss",
     "ColpaliB200Error",
     "DocBank",
     "fused_head",

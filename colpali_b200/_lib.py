@@ -23,6 +23,7 @@ EXPORTED_SYMBOLS = (
     "cpb_maxsim_fwd",
     "cpb_maxsim_workspace_bytes",
     "cpb_colbert_loss_fwd",
+    "cpb_colbert_neg_loss_fwd",
     "cpb_maxsim_bwd",
     "cpb_head_fwd",
 )
@@ -33,6 +34,7 @@ CPB_HEAD_CLAMP_NORM = 1
 CPB_HEAD_SINGLE_ROUNDING = 2
 CPB_LOSS_CE = 0
 CPB_LOSS_PAIRWISE = 1
+CPB_LOSS_SIGMOID = 2
 
 _lib: Optional[ctypes.CDLL] = None
 
@@ -78,6 +80,12 @@ def load() -> ctypes.CDLL:
         c_vp, c_vp, c_i, c_i, c_i, c_i,  # d_scores, d_q, n_queries, nq_pad, n_docs, mode
         c_f, c_i, c_i, c_f, c_f, c_i,  # temperature, normalize, filter, threshold, factor, offset
         c_vp, c_vp, c_vp, c_vp,  # d_loss, d_grad_scores, d_bounds, stream
+    ]
+    lib.cpb_colbert_neg_loss_fwd.restype = c_i
+    lib.cpb_colbert_neg_loss_fwd.argtypes = [
+        c_vp, c_vp, c_vp, c_i, c_i, c_i, c_i, c_i,  # d_scores, d_neg_scores, d_q, n_queries, nq_pad, n_docs, n_neg, inner_mode
+        c_f, c_i, c_i, c_f, c_f, c_f, c_i,  # temperature, normalize, filter, threshold, factor, in_batch_weight, offset
+        c_vp, c_vp, c_vp, c_vp,  # d_loss, d_grad_scores, d_grad_neg_scores, stream
     ]
     lib.cpb_maxsim_bwd.restype = c_i
     lib.cpb_maxsim_bwd.argtypes = [

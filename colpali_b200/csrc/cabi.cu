@@ -31,6 +31,7 @@ int g_opt_cluster = 0;
 int g_opt_qtiles_per_cta = 0;
 unsigned g_opt_debug_flags = 0;
 int g_opt_mma_split = 6;
+int g_opt_dbg_delay = 0;
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -89,9 +90,15 @@ struct DevInfo {
 int current_device_info(DevInfo* out) {
   int dev = 0;
   CPB_CUDA(cudaGetDevice(&dev));
+  static DevInfo cache[64];
+  if (dev >= 0 && dev < 64 && cache[dev].sm_count > 0) {
+    *out = cache[dev];
+    return CPB_OK;
+  }
   CPB_CUDA(cudaDeviceGetAttribute(&out->sm_count, cudaDevAttrMultiProcessorCount, dev));
   CPB_CUDA(cudaDeviceGetAttribute(&out->major, cudaDevAttrComputeCapabilityMajor, dev));
   CPB_CUDA(cudaDeviceGetAttribute(&out->minor, cudaDevAttrComputeCapabilityMinor, dev));
+  if (dev >= 0 && dev < 64) cache[dev] = *out;
   return CPB_OK;
 }
 
@@ -131,6 +138,8 @@ int cpb_set_option(const char* name, int value) {
   } else if (!strcmp(name, "mma_split")) {
     if (value < 5 || value > 8) return fail(CPB_E_INVALID, "mma_split must be 5..8");
     g_opt_mma_split = value;
+  } else if (!strcmp(name, "debug_delay")) {
+    g_opt_dbg_delay = value;
   } else if (!strcmp(name, "debug_flags")) {
     g_opt_debug_flags = static_cast<unsigned>(value) & 0xffff0000u;
   } else {
@@ -188,11 +197,17 @@ int cpb_maxsim_fwd(const void* d_q, int n_queries, int nq_pad, const void* d_doc
   // not a multiple of 4, so they are opt-in.
   int cluster = (p.q_groups >= 2) ? 2 : 1;
   if (g_opt_cluster == 1 || g_opt_cluster == 2 || g_opt_cluster == 4) cluster = g_opt_cluster;
-  int max_clusters = cpb::maxsim_max_clusters(R, cluster);
+  // co-resident cluster count is a property of (device, R, cluster): query the driver once
+  static int occ_cache[3][5] = {};
+  auto max_clusters_cached = [&](int r, int c) {
+    if (occ_cache[r][c] == 0) occ_cache[r][c] = cpb::maxsim_max_clusters(r, c);
+    return occ_cache[r][c];
+  };
+  int max_clusters = max_clusters_cached(R, cluster);
   if (max_clusters <= 0) {
     if (cluster == 1) return fail(CPB_E_CUDA, "kernel cannot be resident on this device (shared memory?)");
     cluster = 1;
-    max_clusters = cpb::maxsim_max_clusters(R, 1);
+    max_clusters = max_clusters_cached(R, 1);
     if (max_clusters <= 0) return fail(CPB_E_CUDA, "kernel cannot be resident on this device (shared memory?)");
   }
   p.cluster = cluster;
@@ -203,6 +218,7 @@ int cpb_maxsim_fwd(const void* d_q, int n_queries, int nq_pad, const void* d_doc
   p.doc_parts = parts;
   p.flags = flags | g_opt_debug_flags;
   p.mma_split = g_opt_mma_split;
+  p.dbg_delay = g_opt_dbg_delay;
   const int grid = p.group_sets * p.doc_parts * cluster;
 
   CUtensorMap tq, td, tt;
@@ -220,13 +236,18 @@ int cpb_maxsim_fwd(const void* d_q, int n_queries, int nq_pad, const void* d_doc
   return CPB_OK;
 }
 
-int cpb_colbert_loss_fwd(const float* d_scores, const void* d_q, int n_queries, int nq_pad, int n_docs, int mode,
+static int loss_fwd_impl(const float* d_scores, const void* d_q, int n_queries, int nq_pad, int n_docs, int mode,
                          float temperature, int normalize_scores, int pos_aware_negative_filtering,
-                         float filter_threshold, float filter_factor, int offset, float* d_loss, float* d_grad_scores,
+                         float filter_threshold, float filter_factor, int offset, const float* d_neg_scores, int n_neg,
+                         float in_batch_weight, float* d_loss, float* d_grad_scores, float* d_grad_neg,
                          float* d_bounds, void* stream_) {
   if (n_queries <= 0 || n_docs <= 0) return fail(CPB_E_INVALID, "n_queries=%d and n_docs=%d must be positive", n_queries, n_docs);
   if (nq_pad <= 0 || (nq_pad % 32) != 0) return fail(CPB_E_INVALID, "nq_pad=%d must be a positive multiple of 32", nq_pad);
-  if (mode != CPB_LOSS_CE && mode != CPB_LOSS_PAIRWISE) return fail(CPB_E_INVALID, "unknown loss mode %d", mode);
+  if (mode != CPB_LOSS_CE && mode != CPB_LOSS_PAIRWISE && mode != CPB_LOSS_SIGMOID) return fail(CPB_E_INVALID, "unknown loss mode %d", mode);
+  if (mode == CPB_LOSS_SIGMOID && (n_docs != n_queries || offset != 0))
+    return fail(CPB_E_INVALID, "the sigmoid loss needs n_docs == n_queries and offset == 0 (got %d, %d, %d)", n_docs, n_queries, offset);
+  if (d_neg_scores && (n_neg <= 0 || mode == CPB_LOSS_SIGMOID || in_batch_weight < 0.f || in_batch_weight > 1.f))
+    return fail(CPB_E_INVALID, "bad explicit-negative arguments (n_neg=%d, mode=%d, weight=%g)", n_neg, mode, static_cast<double>(in_batch_weight));
   if (offset < 0 || offset + n_queries > n_docs)
     return fail(CPB_E_INVALID, "positive index out of range: offset=%d + n_queries=%d > n_docs=%d", offset, n_queries, n_docs);
   if (!(temperature > 0.f)) return fail(CPB_E_INVALID, "temperature must be positive");
@@ -247,8 +268,32 @@ int cpb_colbert_loss_fwd(const float* d_scores, const void* d_q, int n_queries, 
   p.temperature = temperature;
   p.filter_threshold = filter_threshold;
   p.filter_factor = filter_factor;
+  p.neg_scores = d_neg_scores;
+  p.grad_neg = d_grad_neg;
+  p.n_neg = n_neg;
+  p.in_batch_weight = in_batch_weight;
   CPB_CUDA(cpb::colbert_loss_launch(p, static_cast<cudaStream_t>(stream_)));
   return CPB_OK;
+}
+
+int cpb_colbert_loss_fwd(const float* d_scores, const void* d_q, int n_queries, int nq_pad, int n_docs, int mode,
+                         float temperature, int normalize_scores, int pos_aware_negative_filtering,
+                         float filter_threshold, float filter_factor, int offset, float* d_loss, float* d_grad_scores,
+                         float* d_bounds, void* stream_) {
+  return loss_fwd_impl(d_scores, d_q, n_queries, nq_pad, n_docs, mode, temperature, normalize_scores,
+                       pos_aware_negative_filtering, filter_threshold, filter_factor, offset, nullptr, 0, 1.f, d_loss,
+                       d_grad_scores, nullptr, d_bounds, stream_);
+}
+
+int cpb_colbert_neg_loss_fwd(const float* d_scores, const float* d_neg_scores, const void* d_q, int n_queries,
+                             int nq_pad, int n_docs, int n_neg, int inner_mode, float temperature,
+                             int normalize_scores, int pos_aware_negative_filtering, float filter_threshold,
+                             float filter_factor, float in_batch_term_weight, int offset, float* d_loss,
+                             float* d_grad_scores, float* d_grad_neg_scores, void* stream_) {
+  if (!d_neg_scores) return fail(CPB_E_INVALID, "null device pointer");
+  return loss_fwd_impl(d_scores, d_q, n_queries, nq_pad, n_docs, inner_mode, temperature, normalize_scores,
+                       pos_aware_negative_filtering, filter_threshold, filter_factor, offset, d_neg_scores, n_neg,
+                       in_batch_term_weight, d_loss, d_grad_scores, d_grad_neg_scores, nullptr, stream_);
 }
 
 int cpb_maxsim_bwd(const float* d_grad_scores, const float* d_grad_out, const int32_t* d_argmax, const void* d_q,

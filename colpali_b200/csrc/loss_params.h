@@ -13,9 +13,15 @@ struct LossParams {
   float* grad;                // [B, C] dLoss/dScores (raw), or nullptr
   float* bounds;              // [2] min / max of the normalised scores, or nullptr
   int B, C, nq_pad, offset;
-  int mode;                   // 0 = cross entropy (ColbertLoss), 1 = pairwise softplus (ColbertPairwiseCELoss)
+  int mode;                   // 0 = cross entropy (ColbertLoss), 1 = pairwise softplus (ColbertPairwiseCELoss),
+                              // 2 = sigmoid (ColbertSigmoidLoss, needs C == B and offset == 0)
   int normalize, filter;
   float temperature, filter_threshold, filter_factor;
+  // explicit negatives (ColbertNegativeCELoss / ColbertPairwiseNegativeCELoss); neg_scores == nullptr: none
+  const float* neg_scores;    // [B, B * n_neg] raw sums of every query against every query's negatives
+  float* grad_neg;            // [B, B * n_neg] or nullptr
+  int n_neg;
+  float in_batch_weight;      // weight of the in-batch term (mode 0 / 1) when negatives are present
 };
 
 struct BwdParams {

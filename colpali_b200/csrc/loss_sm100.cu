@@ -50,6 +50,9 @@ __global__ void __launch_bounds__(1024, 1) colbert_loss_kernel(const LossParams 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nwarps = blockDim.x >> 5;
   float loss_acc = 0.f, mn = INFINITY, mx = -INFINITY;
+  const bool has_neg = p.neg_scores != nullptr;
+  const float w_ib = has_neg ? p.in_batch_weight : 1.f;     // late_interaction_losses.py:248-250 / :394-396
+  const float w_out = has_neg ? 1.f - p.in_batch_weight : 0.f;
 
   for (int b = warp; b < p.B; b += nwarps) {
     // lengths = (q[:, :, 0] != 0).sum(1)                       late_interaction_losses.py:152
@@ -63,7 +66,7 @@ __global__ void __launch_bounds__(1024, 1) colbert_loss_kernel(const LossParams 
     const float pos = row[pidx] * inv;
     const float thr = p.filter_threshold * pos;                 // :101-104
     const float invT = 1.f / p.temperature;
-    const float invB = 1.f / static_cast<float>(p.B);
+    const float invB = w_ib / static_cast<float>(p.B);
 
     // filtered score of column c and the factor it was multiplied by      (:105-107)
     auto filtered = [&](int c, float& f) {
@@ -90,7 +93,7 @@ __global__ void __launch_bounds__(1024, 1) colbert_loss_kernel(const LossParams 
       }
       se = warp_sum_f(se);
       const float lse = m + __logf(se);
-      loss_acc += lse - pos * invT;  // the positive column is never filtered
+      loss_acc += w_ib * (lse - pos * invT);  // the positive column is never filtered
       if (p.grad != nullptr) {
         float* g = p.grad + static_cast<int64_t>(b) * p.C;
         for (int c = lane; c < p.C; c += 32) {
@@ -100,7 +103,7 @@ __global__ void __launch_bounds__(1024, 1) colbert_loss_kernel(const LossParams 
           g[c] = (sm - (c == pidx ? 1.f : 0.f)) * invT * f * inv * invB;
         }
       }
-    } else {
+    } else if (p.mode == 1) {
       // pos = diagonal(offset); top-2 of the row; neg = top1 == pos ? top2 : top1      (:309-311)
       Top t1{-INFINITY, 0x7fffffff}, t2{-INFINITY, 0x7fffffff};
       for (int c = lane; c < p.C; c += 32) {
@@ -129,7 +132,7 @@ __global__ void __launch_bounds__(1024, 1) colbert_loss_kernel(const LossParams 
       }
       const Top neg = (t1.v == pos) ? t2 : t1;
       const float x = (neg.v - pos) * invT;
-      loss_acc += fmaxf(x, 0.f) + log1pf(__expf(-fabsf(x)));   // softplus                 (:313)
+      loss_acc += w_ib * (fmaxf(x, 0.f) + log1pf(__expf(-fabsf(x))));   // softplus           (:313)
       if (p.grad != nullptr) {
         const float sig = 1.f / (1.f + __expf(-x));
         float* g = p.grad + static_cast<int64_t>(b) * p.C;
@@ -142,6 +145,43 @@ __global__ void __launch_bounds__(1024, 1) colbert_loss_kernel(const LossParams 
           g[c] = v;
         }
       }
+    } else {
+      // sigmoid loss: softplus(-s/T * m), m = +1 on the diagonal, -1 elsewhere; mean over B*B   (:452-465)
+      float* g = p.grad ? p.grad + static_cast<int64_t>(b) * p.C : nullptr;
+      const float invBB = invB / static_cast<float>(p.C);
+      float part = 0.f;  // per-lane partial sum, reduced below (loss_acc must stay warp-uniform)
+      for (int c = lane; c < p.C; c += 32) {
+        float f;
+        const float s = filtered(c, f);
+        mn = fminf(mn, row[c] * inv);
+        mx = fmaxf(mx, row[c] * inv);
+        const float msk = (c == b) ? 1.f : -1.f;
+        const float z = -s * invT * msk;
+        part += (fmaxf(z, 0.f) + log1pf(__expf(-fabsf(z)))) / static_cast<float>(p.C);
+        if (g) g[c] = -msk * invT * f * inv * invBB / (1.f + __expf(-z));
+      }
+      loss_acc += warp_sum_f(part);
+    }
+
+    if (has_neg) {
+      // softplus((neg - pos) / T) over this query's own negatives, mean over B * n_neg          (:235-246, :381-392)
+      const float* nrow = p.neg_scores + static_cast<int64_t>(b) * p.B * p.n_neg;
+      float* gn = p.grad_neg ? p.grad_neg + static_cast<int64_t>(b) * p.B * p.n_neg : nullptr;
+      const float scale = w_out / (static_cast<float>(p.B) * static_cast<float>(p.n_neg));
+      float gpos = 0.f, part = 0.f;
+      for (int c = lane; c < p.B * p.n_neg; c += 32) {
+        float gv = 0.f;
+        if (c / p.n_neg == b) {
+          const float x = (nrow[c] * inv - pos) * invT;
+          part += (fmaxf(x, 0.f) + log1pf(__expf(-fabsf(x)))) * w_out / static_cast<float>(p.n_neg);
+          gv = scale * invT * inv / (1.f + __expf(-x));
+          gpos -= gv;
+        }
+        if (gn) gn[c] = gv;
+      }
+      gpos = warp_sum_f(gpos);
+      loss_acc += warp_sum_f(part);
+      if (p.grad != nullptr && lane == (pidx & 31)) p.grad[static_cast<int64_t>(b) * p.C + pidx] += gpos;
     }
   }
 
@@ -193,6 +233,7 @@ __global__ void __launch_bounds__(256) maxsim_bwd_dq_kernel(const BwdParams p) {
     const int idx = __ldg(p.argmax + static_cast<int64_t>(c) * p.q_rows + row);
     if (idx < 0) continue;
     const float w = __ldg(g + c) * scale;
+    if (w == 0.f) continue;  // block-diagonal gradients of the explicit-negative losses are mostly zero
     const uint2 raw = __ldg(reinterpret_cast<const uint2*>(p.docs + (static_cast<int64_t>(__ldg(p.doc_start + c)) + idx) * 128) + lane);
     const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&raw.x);
     const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);

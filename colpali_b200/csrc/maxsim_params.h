@@ -29,6 +29,7 @@ struct MaxSimParams {
   int group_sets;  // ceil(q_groups / cluster)
   int doc_parts;   // document partitions; grid = group_sets * doc_parts * cluster
   uint32_t flags;
+  int dbg_delay;   // profiling only: cycles the epilogue holds an unread accumulator in CPB_DBG_SKIP_EPILOGUE mode
   int mma_split;   // K-steps of a job issued before the next job's barrier waits (5..8)
 };
 

@@ -484,6 +484,11 @@ maxsim_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
               }
             }
             if (skip) {
+              if (p.dbg_delay > 0) {  // profiling aid: hold the (unread) accumulator for a fixed number of cycles
+                const long long t_start = clock64();
+                while (clock64() - t_start < p.dbg_delay) {
+                }
+              }
               release_acc();
               while (doc_end <= tile_end) {  // advance the cursor without reading the accumulator
                 ++doc;
@@ -686,8 +691,12 @@ template <int R, bool kArgmax>
 static cudaError_t launch_variant(const CUtensorMap& tq, const CUtensorMap& td, const CUtensorMap& tt,
                                   const MaxSimParams& p, int grid, cudaStream_t stream) {
   auto kern = maxsim_fwd_kernel<R, kArgmax>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<R>::kAlloc);
-  if (e != cudaSuccess) return e;
+  static bool attr_set = false;  // per instantiation; the attribute is sticky for the process (single device type)
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<R>::kAlloc);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
   cudaLaunchConfig_t cfg{};
   cudaLaunchAttribute attr[1];
   fill_cluster_cfg<R>(cfg, attr, grid, p.cluster, stream);

@@ -18,7 +18,8 @@ from typing import Dict, Tuple
 
 _saved: Dict[Tuple[str, str], object] = {}
 
-_LOSS_NAMES = ("ColbertModule", "ColbertLoss", "ColbertPairwiseCELoss")
+_LOSS_NAMES = ("ColbertModule", "ColbertLoss", "ColbertPairwiseCELoss", "ColbertNegativeCELoss",
+               "ColbertPairwiseNegativeCELoss", "ColbertSigmoidLoss")
 
 
 def _swap(obj, name: str, new) -> None:

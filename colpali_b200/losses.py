@@ -5,6 +5,8 @@ Mirrors ``colpali_engine/loss/late_interaction_losses.py`` (reference @ 9be8f19)
 * ``ColbertModule``           :6-107   (hyper-parameters + the small helper methods, kept for API parity)
 * ``ColbertLoss``             :110-164 (InfoNCE over in-batch documents)
 * ``ColbertPairwiseCELoss``   :255-313 (softplus(hardest in-batch negative - positive))
+* ``ColbertNegativeCELoss``   :167-252, ``ColbertPairwiseNegativeCELoss`` :316-398 (explicit negatives)
+* ``ColbertSigmoidLoss``      :401-465
 
 Same constructor keyword arguments, same ``forward(query_embeddings, doc_embeddings, offset=0)``.  The
 ``einsum("bnd,csd->bcns")`` / ``amax`` / ``sum`` of :153-154 and everything after it run as
@@ -92,6 +94,83 @@ class _InBatchLossFn(torch.autograd.Function):
         if want_d:
             grad_d = dd.view(d_shape[0], d_shape[1], EMBED_DIM)[:, :, : d_shape[2]].to(d_dtype)
         return grad_q, grad_d, None, None, None, None, None, None, None, None
+
+
+class _NegLossFn(torch.autograd.Function):
+    """Explicit-negative losses: one dense MaxSim launch against the (gathered) positives, one against the flattened
+    negatives of all queries (only the block diagonal is used), one loss kernel for both score matrices."""
+
+    @staticmethod
+    def forward(ctx, q, d, neg, offset, inner_mode, temperature, normalize, filt, thr, factor, weight):
+        if q.dim() != 3 or d.dim() != 3 or neg.dim() != 4:
+            raise ValueError("expected [B, N_q, D], [C, N_d, D] and [B, n_neg, N_neg, D] embeddings, got "
+                             f"{tuple(q.shape)} / {tuple(d.shape)} / {tuple(neg.shape)}")
+        if neg.shape[0] != q.shape[0]:
+            raise ValueError(f"{neg.shape[0]} negative groups for {q.shape[0]} queries")
+        dev = q.device
+        if dev.type != "cuda" or d.device != dev or neg.device != dev:
+            raise _lib.ColpaliB200Error("colpali_b200 losses need all embeddings on the same CUDA device")
+        lib = _lib.load()
+        qb = QueryBlock(q.detach(), dev)
+        bank = DocBank.from_passages(d.detach(), dev)
+        b, n_neg = neg.shape[0], neg.shape[1]
+        nbank = DocBank.from_passages(neg.detach().reshape(b * n_neg, neg.shape[2], neg.shape[3]), dev)
+        need_grad = any(ctx.needs_input_grad[:3])
+        if need_grad:
+            s_pos, am_pos = maxsim(qb, bank, want_argmax=True)
+            s_neg, am_neg = maxsim(qb, nbank, want_argmax=True)
+        else:
+            s_pos, s_neg, am_pos, am_neg = maxsim(qb, bank), maxsim(qb, nbank), None, None
+        c = bank.n_docs
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        g_pos = torch.empty(b, c, dtype=torch.float32, device=dev) if need_grad else None
+        g_neg = torch.empty(b, b * n_neg, dtype=torch.float32, device=dev) if need_grad else None
+        with torch.cuda.device(dev):
+            rc = lib.cpb_colbert_neg_loss_fwd(
+                s_pos.data_ptr(), s_neg.data_ptr(), qb.flat.data_ptr(), b, qb.nq_pad, c, n_neg, inner_mode,
+                float(temperature), int(normalize), int(filt), float(thr), float(factor), float(weight), int(offset),
+                loss.data_ptr(), g_pos.data_ptr() if need_grad else None, g_neg.data_ptr() if need_grad else None,
+                torch.cuda.current_stream(dev).cuda_stream,
+            )
+        _lib.check(rc, "cpb_colbert_neg_loss_fwd")
+        _lib.count_launches(1)
+        if need_grad:
+            ctx.save_for_backward(qb.flat, bank.flat, bank.start, am_pos, g_pos, nbank.flat, nbank.start, am_neg, g_neg)
+            ctx.meta = (b, qb.nq_pad, c, b * n_neg, tuple(q.shape), tuple(d.shape), tuple(neg.shape), q.dtype, d.dtype, neg.dtype)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        q_flat, d_flat, d_start, am_pos, g_pos, n_flat, n_start, am_neg, g_neg = ctx.saved_tensors
+        b, nq_pad, c, cn, q_shape, d_shape, n_shape, q_dtype, d_dtype, n_dtype = ctx.meta
+        dev = q_flat.device
+        lib = _lib.load()
+        want_q, want_d, want_n = ctx.needs_input_grad[:3]
+        go = grad_out.detach().to(torch.float32).reshape(1).contiguous()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+
+        def bwd(g, am, flat, start, n_docs, need_dq, need_dd):
+            dq = torch.empty(b * nq_pad, EMBED_DIM, dtype=torch.float32, device=dev) if need_dq else None
+            dd = torch.zeros(flat.shape[0], EMBED_DIM, dtype=torch.float32, device=dev) if need_dd else None
+            if need_dq or need_dd:
+                with torch.cuda.device(dev):
+                    rc = lib.cpb_maxsim_bwd(g.data_ptr(), go.data_ptr(), am.data_ptr(), q_flat.data_ptr(), b, nq_pad,
+                                            flat.data_ptr(), flat.shape[0], start.data_ptr(), n_docs,
+                                            dq.data_ptr() if need_dq else None, dd.data_ptr() if need_dd else None, stream)
+                _lib.check(rc, "cpb_maxsim_bwd")
+                _lib.count_launches(int(need_dq) + int(need_dd))
+            return dq, dd
+
+        dq1, dd = bwd(g_pos, am_pos, d_flat, d_start, c, want_q, want_d)
+        dq2, dn = bwd(g_neg, am_neg, n_flat, n_start, cn, want_q, want_n)
+        grad_q = grad_d = grad_n = None
+        if want_q:
+            grad_q = (dq1 + dq2).view(b, nq_pad, EMBED_DIM)[:, : q_shape[1], : q_shape[2]].to(q_dtype)
+        if want_d:
+            grad_d = dd.view(d_shape[0], d_shape[1], EMBED_DIM)[:, :, : d_shape[2]].to(d_dtype)
+        if want_n:
+            grad_n = dn.view(n_shape[0], n_shape[1], n_shape[2], EMBED_DIM)[..., : n_shape[3]].to(n_dtype)
+        return (grad_q, grad_d, grad_n) + (None,) * 8
 
 
 class ColbertModule(torch.nn.Module):
@@ -186,3 +265,81 @@ class ColbertPairwiseCELoss(ColbertModule):
 
     def forward(self, query_embeddings: torch.Tensor, doc_embeddings: torch.Tensor, offset: int = 0) -> torch.Tensor:
         return self._fused_in_batch_loss(_lib.CPB_LOSS_PAIRWISE, query_embeddings, doc_embeddings, offset)
+
+
+class ColbertSigmoidLoss(ColbertModule):
+    """Sigmoid loss over the in-batch score matrix (late_interaction_losses.py:401-465).  As in the reference the score
+    matrix must be square and the positives sit on the diagonal (``offset`` other than 0 indexes out of range there)."""
+
+    def __init__(self, temperature: float = 0.02, normalize_scores: bool = True, use_smooth_max: bool = False,
+                 pos_aware_negative_filtering: bool = False, max_batch_size: int = 1024, tau: float = 0.1,
+                 norm_tol: float = 1e-3, filter_threshold: float = 0.95, filter_factor: float = 0.5):
+        super().__init__(max_batch_size, tau, norm_tol, filter_threshold, filter_factor)
+        self.temperature = temperature
+        self.normalize_scores = normalize_scores
+        self.use_smooth_max = use_smooth_max
+        self.pos_aware_negative_filtering = pos_aware_negative_filtering
+        self.ce_loss = torch.nn.CrossEntropyLoss()
+
+    def forward(self, query_embeddings: torch.Tensor, doc_embeddings: torch.Tensor, offset: int = 0) -> torch.Tensor:
+        if offset != 0 or query_embeddings.shape[0] != doc_embeddings.shape[0]:
+            raise ValueError("ColbertSigmoidLoss needs as many documents as queries and offset == 0 "
+                             f"(got {query_embeddings.shape[0]} queries, {doc_embeddings.shape[0]} documents, offset {offset})")
+        return self._fused_in_batch_loss(_lib.CPB_LOSS_SIGMOID, query_embeddings, doc_embeddings, offset)
+
+
+class _NegativeLossBase(ColbertModule):
+    _inner_mode = _lib.CPB_LOSS_CE
+
+    def __init__(self, temperature, normalize_scores, use_smooth_max, pos_aware_negative_filtering, in_batch_term_weight,
+                 max_batch_size, tau, norm_tol, filter_threshold, filter_factor):
+        super().__init__(max_batch_size, tau, norm_tol, filter_threshold, filter_factor)
+        self.temperature = temperature
+        self.normalize_scores = normalize_scores
+        self.use_smooth_max = use_smooth_max
+        self.pos_aware_negative_filtering = pos_aware_negative_filtering
+        self.in_batch_term_weight = in_batch_term_weight
+        assert in_batch_term_weight >= 0, "in_batch_term_weight must be non-negative"
+        assert in_batch_term_weight <= 1, "in_batch_term_weight must be less than 1"
+
+    def forward(self, query_embeddings: torch.Tensor, doc_embeddings: torch.Tensor, neg_doc_embeddings: torch.Tensor,
+                offset: int = 0) -> torch.Tensor:
+        if self.use_smooth_max:
+            raise NotImplementedError("use_smooth_max=True is not implemented in the fused sm_100a path yet")
+        return _NegLossFn.apply(query_embeddings, doc_embeddings, neg_doc_embeddings, int(offset), self._inner_mode,
+                                self.temperature, self.normalize_scores, self.pos_aware_negative_filtering,
+                                self.filter_threshold, self.filter_factor, self.in_batch_term_weight)
+
+
+class ColbertNegativeCELoss(_NegativeLossBase):
+    """InfoNCE-style loss with explicit negative documents (late_interaction_losses.py:167-252):
+    ``(1 - w) * softplus((neg - pos) / T).mean() + w * ColbertLoss``."""
+
+    _inner_mode = _lib.CPB_LOSS_CE
+
+    def __init__(self, temperature: float = 0.02, normalize_scores: bool = True, use_smooth_max: bool = False,
+                 pos_aware_negative_filtering: bool = False, in_batch_term_weight: float = 0.5,
+                 max_batch_size: int = 1024, tau: float = 0.1, norm_tol: float = 1e-3, filter_threshold: float = 0.95,
+                 filter_factor: float = 0.5):
+        super().__init__(temperature, normalize_scores, use_smooth_max, pos_aware_negative_filtering,
+                         in_batch_term_weight, max_batch_size, tau, norm_tol, filter_threshold, filter_factor)
+        self.ce_loss = torch.nn.CrossEntropyLoss()
+        self.inner_loss = ColbertLoss(temperature, normalize_scores, use_smooth_max, pos_aware_negative_filtering,
+                                      max_batch_size, tau, norm_tol, filter_threshold, filter_factor)  # parity (:203-213)
+
+
+class ColbertPairwiseNegativeCELoss(_NegativeLossBase):
+    """Pairwise loss with explicit negatives (late_interaction_losses.py:316-398):
+    ``(1 - w) * softplus((neg - pos) / T).mean() + w * ColbertPairwiseCELoss``."""
+
+    _inner_mode = _lib.CPB_LOSS_PAIRWISE
+
+    def __init__(self, temperature: float = 0.02, normalize_scores: bool = True, use_smooth_max: bool = False,
+                 pos_aware_negative_filtering: bool = False, in_batch_term_weight: float = 0.5,
+                 max_batch_size: int = 1024, tau: float = 0.1, norm_tol: float = 1e-3, filter_threshold: float = 0.95,
+                 filter_factor: float = 0.5):
+        super().__init__(temperature, normalize_scores, use_smooth_max, pos_aware_negative_filtering,
+                         in_batch_term_weight, max_batch_size, tau, norm_tol, filter_threshold, filter_factor)
+        self.inner_pairwise = ColbertPairwiseCELoss(temperature, normalize_scores, use_smooth_max,
+                                                    pos_aware_negative_filtering, max_batch_size, tau, norm_tol,
+                                                    filter_threshold, filter_factor)  # parity (:349-359)

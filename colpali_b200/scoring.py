@@ -75,6 +75,11 @@ class QueryBlock:
             raise ValueError("No queries provided")
         self.n = n
         self.nq_pad = max(32, (nq + 31) // 32 * 32)
+        self.device = device
+        if (isinstance(qs, torch.Tensor) and qs.device == device and qs.dtype == torch.bfloat16 and qs.is_contiguous()
+                and nq == self.nq_pad and qs.shape[2] == EMBED_DIM and qs.data_ptr() % 16 == 0):
+            self.flat = qs.view(n * nq, EMBED_DIM)  # already in kernel layout: zero copy
+            return
         flat = torch.zeros(n, self.nq_pad, EMBED_DIM, dtype=torch.bfloat16, device=device)
         if isinstance(qs, torch.Tensor):
             flat[:, :nq] = _pad_dim(qs.to(device, non_blocking=True))
@@ -83,7 +88,22 @@ class QueryBlock:
                 if lens[i]:
                     flat[i, : lens[i]] = _pad_dim(q.to(device, non_blocking=True))
         self.flat = flat.view(n * self.nq_pad, EMBED_DIM)
-        self.device = device
+
+
+_DENSE_LAYOUT_CACHE: dict = {}
+
+
+def _dense_layout(n: int, length: int, device: torch.device):
+    """(start, len) int32 device arrays of a dense [n, length, dim] bank; cached, they only depend on the shape."""
+    key = (n, length, str(device))
+    hit = _DENSE_LAYOUT_CACHE.get(key)
+    if hit is None:
+        if len(_DENSE_LAYOUT_CACHE) > 64:
+            _DENSE_LAYOUT_CACHE.clear()
+        hit = (torch.arange(0, n * length, length, dtype=torch.int32, device=device),
+               torch.full((n,), length, dtype=torch.int32, device=device))
+        _DENSE_LAYOUT_CACHE[key] = hit
+    return hit
 
 
 class DocBank:
@@ -112,8 +132,7 @@ class DocBank:
                 raise ValueError(f"passage tensor must be [n, len, dim], got {tuple(ps.shape)}")
             n, L, _ = ps.shape
             flat = _pad_dim(ps.to(device, non_blocking=True)).reshape(n * L, EMBED_DIM).contiguous()
-            start = torch.arange(0, n * L, L, dtype=torch.int32, device=device)
-            length = torch.full((n,), L, dtype=torch.int32, device=device)
+            start, length = _dense_layout(n, L, device)
             return DocBank(flat, start, length, None, contiguous=True)  # equal lengths: the reference pads nothing
         lens = [int(p.shape[0]) for p in ps]
         n = len(ps)

@@ -95,6 +95,7 @@ int64_t cpb_maxsim_workspace_bytes(int n_queries, int nq_pad, int n_docs);
 /* loss modes of cpb_colbert_loss_fwd */
 #define CPB_LOSS_CE 0       /* ColbertLoss: cross entropy over in-batch documents          */
 #define CPB_LOSS_PAIRWISE 1 /* ColbertPairwiseCELoss: softplus(hardest negative - positive) */
+#define CPB_LOSS_SIGMOID 2  /* ColbertSigmoidLoss (late_interaction_losses.py:431-465): n_docs == n_queries, offset 0 */
 
 /*
  * In-batch-negative loss on a [n_queries, n_docs] matrix of raw MaxSim sums, with its gradient.
@@ -113,6 +114,25 @@ int cpb_colbert_loss_fwd(const float* d_scores, const void* d_q, int n_queries, 
                          float temperature, int normalize_scores, int pos_aware_negative_filtering,
                          float filter_threshold, float filter_factor, int offset,
                          float* d_loss, float* d_grad_scores, float* d_bounds, void* stream);
+
+/*
+ * Losses with explicit negative documents.
+ *   replaces: ColbertNegativeCELoss.forward          colpali_engine/loss/late_interaction_losses.py:215-252
+ *             ColbertPairwiseNegativeCELoss.forward  colpali_engine/loss/late_interaction_losses.py:361-398
+ *   loss = (1 - w) * mean_{b,l} softplus((neg[b,l] - pos[b]) / T)  +  w * in_batch_loss(inner_mode)
+ *   pos[b] = scores[b, b + offset];  neg[b, l] = neg_scores[b, b * n_neg + l]  (both length-normalised).
+ *
+ *   d_scores           fp32 [n_queries, n_docs]           raw MaxSim sums against the (gathered) positives
+ *   d_neg_scores       fp32 [n_queries, n_queries * n_neg] raw MaxSim sums of every query against every query's
+ *                      negatives (only the block diagonal is used; one dense MaxSim launch produces it)
+ *   inner_mode         CPB_LOSS_CE (ColbertNegativeCELoss) or CPB_LOSS_PAIRWISE (ColbertPairwiseNegativeCELoss)
+ *   d_grad_scores / d_grad_neg_scores   gradients of the loss w.r.t. both score matrices (zeros off the block diagonal)
+ */
+int cpb_colbert_neg_loss_fwd(const float* d_scores, const float* d_neg_scores, const void* d_q, int n_queries,
+                             int nq_pad, int n_docs, int n_neg, int inner_mode, float temperature,
+                             int normalize_scores, int pos_aware_negative_filtering, float filter_threshold,
+                             float filter_factor, float in_batch_term_weight, int offset,
+                             float* d_loss, float* d_grad_scores, float* d_grad_neg_scores, void* stream);
 
 /*
  * Backward of cpb_maxsim_fwd: given g = d loss / d scores and the argmax saved by the forward,

@@ -9,7 +9,9 @@ What it restates (reference = illuin-tech/colpali @ 9be8f19, paths relative to /
 * ``score_multi_vector_port``  <- colpali_engine/utils/processing_utils.py:132-187
   (batching :170/:175, zero padding :172/:176-178, einsum/max/sum :179, fp32 cast :186).
 * ``colbert_scores_port`` / ``colbert_loss_port`` / ``colbert_pairwise_ce_loss_port``
-  <- colpali_engine/loss/late_interaction_losses.py:73-107 (aggregate, filter), :140-164, :284-313.
+  <- colpali_engine/loss/late_interaction_losses.py:73-107 (aggregate, filter), :140-164, :284-313;
+  ``colbert_negative_ce_loss_port`` :215-252, ``colbert_pairwise_negative_ce_loss_port`` :361-398,
+  ``colbert_sigmoid_loss_port`` :431-465.
 * ``head_port`` <- colpali_engine/models/qwen2/colqwen2/modeling_colqwen2.py:65-74
   (and modernvbert's clamp variant, models/modernvbert/colvbert/modeling_colmodernvbert.py:59).
 * ``maxsim_f64`` -- an independent numpy float64 evaluation of sum_n max_s <q_n, d_s> used to
@@ -138,6 +140,56 @@ def colbert_pairwise_ce_loss_port(q: torch.Tensor, d: torch.Tensor, offset: int 
     top2 = scores.topk(2, dim=1).values
     neg = torch.where(top2[:, 0] == pos, top2[:, 1], top2[:, 0])
     return F.softplus((neg - pos) / temperature).mean()
+
+
+def _paired_neg_term(q, d, neg, offset, temperature, normalize_scores):
+    """softplus((neg - pos) / T).mean() over every query's own negatives, late_interaction_losses.py:234-246 / :380-392."""
+    lengths = (q[:, :, 0] != 0).sum(dim=1)
+    pos = torch.einsum("bnd,bsd->bns", q, d[offset : offset + neg.size(0)]).amax(dim=2).sum(dim=1)
+    negs = torch.einsum("bnd,blsd->blns", q, neg).amax(dim=3).sum(dim=2)
+    if normalize_scores:
+        pos = pos / lengths
+        negs = negs / lengths.unsqueeze(1)
+    return F.softplus((negs - pos.unsqueeze(1)) / temperature).mean()
+
+
+def colbert_negative_ce_loss_port(q, d, neg, offset: int = 0, temperature: float = 0.02, normalize_scores: bool = True,
+                                  pos_aware_negative_filtering: bool = False, in_batch_term_weight: float = 0.5,
+                                  filter_threshold: float = 0.95, filter_factor: float = 0.5) -> torch.Tensor:
+    """ColbertNegativeCELoss.forward, late_interaction_losses.py:215-252."""
+    loss = _paired_neg_term(q, d, neg, offset, temperature, normalize_scores)
+    if in_batch_term_weight > 0:
+        ib = colbert_loss_port(q, d, offset, temperature, normalize_scores, False, pos_aware_negative_filtering,
+                               0.1, filter_threshold, filter_factor)
+        loss = loss * (1 - in_batch_term_weight) + ib * in_batch_term_weight
+    return loss
+
+
+def colbert_pairwise_negative_ce_loss_port(q, d, neg, offset: int = 0, temperature: float = 0.02,
+                                           normalize_scores: bool = True, pos_aware_negative_filtering: bool = False,
+                                           in_batch_term_weight: float = 0.5, filter_threshold: float = 0.95,
+                                           filter_factor: float = 0.5) -> torch.Tensor:
+    """ColbertPairwiseNegativeCELoss.forward, late_interaction_losses.py:361-398."""
+    loss = _paired_neg_term(q, d, neg, offset, temperature, normalize_scores)
+    if in_batch_term_weight > 0:
+        ib = colbert_pairwise_ce_loss_port(q, d, offset, temperature, normalize_scores, False,
+                                           pos_aware_negative_filtering, 0.1, filter_threshold, filter_factor)
+        loss = loss * (1 - in_batch_term_weight) + ib * in_batch_term_weight
+    return loss
+
+
+def colbert_sigmoid_loss_port(q, d, offset: int = 0, temperature: float = 0.02, normalize_scores: bool = True,
+                              pos_aware_negative_filtering: bool = False, filter_threshold: float = 0.95,
+                              filter_factor: float = 0.5) -> torch.Tensor:
+    """ColbertSigmoidLoss.forward, late_interaction_losses.py:431-465."""
+    scores = colbert_scores_port(q, d, normalize_scores)
+    b = scores.size(0)
+    pos_idx = torch.arange(b, device=scores.device) + offset
+    if pos_aware_negative_filtering:
+        scores = _filter_high_negatives_port(scores, pos_idx, filter_threshold, filter_factor)
+    pos_mask = -torch.ones(b * b, device=scores.device)
+    pos_mask[pos_idx * (b + 1)] = 1.0
+    return F.softplus(-(scores.reshape(-1) / temperature) * pos_mask).mean()
 
 
 # ---------------------------------------------------------------------------------------------

@@ -24,7 +24,13 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, "/root/reference")
 sys.dont_write_bytecode = True
 
-from colpali_engine.loss import ColbertLoss, ColbertPairwiseCELoss  # noqa: E402  (reference)
+from colpali_engine.loss import (  # noqa: E402  (reference)
+    ColbertLoss,
+    ColbertNegativeCELoss,
+    ColbertPairwiseCELoss,
+    ColbertPairwiseNegativeCELoss,
+)
+from colpali_engine.loss.late_interaction_losses import ColbertSigmoidLoss  # noqa: E402
 from colpali_engine.utils.processing_utils import BaseVisualRetrieverProcessor as RefProc  # noqa: E402
 
 from oracle import li_oracle as O  # noqa: E402
@@ -150,6 +156,43 @@ def loss_small():
     print("loss_small ok")
 
 
+def loss_neg_small():
+    """Explicit-negative and sigmoid losses: B=4, C=6 (offset 1), n_neg=3, N_q=5, N_d=9 / 7, bf16-representable fp32."""
+    g = torch.Generator().manual_seed(6)
+    rnd = lambda *sh: torch.nn.functional.normalize(torch.randn(*sh, generator=g), dim=-1).bfloat16().float()  # noqa: E731
+    q, d, neg = rnd(4, 5, 16), rnd(6, 9, 16), rnd(4, 3, 7, 16)
+    q[2, 4:] = 0
+    d[1, :3] = 0
+    neg[0, 1, :2] = 0
+    out = {"q": q.numpy().copy(), "d": d.numpy().copy(), "neg": neg.numpy().copy()}
+    cases = (
+        ("negce", ColbertNegativeCELoss(), O.colbert_negative_ce_loss_port, {}),
+        ("negce_w0", ColbertNegativeCELoss(in_batch_term_weight=0.0), O.colbert_negative_ce_loss_port, dict(in_batch_term_weight=0.0)),
+        ("negce_filter", ColbertNegativeCELoss(pos_aware_negative_filtering=True, in_batch_term_weight=0.3),
+         O.colbert_negative_ce_loss_port, dict(pos_aware_negative_filtering=True, in_batch_term_weight=0.3)),
+        ("pairneg", ColbertPairwiseNegativeCELoss(), O.colbert_pairwise_negative_ce_loss_port, {}),
+        ("pairneg_t1", ColbertPairwiseNegativeCELoss(temperature=1.0, in_batch_term_weight=0.7),
+         O.colbert_pairwise_negative_ce_loss_port, dict(temperature=1.0, in_batch_term_weight=0.7)),
+    )
+    for name, mod, port, kw in cases:
+        qq, dd, nn = q.clone().requires_grad_(True), d.clone().requires_grad_(True), neg.clone().requires_grad_(True)
+        loss = mod(qq, dd, nn, offset=1)
+        loss.backward()
+        out[f"{name}_loss"], out[f"{name}_dq"], out[f"{name}_dd"], out[f"{name}_dn"] = (
+            loss.detach().numpy(), qq.grad.numpy(), dd.grad.numpy(), nn.grad.numpy())
+        assert torch.allclose(port(q, d, neg, offset=1, **kw), loss.detach(), atol=1e-6), name
+    for name, mod, kw in (("sigmoid", ColbertSigmoidLoss(), {}),
+                          ("sigmoid_filter_t1", ColbertSigmoidLoss(temperature=1.0, pos_aware_negative_filtering=True),
+                           dict(temperature=1.0, pos_aware_negative_filtering=True))):
+        qq, dd = q.clone().requires_grad_(True), d[:4].clone().requires_grad_(True)
+        loss = mod(qq, dd)
+        loss.backward()
+        out[f"{name}_loss"], out[f"{name}_dq"], out[f"{name}_dd"] = loss.detach().numpy(), qq.grad.numpy(), dd.grad.numpy()
+        assert torch.allclose(O.colbert_sigmoid_loss_port(q, d[:4], **kw), loss.detach(), atol=1e-6), name
+    np.savez_compressed(os.path.join(GOLD, "loss_neg_small.npz"), **out)
+    print("loss_neg_small ok")
+
+
 def loss_cfg3():
     q, d, lens = O.cfg3_inputs()
     out = {"q_checksum": checksum(q), "d_checksum": checksum(d), "lens": lens.numpy()}
@@ -209,7 +252,7 @@ def head_small():
 
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
-    which = set(sys.argv[1:]) or {"scorer_small", "cfg1", "cfg2", "loss_small", "loss_cfg3", "head_small"}
+    which = set(sys.argv[1:]) or {"scorer_small", "cfg1", "cfg2", "loss_small", "loss_neg_small", "loss_cfg3", "head_small"}
     if "scorer_small" in which:
         scorer_small()
     if "cfg1" in which:
@@ -218,6 +261,8 @@ if __name__ == "__main__":
         scorer_cfg("cfg2", *O.cfg2_inputs())
     if "loss_small" in which:
         loss_small()
+    if "loss_neg_small" in which:
+        loss_neg_small()
     if "loss_cfg3" in which:
         loss_cfg3()
     if "head_small" in which:

@@ -133,3 +133,57 @@ def test_smooth_max_is_refused_loudly():
     q = O.unit_rows((2, 4, 128), 1).to(DEV)
     with pytest.raises(NotImplementedError):
         cb.ColbertLoss(use_smooth_max=True)(q, q)
+
+
+NEG_CASES = (
+    ("negce", lambda: cb.ColbertNegativeCELoss()),
+    ("negce_w0", lambda: cb.ColbertNegativeCELoss(in_batch_term_weight=0.0)),
+    ("negce_filter", lambda: cb.ColbertNegativeCELoss(pos_aware_negative_filtering=True, in_batch_term_weight=0.3)),
+    ("pairneg", lambda: cb.ColbertPairwiseNegativeCELoss()),
+    ("pairneg_t1", lambda: cb.ColbertPairwiseNegativeCELoss(temperature=1.0, in_batch_term_weight=0.7)),
+)
+
+
+@pytest.mark.parametrize("name,make", NEG_CASES)
+def test_explicit_negative_losses_match_reference(name, make):
+    """ColbertNegativeCELoss / ColbertPairwiseNegativeCELoss (late_interaction_losses.py:215-252, :361-398):
+    B=4, C=6 (offset 1), 3 negatives per query, zero rows; losses and all three gradients vs the reference."""
+    g = load_golden("loss_neg_small.npz")
+    q, d, neg = (torch.from_numpy(g[k]) for k in ("q", "d", "neg"))
+    qq, dd, nn = (t.to(DEV).requires_grad_(True) for t in (q, d, neg))
+    loss = make()(qq, dd, nn, offset=1)
+    loss.backward()
+    assert abs(float(loss) - float(g[f"{name}_loss"])) < 2e-5, (float(loss), float(g[f"{name}_loss"]))
+    for got, key, src in ((qq.grad, "dq", q), (dd.grad, "dd", d), (nn.grad, "dn", neg)):
+        real = src.abs().sum(-1) > 0
+        ref = torch.from_numpy(g[f"{name}_{key}"])
+        assert torch.allclose(got.cpu()[real], ref[real], rtol=1e-4, atol=2e-6), (name, key)
+
+
+@pytest.mark.parametrize("name,make", (("sigmoid", lambda: cb.ColbertSigmoidLoss()),
+                                       ("sigmoid_filter_t1", lambda: cb.ColbertSigmoidLoss(temperature=1.0, pos_aware_negative_filtering=True))))
+def test_sigmoid_loss_matches_reference(name, make):
+    g = load_golden("loss_neg_small.npz")
+    q, d = torch.from_numpy(g["q"]), torch.from_numpy(g["d"])[:4]
+    loss, dq, dd = _run(make(), q, d)
+    assert abs(float(loss) - float(g[f"{name}_loss"])) < 2e-5
+    real_q, real_d = q.abs().sum(-1) > 0, d.abs().sum(-1) > 0
+    assert torch.allclose(dq[real_q], torch.from_numpy(g[f"{name}_dq"])[real_q], rtol=1e-4, atol=2e-6)
+    assert torch.allclose(dd[real_d], torch.from_numpy(g[f"{name}_dd"])[real_d], rtol=1e-4, atol=2e-6)
+    with pytest.raises(ValueError):
+        cb.ColbertSigmoidLoss()(q.to(DEV), torch.from_numpy(g["d"]).to(DEV))  # non-square score matrix
+
+
+def test_reference_kats_for_negative_losses():
+    """tests/loss/test_li_losses.py:103-181: all-zero embeddings -> softplus(0) = ln 2 (with and without in-batch term)."""
+    b, nq, dim, nneg = 2, 1, 3, 1
+    q = torch.zeros(b, nq, dim, device=DEV)
+    d = torch.zeros(b, nq, dim, device=DEV)
+    n = torch.zeros(b, nneg, nq, dim, device=DEV)
+    ln2 = math.log(2.0)
+    no_ib = cb.ColbertNegativeCELoss(temperature=1.0, normalize_scores=False, in_batch_term_weight=0)
+    assert math.isclose(float(no_ib(q, d, n)), ln2, rel_tol=1e-6)
+    with_ib = cb.ColbertNegativeCELoss(temperature=1.0, normalize_scores=False, in_batch_term_weight=0.5)
+    assert math.isclose(float(with_ib(q, d, n)), ln2, rel_tol=1e-6)  # in-batch CE over 2 zeros is ln 2 as well
+    pw = cb.ColbertPairwiseNegativeCELoss(temperature=1.0, normalize_scores=False, in_batch_term_weight=0.5)
+    assert math.isclose(float(pw(q, d, n)), ln2, rel_tol=1e-6)
