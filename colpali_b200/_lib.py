@@ -22,6 +22,8 @@ EXPORTED_SYMBOLS = (
     "cpb_set_option",
     "cpb_maxsim_fwd",
     "cpb_maxsim_workspace_bytes",
+    "cpb_maxsim_fwd_balanced",
+    "cpb_maxsim_split_workspace_bytes",
     "cpb_colbert_loss_fwd",
     "cpb_colbert_neg_loss_fwd",
     "cpb_maxsim_bwd",
@@ -74,6 +76,10 @@ def load() -> ctypes.CDLL:
         c_vp, c_vp, c_vp,  # d_scores, d_argmax, d_workspace
         c_u32, c_vp,  # flags, stream
     ]
+    lib.cpb_maxsim_split_workspace_bytes.restype = c_i64
+    lib.cpb_maxsim_split_workspace_bytes.argtypes = [c_i, c_i]
+    lib.cpb_maxsim_fwd_balanced.restype = c_i
+    lib.cpb_maxsim_fwd_balanced.argtypes = lib.cpb_maxsim_fwd.argtypes[:-1] + [c_i, c_i, c_vp, c_i64, c_u32, c_vp]
     c_f = ctypes.c_float
     lib.cpb_colbert_loss_fwd.restype = c_i
     lib.cpb_colbert_loss_fwd.argtypes = [

@@ -32,6 +32,7 @@ int g_opt_qtiles_per_cta = 0;
 unsigned g_opt_debug_flags = 0;
 int g_opt_mma_split = 6;
 int g_opt_dbg_delay = 0;
+int g_opt_balanced = 1;
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -138,6 +139,8 @@ int cpb_set_option(const char* name, int value) {
   } else if (!strcmp(name, "mma_split")) {
     if (value < 5 || value > 8) return fail(CPB_E_INVALID, "mma_split must be 5..8");
     g_opt_mma_split = value;
+  } else if (!strcmp(name, "balanced")) {
+    g_opt_balanced = value != 0;
   } else if (!strcmp(name, "debug_delay")) {
     g_opt_dbg_delay = value;
   } else if (!strcmp(name, "debug_flags")) {
@@ -153,9 +156,10 @@ int64_t cpb_maxsim_workspace_bytes(int n_queries, int nq_pad, int n_docs) {
   return static_cast<int64_t>(nq_pad / 32) * n_queries * n_docs * 4;
 }
 
-int cpb_maxsim_fwd(const void* d_q, int n_queries, int nq_pad, const void* d_docs, int64_t doc_rows,
-                   const int32_t* d_doc_start, const int32_t* d_doc_len, const float* d_doc_floor, int n_docs,
-                   float* d_scores, int32_t* d_argmax, float* d_workspace, uint32_t flags, void* stream_) {
+static int maxsim_fwd_impl(const void* d_q, int n_queries, int nq_pad, const void* d_docs, int64_t doc_rows,
+                           const int32_t* d_doc_start, const int32_t* d_doc_len, const float* d_doc_floor, int n_docs,
+                           float* d_scores, int32_t* d_argmax, float* d_workspace, uint32_t flags, int uniform_len,
+                           int max_doc_len, void* d_split_ws, int64_t split_ws_bytes, uint32_t epoch, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (n_queries <= 0 || n_docs <= 0) return fail(CPB_E_INVALID, "n_queries=%d and n_docs=%d must be positive", n_queries, n_docs);
   if (nq_pad <= 0 || (nq_pad % 32) != 0) return fail(CPB_E_INVALID, "nq_pad=%d must be a positive multiple of 32", nq_pad);
@@ -215,6 +219,26 @@ int cpb_maxsim_fwd(const void* d_q, int n_queries, int nq_pad, const void* d_doc
   int parts = max_clusters / p.group_sets;
   if (parts < 1) parts = 1;
   if (parts > n_docs) parts = n_docs;
+  // tile-balanced partitions (a document may be cut between two partitions): contiguous banks only, every
+  // partition at least as long as the longest document, caller-provided exchange workspace
+  const int64_t tiles = (doc_rows + 255) / 256;
+  if (g_opt_balanced && (flags & CPB_FLAG_CONTIGUOUS) && d_split_ws && max_doc_len > 0 && doc_rows <= 0x7fffffffLL) {
+    int bparts = parts;
+    if (bparts > tiles) bparts = static_cast<int>(tiles);
+    const int64_t min_rows = 256 * (tiles / (bparts > 0 ? bparts : 1));
+    const int64_t need = static_cast<int64_t>(p.group_sets) * cluster * bparts * R * (128 * 8 + 16);
+    if (bparts > 1 && min_rows >= max_doc_len && need <= split_ws_bytes) {
+      parts = bparts;
+      p.balanced = 1;
+      p.bank_rows = static_cast<int>(doc_rows);
+      p.uniform_len = uniform_len;
+      const int64_t slots = static_cast<int64_t>(p.group_sets) * cluster * bparts * R;
+      p.split_max = static_cast<float*>(d_split_ws);
+      p.split_idx = reinterpret_cast<int32_t*>(p.split_max + slots * 128);
+      p.split_flag = reinterpret_cast<uint32_t*>(p.split_idx + slots * 128);
+      p.epoch = epoch;
+    }
+  }
   p.doc_parts = parts;
   p.flags = flags | g_opt_debug_flags;
   p.mma_split = g_opt_mma_split;
@@ -283,6 +307,29 @@ int cpb_colbert_loss_fwd(const float* d_scores, const void* d_q, int n_queries, 
   return loss_fwd_impl(d_scores, d_q, n_queries, nq_pad, n_docs, mode, temperature, normalize_scores,
                        pos_aware_negative_filtering, filter_threshold, filter_factor, offset, nullptr, 0, 1.f, d_loss,
                        d_grad_scores, nullptr, d_bounds, stream_);
+}
+
+int cpb_maxsim_fwd(const void* d_q, int n_queries, int nq_pad, const void* d_docs, int64_t doc_rows,
+                   const int32_t* d_doc_start, const int32_t* d_doc_len, const float* d_doc_floor, int n_docs,
+                   float* d_scores, int32_t* d_argmax, float* d_workspace, uint32_t flags, void* stream_) {
+  return maxsim_fwd_impl(d_q, n_queries, nq_pad, d_docs, doc_rows, d_doc_start, d_doc_len, d_doc_floor, n_docs, d_scores,
+                         d_argmax, d_workspace, flags, 0, 0, nullptr, 0, 0, stream_);
+}
+
+int cpb_maxsim_fwd_balanced(const void* d_q, int n_queries, int nq_pad, const void* d_docs, int64_t doc_rows,
+                            const int32_t* d_doc_start, const int32_t* d_doc_len, const float* d_doc_floor, int n_docs,
+                            float* d_scores, int32_t* d_argmax, float* d_workspace, uint32_t flags, int uniform_len,
+                            int max_doc_len, void* d_split_ws, int64_t split_ws_bytes, uint32_t epoch, void* stream_) {
+  if (epoch == 0) return fail(CPB_E_INVALID, "epoch must be non-zero (a zero-initialised workspace means 'nothing published')");
+  return maxsim_fwd_impl(d_q, n_queries, nq_pad, d_docs, doc_rows, d_doc_start, d_doc_len, d_doc_floor, n_docs, d_scores,
+                         d_argmax, d_workspace, flags, uniform_len, max_doc_len, d_split_ws, split_ws_bytes, epoch, stream_);
+}
+
+int64_t cpb_maxsim_split_workspace_bytes(int n_queries, int nq_pad) {
+  // worst case: every SM is a partition of some query-tile group
+  const int64_t qtiles = (static_cast<int64_t>(n_queries) * nq_pad + 127) / 128;
+  const int64_t groups = qtiles + 4;  // padded to the cluster size
+  return groups * 160 * 2 * (128 * 8 + 16);
 }
 
 int cpb_colbert_neg_loss_fwd(const float* d_scores, const float* d_neg_scores, const void* d_q, int n_queries,

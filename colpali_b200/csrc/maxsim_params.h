@@ -29,6 +29,15 @@ struct MaxSimParams {
   int group_sets;  // ceil(q_groups / cluster)
   int doc_parts;   // document partitions; grid = group_sets * doc_parts * cluster
   uint32_t flags;
+  // tile-balanced partitioning of a contiguous bank (a document may straddle two partitions; its two partial
+  // per-token maxima are combined through `split_*`): see maxsim_sm100.cu
+  int balanced;        // 0 = partitions are whole documents, 1 = partitions are whole 256-row tiles
+  int bank_rows;       // rows of the bank covered by documents (balanced mode)
+  int uniform_len;     // > 0: every document has this many rows (first document of a partition = row / len)
+  float* split_max;    // [q_groups_padded, doc_parts, R, 128]
+  int32_t* split_idx;  // same shape (argmax variant)
+  uint32_t* split_flag;  // [q_groups_padded, doc_parts, R, 4]; a slot is valid when it holds `epoch`
+  uint32_t epoch;
   int dbg_delay;   // profiling only: cycles the epilogue holds an unread accumulator in CPB_DBG_SKIP_EPILOGUE mode
   int mma_split;   // K-steps of a job issued before the next job's barrier waits (5..8)
 };

@@ -70,8 +70,14 @@ struct SmemLayout {
 struct Run {
   int e, row0, row1;
 };
-__device__ __forceinline__ Run next_run(const MaxSimParams& p, int d, int d1) {
+__device__ __forceinline__ Run next_run(const MaxSimParams& p, int d, int d1, int bal_r0, int bal_r1) {
   Run r;
+  if (p.balanced) {  // the partition is the row range [bal_r0, bal_r1), whatever documents it cuts
+    r.e = d1;
+    r.row0 = bal_r0;
+    r.row1 = bal_r1;
+    return r;
+  }
   r.row0 = __ldg(p.doc_start + d);
   if (p.flags & CPB_FLAG_CONTIGUOUS) {
     r.e = d1;
@@ -178,8 +184,20 @@ maxsim_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   const int g = (cluster_id % p.group_sets) * C + static_cast<int>(crank);  // query-tile group
   const int part = cluster_id / p.group_sets;                                // document partition
   const int r_cnt = max(0, min(R, p.num_qtiles - g * R));
-  const int d0 = static_cast<int>((static_cast<int64_t>(p.n_docs) * part) / p.doc_parts);
-  const int d1 = static_cast<int>((static_cast<int64_t>(p.n_docs) * (part + 1)) / p.doc_parts);
+  int d0 = static_cast<int>((static_cast<int64_t>(p.n_docs) * part) / p.doc_parts);
+  int d1 = static_cast<int>((static_cast<int64_t>(p.n_docs) * (part + 1)) / p.doc_parts);
+  // Balanced mode: partitions are equal shares of the bank's 256-row TILES instead of whole documents, so every CTA
+  // gets the same number of MMA jobs (at cfg2 one partition of 37 had 28 documents instead of 27: 3.5 % of the kernel).
+  // A document cut by a partition boundary is folded by both neighbours; the right one publishes its partial per-token
+  // maxima, the left one combines and emits the score (see the epilogue).
+  int bal_r0 = 0, bal_r1 = 0;
+  if (p.balanced) {
+    const int64_t tiles = (p.bank_rows + kTileN - 1) / kTileN;
+    bal_r0 = static_cast<int>(min(static_cast<int64_t>(p.bank_rows), kTileN * ((tiles * part) / p.doc_parts)));
+    bal_r1 = static_cast<int>(min(static_cast<int64_t>(p.bank_rows), kTileN * ((tiles * (part + 1)) / p.doc_parts)));
+    d0 = 0;
+    d1 = p.n_docs;
+  }
 
   // ---- one-time setup ---------------------------------------------------------------------
   if (warp == 0 && lane == 0) {
@@ -223,7 +241,7 @@ maxsim_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       for (int d = d0; d < d1;) {
-        const Run run = next_run(p, d, d1);
+        const Run run = next_run(p, d, d1, bal_r0, bal_r1);
         d = run.e;
         for (int row = run.row0; row < run.row1; row += kTileN) {
           const int n_valid = min(kTileN, run.row1 - row);
@@ -303,7 +321,7 @@ maxsim_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         }
         while (!it_have_tile || it_row >= it_row1) {
           if (it_d >= d1) return false;
-          const Run run = next_run(p, it_d, d1);
+          const Run run = next_run(p, it_d, d1, bal_r0, bal_r1);
           it_d = run.e;
           it_row = run.row0;
           it_row1 = run.row1;
@@ -403,18 +421,68 @@ maxsim_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     const bool dbg = (p.flags & CPB_DBG_CLOCKS) != 0;
     long long e_wait = 0, e_hold = 0, e_post = 0, e_hold2 = 0;
     int n_path2 = 0;
-    for (int d = d0; d < d1;) {
-      const Run run = next_run(p, d, d1);
+
+    // ---- balanced mode: which document contains the first row of my partition, and is it cut? ----------------
+    int first_doc = d0;
+    bool head_frag = false;
+    if (p.balanced) {
+      if (bal_r0 == 0) {
+        first_doc = 0;
+      } else if (p.uniform_len > 0) {
+        first_doc = bal_r0 / p.uniform_len;
+      } else {  // last document that starts at or before bal_r0 (starts are sorted in a contiguous bank)
+        int lo = 0, hi = p.n_docs - 1;
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (__ldg(p.doc_start + mid) <= bal_r0) lo = mid; else hi = mid - 1;
+        }
+        first_doc = lo;
+      }
+      first_doc = min(first_doc, p.n_docs - 1);
+      head_frag = __ldg(p.doc_start + first_doc) < bal_r0;
+    }
+    // slot of the boundary between partitions `bp` and `bp + 1` for resident query tile r
+    auto split_slot = [&](int bp, int r) { return ((g * p.doc_parts + bp) * R + r); };
+    auto publish = [&](int r, float mm, int ai) {  // I hold the RIGHT part of a cut document
+      const int slot = split_slot(part - 1, r);
+      p.split_max[slot * 128 + quad * 32 + lane] = mm;
+      if (kArgmax) p.split_idx[slot * 128 + quad * 32 + lane] = ai;
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) *reinterpret_cast<volatile uint32_t*>(p.split_flag + slot * 4 + quad) = p.epoch;
+    };
+    auto consume = [&](int r, float& mm, int& ai) {  // I hold the LEFT part: wait for the neighbour's partial, combine
+      const int slot = split_slot(part, r);
+      if (lane == 0) {
+        const volatile uint32_t* f = reinterpret_cast<volatile uint32_t*>(p.split_flag + slot * 4 + quad);
+        const uint64_t t0 = global_timer_ns();
+        while (*f != p.epoch) {
+          if (global_timer_ns() - t0 > 4000000000ull) __trap();
+        }
+      }
+      __syncwarp();
+      __threadfence();
+      const float om = __ldcg(p.split_max + slot * 128 + quad * 32 + lane);
+      const int oi = kArgmax ? __ldcg(p.split_idx + slot * 128 + quad * 32 + lane) : -1;
+      if (om > mm) {  // on a tie the earlier (left) token wins, like torch.max
+        mm = om;
+        ai = oi;
+      }
+    };
+
+    for (int d = p.balanced ? first_doc : d0; d < d1;) {
+      const Run run = next_run(p, d, d1, bal_r0, bal_r1);
       if (run.row1 == run.row0) {
-        // nothing but empty documents: their score is the sum of the floors
-        for (int e = d; e < run.e; ++e)
-          for (int r = 0; r < r_cnt; ++r) finalize(e, r, doc_init(e), -1);
+        // nothing but empty documents: their score is the sum of the floors (balanced mode: an empty partition)
+        if (!p.balanced)
+          for (int e = d; e < run.e; ++e)
+            for (int r = 0; r < r_cnt; ++r) finalize(e, r, doc_init(e), -1);
         d = run.e;
         continue;
       }
       // state at the start of each tile: current document, its first/last bank row, running maxima
       int cur = d;
-      int cur_row0 = run.row0;
+      int cur_row0 = p.balanced ? __ldg(p.doc_start + cur) : run.row0;
       int cur_end = cur_row0 + __ldg(p.doc_len + cur);
       // length and floor of the FOLLOWING document are fetched when the cursor moves, long before they are needed:
       // a global load while the accumulator is held costs ~300 cycles of tensor idle time on boundary tiles
@@ -451,7 +519,7 @@ maxsim_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
 
             // the current document is complete: emit it and step to the next one of the run
             auto finish_doc = [&]() {
-              finalize(doc, r, mm, ai);
+              if (head_frag && doc == first_doc) publish(r, mm, ai); else finalize(doc, r, mm, ai);
               ++doc;
               if (doc >= run.e) {
                 doc_end = 0x7fffffff;  // run exhausted
@@ -634,6 +702,19 @@ maxsim_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         cur_end = nxt_end;
         cur_nlen = nxt_nlen;
         cur_ninit = nxt_ninit;
+      }
+      if (p.balanced && !skip && cur < p.n_docs && cur_end != 0x7fffffff && cur_row0 < bal_r1 && cur_end > bal_r1) {
+        // my last document continues in the next partition: combine with the neighbour's partial and emit it
+        for (int r = 0; r < r_cnt; ++r) {
+          float mm = m[r];
+          int ai = am[r];
+          if (head_frag && cur == first_doc) {
+            // (a document longer than a whole partition is excluded by the host: it would need a chain)
+            __trap();
+          }
+          consume(r, mm, ai);
+          finalize(cur, r, mm, ai);
+        }
       }
       d = run.e;
     }

@@ -115,9 +115,11 @@ class DocBank:
     """
 
     def __init__(self, flat: torch.Tensor, start: torch.Tensor, length: torch.Tensor,
-                 floor: Optional[torch.Tensor], contiguous: bool = False):
+                 floor: Optional[torch.Tensor], contiguous: bool = False, uniform_len: int = 0, max_len: int = 0):
         self.flat, self.start, self.length, self.floor = flat, start, length, floor
         self.contiguous = contiguous  # documents stored back to back (start[j+1] == start[j] + len[j])
+        self.uniform_len = uniform_len  # > 0: every document has this many rows
+        self.max_len = max_len          # longest document (0 = unknown: no tile-balanced partitioning)
         self.n_docs = int(start.numel())
         self.device = flat.device
 
@@ -133,7 +135,7 @@ class DocBank:
             n, L, _ = ps.shape
             flat = _pad_dim(ps.to(device, non_blocking=True)).reshape(n * L, EMBED_DIM).contiguous()
             start, length = _dense_layout(n, L, device)
-            return DocBank(flat, start, length, None, contiguous=True)  # equal lengths: the reference pads nothing
+            return DocBank(flat, start, length, None, contiguous=True, uniform_len=L, max_len=L)  # equal lengths: no padding
         lens = [int(p.shape[0]) for p in ps]
         n = len(ps)
         # one pass over the bank: device-side cat of the per-document uploads
@@ -154,7 +156,22 @@ class DocBank:
                     any_pad = True
                     fl[j : j + batch_size][padded] = 0.0
             floor = fl.to(device) if any_pad else None
-        return DocBank(flat, start, length, floor, contiguous=True)
+        uniform = lens[0] if len(set(lens)) == 1 else 0
+        return DocBank(flat, start, length, floor, contiguous=True, uniform_len=uniform, max_len=max(lens))
+
+
+_SPLIT_WS: dict = {}
+_EPOCH = [0]
+
+
+def _split_workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
+    """Per-device exchange buffer for documents cut by a partition boundary (zeroed once, reused: slots are tagged
+    with a per-call epoch).  Calls that share it must be stream-ordered, which they are on one PyTorch stream."""
+    ws = _SPLIT_WS.get(str(dev))
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+        _SPLIT_WS[str(dev)] = ws
+    return ws
 
 
 def maxsim(q: QueryBlock, bank: DocBank, *, round_bf16: bool = False, want_argmax: bool = False):
@@ -169,15 +186,22 @@ def maxsim(q: QueryBlock, bank: DocBank, *, round_bf16: bool = False, want_argma
     flags = (_lib.CPB_FLAG_ROUND_BF16 if round_bf16 else 0) | (_lib.CPB_FLAG_CONTIGUOUS if bank.contiguous else 0)
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
-        rc = lib.cpb_maxsim_fwd(
+        common = (
             q.flat.data_ptr(), q.n, q.nq_pad,
             bank.flat.data_ptr(), bank.flat.shape[0],
             bank.start.data_ptr(), bank.length.data_ptr(),
             bank.floor.data_ptr() if bank.floor is not None else None, bank.n_docs,
             scores.data_ptr(), argmax.data_ptr() if argmax is not None else None,
             ws.data_ptr() if ws is not None else None,
-            flags, stream,
+            flags,
         )
+        if bank.contiguous and bank.max_len > 0 and torch.cuda.current_stream(dev) == torch.cuda.default_stream(dev):
+            split = _split_workspace(dev, lib.cpb_maxsim_split_workspace_bytes(q.n, q.nq_pad))
+            _EPOCH[0] = _EPOCH[0] % 0xFFFFFFF0 + 1
+            rc = lib.cpb_maxsim_fwd_balanced(*common, bank.uniform_len, bank.max_len, split.data_ptr(), split.numel(),
+                                             _EPOCH[0], stream)
+        else:
+            rc = lib.cpb_maxsim_fwd(*common, stream)
     _lib.check(rc, "cpb_maxsim_fwd")
     _lib.count_launches(2 if ws is not None else 1)
     return (scores, argmax) if want_argmax else scores

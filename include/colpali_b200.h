@@ -55,6 +55,8 @@ int cpb_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
  *   "cluster"         0 = auto, 1 / 2 / 4 = CTAs per cluster sharing document tiles by TMA multicast
  *   "qtiles_per_cta"  0 = auto, 1 / 2     = resident 128-row query tiles per CTA
  *   "mma_split"       5..8 (default 6): K-steps of a job issued before the next job's barrier waits
+ *   "balanced"        1 (default) / 0: allow tile-balanced partitions in cpb_maxsim_fwd_balanced
+ *   "debug_delay"     profiling only
  *   "debug_flags"     profiling-only bits (upper 16), 0 in production
  */
 int cpb_set_option(const char* name, int value);
@@ -88,6 +90,24 @@ int cpb_maxsim_fwd(const void* d_q, int n_queries, int nq_pad,
                    const int32_t* d_doc_start, const int32_t* d_doc_len, const float* d_doc_floor, int n_docs,
                    float* d_scores, int32_t* d_argmax, float* d_workspace,
                    uint32_t flags, void* stream);
+
+/*
+ * Same as cpb_maxsim_fwd, with tile-balanced partitioning for CPB_FLAG_CONTIGUOUS banks: every persistent CTA gets
+ * the same number of 256-row tiles even if that cuts a document in two; the two partial per-token maxima of a cut
+ * document are exchanged through d_split_ws (right neighbour publishes, left neighbour combines and emits the score).
+ *   uniform_len     > 0 if every document has exactly this many rows (skips a binary search), else 0
+ *   max_doc_len     length of the longest document (partitions shorter than this fall back to whole documents)
+ *   d_split_ws      device scratch of cpb_maxsim_split_workspace_bytes() bytes, ZERO-INITIALISED ONCE by the caller and
+ *                   then reused across calls on the same stream order; NULL disables balancing
+ *   epoch           non-zero, different for every call that shares d_split_ws (a slot is valid when it holds `epoch`)
+ */
+int cpb_maxsim_fwd_balanced(const void* d_q, int n_queries, int nq_pad,
+                            const void* d_docs, int64_t doc_rows,
+                            const int32_t* d_doc_start, const int32_t* d_doc_len, const float* d_doc_floor, int n_docs,
+                            float* d_scores, int32_t* d_argmax, float* d_workspace, uint32_t flags,
+                            int uniform_len, int max_doc_len, void* d_split_ws, int64_t split_ws_bytes, uint32_t epoch,
+                            void* stream);
+int64_t cpb_maxsim_split_workspace_bytes(int n_queries, int nq_pad);
 
 /* Bytes of d_workspace cpb_maxsim_fwd needs for this shape (0 when nq_pad == 32). */
 int64_t cpb_maxsim_workspace_bytes(int n_queries, int nq_pad, int n_docs);
