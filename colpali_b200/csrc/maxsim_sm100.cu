@@ -369,6 +369,18 @@ maxsim_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
           }
         }
       };
+      if (r_cnt == 0) {
+        // phantom CTA (odd number of query-tile groups in a cluster): no MMAs, but the cluster's TMA ring still
+        // needs this CTA's release of every stage (the `empty` barriers count one arrival per CTA)
+        while (next_tile()) {
+          mbar_wait(&full[it_stage], it_phase);
+          tc_fence_after();
+          if (elect_one()) {
+            if (C > 1) umma_commit_mc(&empty[it_stage], cmask); else umma_commit(&empty[it_stage]);
+          }
+          __syncwarp();
+        }
+      }
       constexpr int kSplit = CPB_MMA_SPLIT;  // K-steps issued before the next job's waits
       advance(cur);
       if (cur.valid) prepare(cur);

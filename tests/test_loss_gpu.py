@@ -153,7 +153,7 @@ def test_explicit_negative_losses_match_reference(name, make):
     qq, dd, nn = (t.to(DEV).requires_grad_(True) for t in (q, d, neg))
     loss = make()(qq, dd, nn, offset=1)
     loss.backward()
-    assert abs(float(loss) - float(g[f"{name}_loss"])) < 2e-5, (float(loss), float(g[f"{name}_loss"]))
+    assert abs(loss.item() - float(g[f"{name}_loss"])) < 2e-5, (loss.item(), float(g[f"{name}_loss"]))
     for got, key, src in ((qq.grad, "dq", q), (dd.grad, "dd", d), (nn.grad, "dn", neg)):
         real = src.abs().sum(-1) > 0
         ref = torch.from_numpy(g[f"{name}_{key}"])

@@ -180,3 +180,89 @@ def test_errors():
         cb.score_multi_vector([torch.randn(3, 128)], [], device=DEV)
     with pytest.raises(cb.ColpaliB200Error):
         cb.score_multi_vector([torch.randn(3, 256)], [torch.randn(3, 256)], device=DEV)
+
+
+@pytest.mark.parametrize("n_queries", [3, 40])
+def test_tile_balanced_partitions_on_a_ragged_bank(n_queries):
+    """Many short ragged documents (some empty): partitions are whole tiles, documents are cut at partition
+    boundaries and re-assembled through the split workspace; the first document of a partition is found by binary
+    search.  Scores (with the reference's padding floors) and argmax must match the fp64 evaluation."""
+    dev = torch.device(DEV)
+    g = torch.Generator().manual_seed(12)
+    lens = torch.randint(0, 300, (700,), generator=g).tolist()
+    lens[0] = 0
+    lens[17] = 0
+    lens[699] = 0
+    qs = [O.unit_rows((32, 128), 500 + i) for i in range(n_queries)]
+    ps = [O.unit_rows((n, 128), 1000 + j) if n else torch.zeros(0, 128, dtype=torch.bfloat16) for j, n in enumerate(lens)]
+    bank = cb.DocBank.from_passages([p.to(dev) for p in ps], dev)
+    assert bank.contiguous and bank.max_len == max(lens) and bank.uniform_len == 0
+    qb = cb.QueryBlock([x.to(dev) for x in qs], dev)
+    got, am = cb.maxsim(qb, bank, want_argmax=True)
+    got2 = cb.maxsim(qb, bank)
+    floors = O.reference_floors(lens, 128)
+    want = torch.from_numpy(O.maxsim_f64(qs, ps, floors)).float()
+    finite = torch.isfinite(want)
+    assert torch.equal(torch.isfinite(got.cpu()), finite)
+    assert torch.allclose(got.cpu()[finite], want[finite], rtol=1e-5, atol=1e-4)
+    assert torch.equal(got, got2)
+    # argmax of a few documents against a direct evaluation
+    for j in (1, 100, 350, 698):
+        if lens[j] == 0:
+            continue
+        sim = torch.cat(qs).float() @ ps[j].float().T
+        mx, ix = sim.max(1)
+        rows = am[j].cpu().long()
+        hit_floor = rows < 0
+        assert torch.equal(rows[~hit_floor], ix[~hit_floor])
+        assert (mx[hit_floor] <= 0).all()
+    # switching balancing off gives bit-identical scores
+    from colpali_b200 import _lib
+    _lib.set_option("balanced", 0)
+    try:
+        assert torch.equal(cb.maxsim(qb, bank), got2)
+    finally:
+        _lib.set_option("balanced", 1)
+
+
+@pytest.mark.parametrize("n_queries", [12, 20, 36])
+def test_odd_number_of_query_tile_groups(n_queries):
+    """3, 5 and 9 query tiles: the last 2-CTA cluster of a partition has a CTA without query tiles, which must still
+    keep the shared TMA ring moving."""
+    dev = torch.device(DEV)
+    qs = O.unit_rows((n_queries, 32, 128), 77)
+    ps = O.unit_rows((90, 300, 128), 78)
+    got = cb.score_multi_vector(qs, ps, device=dev)
+    want = torch.einsum("bnd,csd->bcns", qs.float(), ps.float()).amax(3).sum(2)
+    assert torch.allclose(got, want, rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_randomised_shapes_against_fp64(seed):
+    """Seeded sweep over query counts / lengths, bank sizes, ragged and dense banks, empty documents: exercises the
+    R = 1 / 2 variants, odd group counts, clusters with a phantom CTA, balanced and whole-document partitions."""
+    dev = torch.device(DEV)
+    g = torch.Generator().manual_seed(1000 + seed)
+    ri = lambda lo, hi: int(torch.randint(lo, hi + 1, (1,), generator=g))  # noqa: E731
+    n_q, nq = ri(1, 50), ri(1, 70)
+    n_d = ri(1, 500)
+    dense = seed % 3 == 0
+    if dense:
+        L = ri(1, 400)
+        lens = [L] * n_d
+    else:
+        lens = [ri(0, 350) if ri(0, 9) else 0 for _ in range(n_d)]
+        if sum(lens) == 0:
+            lens[0] = 5
+    q = O.unit_rows((n_q, nq, 128), 3 * seed)
+    ps = [O.unit_rows((n, 128), 7000 + 31 * seed + j) if n else torch.zeros(0, 128, dtype=torch.bfloat16) for j, n in enumerate(lens)]
+    if dense:
+        got = cb.score_multi_vector(q, torch.stack(ps), device=dev)
+        floors = None
+    else:
+        got = cb.score_multi_vector(list(q), ps, device=dev)
+        floors = O.reference_floors(lens, 128)
+    want = torch.from_numpy(O.maxsim_f64(list(q), ps, floors)).float()
+    finite = torch.isfinite(want)
+    assert torch.equal(torch.isfinite(got), finite), (n_q, nq, n_d, dense)
+    assert torch.allclose(got[finite], want[finite], rtol=1e-5, atol=2e-4), (n_q, nq, n_d, dense)
