@@ -182,6 +182,21 @@ def test_errors():
         cb.score_multi_vector([torch.randn(3, 256)], [torch.randn(3, 256)], device=DEV)
 
 
+def _torch_fp32_maxsim(q, ps, floors, dev):
+    """Plain PyTorch fp32 evaluation on the GPU (padded einsum + masked amax): fast checker for the shape sweep."""
+    lens = torch.tensor([p.shape[0] for p in ps], device=dev)
+    pad = torch.nn.utils.rnn.pad_sequence([p.to(dev).float() for p in ps], batch_first=True)  # [n_d, Lmax, 128]
+    if pad.shape[1] == 0:
+        pad = torch.zeros(len(ps), 1, 128, device=dev)
+    sim = torch.einsum("bnd,csd->bcns", q.to(dev).float(), pad)
+    valid = torch.arange(pad.shape[1], device=dev)[None, :] < lens[:, None]
+    sim = sim.masked_fill(~valid[None, :, None, :], float("-inf"))
+    mx = sim.amax(dim=3)
+    if floors is not None:
+        mx = torch.maximum(mx, torch.tensor(floors, device=dev)[None, :, None])
+    return mx.sum(dim=2).cpu()
+
+
 @pytest.mark.parametrize("n_queries", [3, 40])
 def test_tile_balanced_partitions_on_a_ragged_bank(n_queries):
     """Many short ragged documents (some empty): partitions are whole tiles, documents are cut at partition
@@ -201,7 +216,7 @@ def test_tile_balanced_partitions_on_a_ragged_bank(n_queries):
     got, am = cb.maxsim(qb, bank, want_argmax=True)
     got2 = cb.maxsim(qb, bank)
     floors = O.reference_floors(lens, 128)
-    want = torch.from_numpy(O.maxsim_f64(qs, ps, floors)).float()
+    want = _torch_fp32_maxsim(torch.stack(qs), ps, floors, dev)
     finite = torch.isfinite(want)
     assert torch.equal(torch.isfinite(got.cpu()), finite)
     assert torch.allclose(got.cpu()[finite], want[finite], rtol=1e-5, atol=1e-4)
@@ -237,8 +252,8 @@ def test_odd_number_of_query_tile_groups(n_queries):
     assert torch.allclose(got, want, rtol=1e-5, atol=1e-4)
 
 
-@pytest.mark.parametrize("seed", range(12))
-def test_randomised_shapes_against_fp64(seed):
+@pytest.mark.parametrize("seed", range(8))
+def test_randomised_shapes_against_fp32_torch(seed):
     """Seeded sweep over query counts / lengths, bank sizes, ragged and dense banks, empty documents: exercises the
     R = 1 / 2 variants, odd group counts, clusters with a phantom CTA, balanced and whole-document partitions."""
     dev = torch.device(DEV)
@@ -248,21 +263,21 @@ def test_randomised_shapes_against_fp64(seed):
     n_d = ri(1, 500)
     dense = seed % 3 == 0
     if dense:
-        L = ri(1, 400)
-        lens = [L] * n_d
+        lens = [ri(1, 400)] * n_d
     else:
         lens = [ri(0, 350) if ri(0, 9) else 0 for _ in range(n_d)]
         if sum(lens) == 0:
             lens[0] = 5
     q = O.unit_rows((n_q, nq, 128), 3 * seed)
-    ps = [O.unit_rows((n, 128), 7000 + 31 * seed + j) if n else torch.zeros(0, 128, dtype=torch.bfloat16) for j, n in enumerate(lens)]
+    bank = O.unit_rows((sum(lens), 128), 7000 + seed)
+    ps = list(torch.split(bank, lens))
     if dense:
         got = cb.score_multi_vector(q, torch.stack(ps), device=dev)
         floors = None
     else:
         got = cb.score_multi_vector(list(q), ps, device=dev)
         floors = O.reference_floors(lens, 128)
-    want = torch.from_numpy(O.maxsim_f64(list(q), ps, floors)).float()
+    want = _torch_fp32_maxsim(q, ps, floors, dev)
     finite = torch.isfinite(want)
     assert torch.equal(torch.isfinite(got), finite), (n_q, nq, n_d, dense)
     assert torch.allclose(got[finite], want[finite], rtol=1e-5, atol=2e-4), (n_q, nq, n_d, dense)
