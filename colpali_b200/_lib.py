@@ -24,6 +24,8 @@ EXPORTED_SYMBOLS = (
     "cpb_maxsim_workspace_bytes",
     "cpb_maxsim_fwd_balanced",
     "cpb_maxsim_split_workspace_bytes",
+    "cpb_maxsim_fwd_allgather",
+    "cpb_wait_flags",
     "cpb_colbert_loss_fwd",
     "cpb_colbert_neg_loss_fwd",
     "cpb_maxsim_bwd",
@@ -80,6 +82,15 @@ def load() -> ctypes.CDLL:
     lib.cpb_maxsim_split_workspace_bytes.argtypes = [c_i, c_i]
     lib.cpb_maxsim_fwd_balanced.restype = c_i
     lib.cpb_maxsim_fwd_balanced.argtypes = lib.cpb_maxsim_fwd.argtypes[:-1] + [c_i, c_i, c_vp, c_i64, c_u32, c_vp]
+    lib.cpb_maxsim_fwd_allgather.restype = c_i
+    lib.cpb_maxsim_fwd_allgather.argtypes = [
+        c_vp, c_i, c_i, c_vp, c_i64, c_vp, c_vp, c_vp, c_i,  # q, n_queries, nq_pad, docs, rows, start, len, floor, n_docs
+        c_vp, c_i, c_i, c_u32,  # d_peer_slabs, n_peers, my_rank, flags
+        c_i, c_i, c_vp, c_i64, c_u32,  # uniform_len, max_doc_len, d_split_ws, split_ws_bytes, epoch
+        c_vp, c_i64, c_u32, c_vp,  # d_done_counter, flag_word_offset, signal_value, stream
+    ]
+    lib.cpb_wait_flags.restype = c_i
+    lib.cpb_wait_flags.argtypes = [c_vp, c_i, c_u32, c_vp]
     c_f = ctypes.c_float
     lib.cpb_colbert_loss_fwd.restype = c_i
     lib.cpb_colbert_loss_fwd.argtypes = [

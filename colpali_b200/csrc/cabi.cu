@@ -18,6 +18,7 @@ cudaError_t maxsim_launch(const CUtensorMap& tq, const CUtensorMap& td, const CU
                           int r, bool argmax, int grid, cudaStream_t stream);
 int maxsim_max_clusters(int r, int cluster);
 int maxsim_tile_n();
+cudaError_t wait_flags_launch(const uint32_t* flags, int n, uint32_t value, cudaStream_t stream);
 cudaError_t maxsim_reduce_segments(const float* partial, float* out, int64_t plane, int nseg, int round_ref,
                                    cudaStream_t stream);
 }  // namespace cpb
@@ -159,12 +160,14 @@ int64_t cpb_maxsim_workspace_bytes(int n_queries, int nq_pad, int n_docs) {
 static int maxsim_fwd_impl(const void* d_q, int n_queries, int nq_pad, const void* d_docs, int64_t doc_rows,
                            const int32_t* d_doc_start, const int32_t* d_doc_len, const float* d_doc_floor, int n_docs,
                            float* d_scores, int32_t* d_argmax, float* d_workspace, uint32_t flags, int uniform_len,
-                           int max_doc_len, void* d_split_ws, int64_t split_ws_bytes, uint32_t epoch, void* stream_) {
+                           int max_doc_len, void* d_split_ws, int64_t split_ws_bytes, uint32_t epoch,
+                           const uint64_t* d_peer_ptrs, int n_peers, int my_rank, uint32_t* d_done_counter,
+                           int64_t flag_word_offset, uint32_t signal_value, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (n_queries <= 0 || n_docs <= 0) return fail(CPB_E_INVALID, "n_queries=%d and n_docs=%d must be positive", n_queries, n_docs);
   if (nq_pad <= 0 || (nq_pad % 32) != 0) return fail(CPB_E_INVALID, "nq_pad=%d must be a positive multiple of 32", nq_pad);
   if (reinterpret_cast<uintptr_t>(d_q) & 15u) return fail(CPB_E_INVALID, "d_q is not 16-byte aligned");
-  if (!d_q || !d_docs || !d_doc_start || !d_doc_len || !d_scores) return fail(CPB_E_INVALID, "null device pointer");
+  if (!d_q || !d_docs || !d_doc_start || !d_doc_len || (!d_scores && !d_peer_ptrs)) return fail(CPB_E_INVALID, "null device pointer");
   if (doc_rows <= 0 || doc_rows > 0x7fffffffLL) return fail(CPB_E_INVALID, "doc_rows=%lld out of range (1..2^31-1)", static_cast<long long>(doc_rows));
   const int nseg = nq_pad / 32;
   if (nseg > 1 && !d_workspace) return fail(CPB_E_INVALID, "nq_pad=%d needs a workspace (cpb_maxsim_workspace_bytes)", nq_pad);
@@ -190,6 +193,17 @@ static int maxsim_fwd_impl(const void* d_q, int n_queries, int nq_pad, const voi
   p.num_qtiles = (p.q_rows + 127) / 128;
   p.flags = flags;
   p.scores = (nseg == 1) ? d_scores : d_workspace;
+  if (d_peer_ptrs) {
+    if (nseg != 1) return fail(CPB_E_UNSUPPORTED, "the fused all-gather needs queries of at most 32 tokens (nq_pad == 32)");
+    if (n_peers < 1 || n_peers > 64 || my_rank < 0 || my_rank >= n_peers) return fail(CPB_E_INVALID, "bad peer arguments (%d peers, rank %d)", n_peers, my_rank);
+    p.peer_scores = d_peer_ptrs;
+    p.n_peers = n_peers;
+    p.peer_slab_offset = static_cast<int64_t>(my_rank) * n_queries * n_docs;
+    p.done_counter = d_done_counter;
+    p.peer_flag_offset = flag_word_offset;
+    p.signal_value = signal_value;
+    p.my_rank = my_rank;
+  }
 
   // Two resident query tiles per CTA halve the L2->SMEM traffic per flop; a single tile only
   // when there is just one.
@@ -313,7 +327,7 @@ int cpb_maxsim_fwd(const void* d_q, int n_queries, int nq_pad, const void* d_doc
                    const int32_t* d_doc_start, const int32_t* d_doc_len, const float* d_doc_floor, int n_docs,
                    float* d_scores, int32_t* d_argmax, float* d_workspace, uint32_t flags, void* stream_) {
   return maxsim_fwd_impl(d_q, n_queries, nq_pad, d_docs, doc_rows, d_doc_start, d_doc_len, d_doc_floor, n_docs, d_scores,
-                         d_argmax, d_workspace, flags, 0, 0, nullptr, 0, 0, stream_);
+                         d_argmax, d_workspace, flags, 0, 0, nullptr, 0, 0, nullptr, 0, 0, nullptr, 0, 0, stream_);
 }
 
 int cpb_maxsim_fwd_balanced(const void* d_q, int n_queries, int nq_pad, const void* d_docs, int64_t doc_rows,
@@ -322,7 +336,25 @@ int cpb_maxsim_fwd_balanced(const void* d_q, int n_queries, int nq_pad, const vo
                             int max_doc_len, void* d_split_ws, int64_t split_ws_bytes, uint32_t epoch, void* stream_) {
   if (epoch == 0) return fail(CPB_E_INVALID, "epoch must be non-zero (a zero-initialised workspace means 'nothing published')");
   return maxsim_fwd_impl(d_q, n_queries, nq_pad, d_docs, doc_rows, d_doc_start, d_doc_len, d_doc_floor, n_docs, d_scores,
-                         d_argmax, d_workspace, flags, uniform_len, max_doc_len, d_split_ws, split_ws_bytes, epoch, stream_);
+                         d_argmax, d_workspace, flags, uniform_len, max_doc_len, d_split_ws, split_ws_bytes, epoch, nullptr,
+                         0, 0, nullptr, 0, 0, stream_);
+}
+
+int cpb_maxsim_fwd_allgather(const void* d_q, int n_queries, int nq_pad, const void* d_docs, int64_t doc_rows,
+                             const int32_t* d_doc_start, const int32_t* d_doc_len, const float* d_doc_floor, int n_docs,
+                             const uint64_t* d_peer_slabs, int n_peers, int my_rank, uint32_t flags, int uniform_len,
+                             int max_doc_len, void* d_split_ws, int64_t split_ws_bytes, uint32_t epoch,
+                             uint32_t* d_done_counter, int64_t flag_word_offset, uint32_t signal_value, void* stream_) {
+  if (!d_peer_slabs) return fail(CPB_E_INVALID, "null peer pointer array");
+  return maxsim_fwd_impl(d_q, n_queries, nq_pad, d_docs, doc_rows, d_doc_start, d_doc_len, d_doc_floor, n_docs, nullptr,
+                         nullptr, nullptr, flags, uniform_len, max_doc_len, d_split_ws, d_split_ws ? split_ws_bytes : 0,
+                         epoch, d_peer_slabs, n_peers, my_rank, d_done_counter, flag_word_offset, signal_value, stream_);
+}
+
+int cpb_wait_flags(const uint32_t* d_flags, int n, uint32_t value, void* stream_) {
+  if (!d_flags || n <= 0 || n > 64) return fail(CPB_E_INVALID, "bad flag array");
+  CPB_CUDA(cpb::wait_flags_launch(d_flags, n, value, static_cast<cudaStream_t>(stream_)));
+  return CPB_OK;
 }
 
 int64_t cpb_maxsim_split_workspace_bytes(int n_queries, int nq_pad) {

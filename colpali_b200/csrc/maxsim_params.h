@@ -38,6 +38,16 @@ struct MaxSimParams {
   int32_t* split_idx;  // same shape (argmax variant)
   uint32_t* split_flag;  // [q_groups_padded, doc_parts, R, 4]; a slot is valid when it holds `epoch`
   uint32_t epoch;
+  // fused all-gather: scores are stored straight into every peer GPU's slab [n_peers][n_queries][n_docs] over NVLink
+  const uint64_t* peer_scores;  // device array of n_peers base pointers (symmetric memory), or nullptr
+  int n_peers;
+  int64_t peer_slab_offset;     // my_rank * n_queries * n_docs (floats)
+  // completion signal of the fused all-gather: the last CTA to finish stores `signal_value` into word
+  // peer_flag_offset + my_rank of every peer's buffer (consumers wait on their own copy)
+  uint32_t* done_counter;       // local device word, zero before the first launch (the last CTA resets it)
+  int64_t peer_flag_offset;     // in 4-byte words from the slab base
+  uint32_t signal_value;
+  int my_rank;
   int dbg_delay;   // profiling only: cycles the epilogue holds an unread accumulator in CPB_DBG_SKIP_EPILOGUE mode
   int mma_split;   // K-steps of a job issued before the next job's barrier waits (5..8)
 };

@@ -422,8 +422,16 @@ maxsim_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       float x = round_ref ? round_bf16(mm) : mm;
       x = warp_sum(x);
       if (round_ref && p.nq_pad == 32) x = round_bf16(x);
-      if (lane == 0 && q < p.n_queries && !(p.flags & CPB_DBG_CLOCKS))
-        p.scores[static_cast<int64_t>(seg) * p.plane_stride + static_cast<int64_t>(q) * p.n_docs + doc] = x;
+      if (lane == 0 && q < p.n_queries && !(p.flags & CPB_DBG_CLOCKS)) {
+        if (p.peer_scores != nullptr) {
+          // fused all-gather of the score slabs: one 4-byte store per peer GPU, straight into its copy of
+          // gathered[my_rank] through the NVLink peer mapping (no collective kernel afterwards, only a barrier)
+          const int64_t off = p.peer_slab_offset + static_cast<int64_t>(q) * p.n_docs + doc;
+          for (int pr = 0; pr < p.n_peers; ++pr) reinterpret_cast<float*>(__ldg(p.peer_scores + pr))[off] = x;
+        } else {
+          p.scores[static_cast<int64_t>(seg) * p.plane_stride + static_cast<int64_t>(q) * p.n_docs + doc] = x;
+        }
+      }
     };
     auto doc_init = [&](int doc) { return (p.doc_floor != nullptr) ? __ldg(p.doc_floor + doc) : -INFINITY; };
 
@@ -742,6 +750,8 @@ maxsim_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   }
 
   // ---- teardown ---------------------------------------------------------------------------
+  if (p.peer_scores != nullptr && p.done_counter != nullptr && warp >= 2)
+    __threadfence_system();  // my peer stores are ordered before the completion signal below
   tc_fence_before();
   // no CTA may exit while a peer can still multicast into its shared memory or signal its barriers
   if (C > 1) cluster_sync_all(); else __syncthreads();
@@ -749,10 +759,39 @@ maxsim_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     p.scores[2 * blockIdx.x] = static_cast<float>(clock64() - dbg_c0);
     p.scores[2 * blockIdx.x + 1] = static_cast<float>(global_timer_ns() - dbg_t0);
   }
+  if (p.peer_scores != nullptr && p.done_counter != nullptr && threadIdx.x == 0) {
+    // fused all-gather completion: the last CTA of the grid tells every peer that this rank's slab is complete
+    __threadfence();
+    const unsigned prev = atomicAdd(p.done_counter, 1u);
+    if (prev + 1u == gridDim.x) {
+      *p.done_counter = 0u;  // ready for the next launch (stream ordered)
+      __threadfence_system();
+      for (int pr = 0; pr < p.n_peers; ++pr) {
+        volatile uint32_t* f = reinterpret_cast<volatile uint32_t*>(__ldg(p.peer_scores + pr)) + p.peer_flag_offset + p.my_rank;
+        *f = p.signal_value;
+      }
+    }
+  }
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
+}
+
+// Wait (on the stream) until flags[0..n) have all reached `value` (launch counters only grow; wrap-safe compare):
+// consumer side of the fused all-gather.
+__global__ void wait_flags_kernel(const uint32_t* flags, int n, uint32_t value) {
+  if (threadIdx.x >= n) return;
+  const volatile uint32_t* f = flags + threadIdx.x;
+  const uint64_t t0 = global_timer_ns();
+  while (static_cast<int32_t>(*f - value) < 0) {
+    if (global_timer_ns() - t0 > 4000000000ull) __trap();
+  }
+  __threadfence_system();
+}
+cudaError_t wait_flags_launch(const uint32_t* flags, int n, uint32_t value, cudaStream_t stream) {
+  wait_flags_kernel<<<1, 64, 0, stream>>>(flags, n, value);
+  return cudaGetLastError();
 }
 
 // scores[q, d] = sum_seg partial[seg, q, d]   (only used when a query spans more than 32 rows)

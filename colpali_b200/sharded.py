@@ -104,3 +104,89 @@ def score_sharded(
     dist.all_gather_into_tensor(all_s.view(world * nq, top_k), cand_s, group=group)
     dist.all_gather_into_tensor(all_i.view(world * nq, top_k), cand_i, group=group)
     return merge_topk(all_s.permute(1, 0, 2).reshape(nq, world * top_k), all_i.permute(1, 0, 2).reshape(nq, world * top_k), top_k)
+
+
+class FusedGatherScorer:
+    """Corpus-sharded scoring whose all-gather is fused into the MaxSim kernel (no collective kernel at all).
+
+    Every rank owns ``n_local`` documents; the kernel epilogue stores each score into all ranks' copies of
+    ``gathered[my_rank]`` through NVLink peer mappings of a symmetric-memory buffer
+    (``torch.distributed._symmetric_memory``), and the last CTA of each rank's grid then stores a per-launch completion
+    word into every peer; after ``wait()`` (or ``barrier()``) every rank holds ``[world, n_queries, n_local]``.
+    Needs queries of at most 32 tokens and equally sized shards.  ``available()`` tells whether symmetric memory can be
+    set up in this process group; callers fall back to ``score_sharded`` (NCCL all-gather) otherwise.
+    """
+
+    def __init__(self, n_queries: int, n_local: int, device: torch.device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank = dist.get_rank(self.group)
+        self.world = dist.get_world_size(self.group)
+        self.n_queries, self.n_local, self.device = n_queries, n_local, device
+        self.n_slab = self.world * n_queries * n_local
+        # gathered slabs followed by one completion word per rank (64 words reserved)
+        self.buf = symm_mem.empty(self.n_slab + 64, dtype=torch.float32, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, self.group)
+        self.peer_ptrs = torch.tensor(list(self.hdl.buffer_ptrs), dtype=torch.int64, device=device)
+        self.counter = torch.zeros(1, dtype=torch.int32, device=device)
+        self.step = 0
+        self.buf.zero_()
+        torch.cuda.synchronize(device)
+        self.hdl.barrier()
+
+    @staticmethod
+    def available(device: torch.device, group=None) -> bool:
+        try:
+            FusedGatherScorer(1, 1, device, group)
+            return True
+        except Exception:  # noqa: BLE001 - any failure means "use the NCCL path"
+            return False
+
+    def score(self, q, bank) -> torch.Tensor:
+        """Enqueue the fused kernel; returns the local gathered view ``[world, n_queries, n_local]`` (the other ranks'
+        slabs are complete after ``barrier()``)."""
+        from . import _lib
+        from .scoring import _EPOCH, _split_workspace
+
+        if q.n != self.n_queries or bank.n_docs != self.n_local or q.nq_pad != 32:
+            raise ValueError("FusedGatherScorer was built for a different shape (or queries longer than 32 tokens)")
+        lib = _lib.load()
+        dev = self.device
+        flags = _lib.CPB_FLAG_CONTIGUOUS if bank.contiguous else 0
+        split = None
+        if bank.contiguous and bank.max_len > 0:
+            split = _split_workspace(dev, lib.cpb_maxsim_split_workspace_bytes(q.n, q.nq_pad))
+        _EPOCH[0] = _EPOCH[0] % 0xFFFFFFF0 + 1
+        with torch.cuda.device(dev):
+            rc = lib.cpb_maxsim_fwd_allgather(
+                q.flat.data_ptr(), q.n, q.nq_pad, bank.flat.data_ptr(), bank.flat.shape[0],
+                bank.start.data_ptr(), bank.length.data_ptr(),
+                bank.floor.data_ptr() if bank.floor is not None else None, bank.n_docs,
+                self.peer_ptrs.data_ptr(), self.world, self.rank, flags,
+                bank.uniform_len, bank.max_len, split.data_ptr() if split is not None else None,
+                split.numel() if split is not None else 0, _EPOCH[0],
+                self.counter.data_ptr(), self.n_slab, self.step + 1, torch.cuda.current_stream(dev).cuda_stream,
+            )
+        _lib.check(rc, "cpb_maxsim_fwd_allgather")
+        _lib.count_launches(1)
+        self.step += 1
+        return self.buf[: self.n_slab].view(self.world, self.n_queries, self.n_local)
+
+    def wait(self) -> None:
+        """Enqueue a wait until every rank has signalled completion of its most recent ``score`` launch (all ranks must
+        have issued the same number of launches): afterwards the gathered view is complete."""
+        from . import _lib
+
+        lib = _lib.load()
+        flags = self.buf[self.n_slab :]
+        with torch.cuda.device(self.device):
+            rc = lib.cpb_wait_flags(flags.data_ptr(), self.world, self.step,
+                                    torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.check(rc, "cpb_wait_flags")
+        _lib.count_launches(1)
+
+    def barrier(self) -> None:
+        """Device-side cross-rank barrier on the current stream (symmetric-memory signal pads): after it, every rank's
+        kernel has finished and all slabs are visible."""
+        self.hdl.barrier()

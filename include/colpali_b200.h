@@ -109,6 +109,30 @@ int cpb_maxsim_fwd_balanced(const void* d_q, int n_queries, int nq_pad,
                             void* stream);
 int64_t cpb_maxsim_split_workspace_bytes(int n_queries, int nq_pad);
 
+/*
+ * Corpus-sharded scoring with the all-gather of the score slabs FUSED into the kernel epilogue (BASELINE configs[3];
+ * the reference scores on one device only).  Every rank owns n_docs documents and the same n_queries queries; each
+ * score is stored straight into all ranks' gathered buffers through NVLink peer mappings:
+ *     peer_slabs[r][my_rank][q][doc] = score      for r in 0..n_peers-1      (fp32, [n_peers, n_queries, n_docs] each)
+ * No collective kernel follows.  Completion: if d_done_counter is given, the last CTA of the grid stores `signal_value`
+ * into 32-bit word (flag_word_offset + my_rank) of every peer's buffer once all of this rank's scores are written
+ * (__threadfence_system ordered); a consumer waits until its own words [flag_word_offset, +n_peers) hold the value
+ * (cpb_wait_flags).  Without d_done_counter the caller needs a cross-rank barrier instead.  nq_pad must be 32.
+ *   d_done_counter   local device uint32, zero before the first launch (reset by the kernel), or NULL
+ *   d_peer_slabs   device array of n_peers uint64 base addresses of the peers' gathered buffers (this rank's included),
+ *                  e.g. torch.distributed._symmetric_memory handle.buffer_ptrs_dev
+ * Other arguments as cpb_maxsim_fwd_balanced (d_split_ws may be NULL).
+ */
+int cpb_maxsim_fwd_allgather(const void* d_q, int n_queries, int nq_pad,
+                             const void* d_docs, int64_t doc_rows,
+                             const int32_t* d_doc_start, const int32_t* d_doc_len, const float* d_doc_floor, int n_docs,
+                             const uint64_t* d_peer_slabs, int n_peers, int my_rank, uint32_t flags,
+                             int uniform_len, int max_doc_len, void* d_split_ws, int64_t split_ws_bytes, uint32_t epoch,
+                             uint32_t* d_done_counter, int64_t flag_word_offset, uint32_t signal_value, void* stream);
+
+/* Enqueue a wait on `stream` until d_flags[0..n) all equal `value` (consumer side of cpb_maxsim_fwd_allgather). */
+int cpb_wait_flags(const uint32_t* d_flags, int n, uint32_t value, void* stream);
+
 /* Bytes of d_workspace cpb_maxsim_fwd needs for this shape (0 when nq_pad == 32). */
 int64_t cpb_maxsim_workspace_bytes(int n_queries, int nq_pad, int n_docs);
 

@@ -60,3 +60,47 @@ def test_two_ranks_nccl(tmp_path):
         got = np.load(os.path.join(tmp_path, f"r{r}.npz"))
         assert np.allclose(got["full"], want.numpy(), rtol=1e-5, atol=1e-4)
         assert np.array_equal(got["ti"], torch.topk(torch.from_numpy(got["full"]), 10, dim=1).indices.numpy())
+
+
+def _fused_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from colpali_b200.sharded import FusedGatherScorer
+
+    qs = O.unit_rows((8, 32, 128), 5)
+    docs = O.unit_rows((60, 200, 128), 50 + rank)          # every rank owns a different dense shard
+    bank = cb.DocBank.from_passages(docs.to(dev), dev)
+    qb = cb.QueryBlock(qs.to(dev), dev)
+    ok = FusedGatherScorer.available(dev)
+    res = {"available": np.array(ok)}
+    if ok:
+        sc = FusedGatherScorer(8, 60, dev)
+        for _ in range(3):
+            gathered = sc.score(qb, bank)
+            sc.wait()  # per-launch completion words written by the last CTA of every rank's grid
+            torch.cuda.synchronize()
+            dist.barrier()  # nobody starts the next launch (which overwrites the slabs) before everyone has read
+        snap = gathered.clone()
+        gathered = snap
+        res["gathered"] = gathered.cpu().numpy()
+        res["local"] = cb.maxsim(qb, bank).cpu().numpy()
+    np.savez(os.path.join(out_dir, f"f{rank}.npz"), **res)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_fused_allgather_two_ranks(tmp_path):
+    """The kernel stores its scores straight into both ranks' gathered buffers (NVLink peer stores)."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_fused_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r = [np.load(os.path.join(tmp_path, f"f{k}.npz")) for k in range(2)]
+    if not bool(r[0]["available"]):
+        pytest.skip("symmetric memory is not available in this environment")
+    for k in range(2):
+        for src in range(2):
+            assert np.array_equal(r[k]["gathered"][src], r[src]["local"]), (k, src)
