@@ -823,11 +823,14 @@ template <int R, bool kArgmax>
 static cudaError_t launch_variant(const CUtensorMap& tq, const CUtensorMap& td, const CUtensorMap& tt,
                                   const MaxSimParams& p, int grid, cudaStream_t stream) {
   auto kern = maxsim_fwd_kernel<R, kArgmax>;
-  static bool attr_set = false;  // per instantiation; the attribute is sticky for the process (single device type)
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<R>::kAlloc);
+  static bool attr_set[64] = {};  // per instantiation and per device: the attribute is sticky once set
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<R>::kAlloc);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   cudaLaunchConfig_t cfg{};
   cudaLaunchAttribute attr[1];
