@@ -57,3 +57,39 @@ def test_product_path_fails_loudly_on_cpu():
         cb.score_multi_vector([], q, device="cpu")
     with pytest.raises(ValueError, match="No passages"):
         cb.score_multi_vector(q, [], device="cpu")
+
+
+def test_every_entry_point_validates_before_touching_cuda(lib):
+    """Bad arguments are rejected with CPB_E_INVALID / CPB_E_UNSUPPORTED and a message, without a GPU."""
+    INVALID, UNSUPPORTED = -1, -2
+    # losses
+    rc = lib.cpb_colbert_loss_fwd(None, None, 4, 32, 3, 0, 0.02, 1, 0, 0.95, 0.5, 0, None, None, None, None)
+    assert rc == INVALID and b"positive index out of range" in lib.cpb_last_error()          # offset + B > C
+    rc = lib.cpb_colbert_loss_fwd(None, None, 4, 32, 4, 7, 0.02, 1, 0, 0.95, 0.5, 0, None, None, None, None)
+    assert rc == INVALID and b"unknown loss mode" in lib.cpb_last_error()
+    rc = lib.cpb_colbert_loss_fwd(None, None, 4, 32, 6, 2, 0.02, 1, 0, 0.95, 0.5, 0, None, None, None, None)
+    assert rc == INVALID and b"sigmoid" in lib.cpb_last_error()                               # needs a square matrix
+    rc = lib.cpb_colbert_loss_fwd(None, None, 4, 32, 4, 0, -1.0, 1, 0, 0.95, 0.5, 0, None, None, None, None)
+    assert rc == INVALID and b"temperature" in lib.cpb_last_error()
+    rc = lib.cpb_colbert_neg_loss_fwd(None, None, None, 4, 32, 4, 2, 0, 0.02, 1, 0, 0.95, 0.5, 0.5, 0, None, None, None, None)
+    assert rc == INVALID
+    # backward
+    rc = lib.cpb_maxsim_bwd(None, None, None, None, 4, 32, None, 10, None, 3, None, None, None)
+    assert rc == INVALID and b"null device pointer" in lib.cpb_last_error()
+    # head
+    rc = lib.cpb_head_fwd(None, 0, 1536, None, None, 128, None, None, None, 0, None)
+    assert rc == INVALID
+    rc = lib.cpb_head_fwd(None, 10, 1536, None, None, 320, None, None, None, 0, None)
+    assert rc == UNSUPPORTED and b"320" in lib.cpb_last_error()                               # ColQwen3 dim: next row
+    rc = lib.cpb_head_fwd(None, 10, 1000, None, None, 128, None, None, None, 0, None)
+    assert rc == UNSUPPORTED and b"multiple of 64" in lib.cpb_last_error()
+    # balanced / all-gather variants and their helpers
+    rc = lib.cpb_maxsim_fwd_balanced(None, 1, 32, None, 0, None, None, None, 1, None, None, None, 0, 0, 0, None, 0, 0, None)
+    assert rc == INVALID and b"epoch" in lib.cpb_last_error()
+    rc = lib.cpb_maxsim_fwd_allgather(None, 1, 32, None, 0, None, None, None, 1, None, 2, 0, 0, 0, 0, None, 0, 1, None, 0, 1, None)
+    assert rc == INVALID and b"peer" in lib.cpb_last_error()
+    assert lib.cpb_wait_flags(None, 2, 1, None) == INVALID
+    assert lib.cpb_maxsim_split_workspace_bytes(32, 32) > 0
+    # tuning knobs
+    assert lib.cpb_set_option(b"cluster", 3) == INVALID and lib.cpb_set_option(b"no_such_option", 1) == INVALID
+    assert lib.cpb_set_option(b"cluster", 0) == 0 and lib.cpb_set_option(b"balanced", 1) == 0
