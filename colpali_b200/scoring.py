@@ -14,7 +14,7 @@ per-token maximum is ``max(real, 0)``).  ``DocBank`` records that as a per-docum
 
 from __future__ import annotations
 
-from typing import List, Optional, Sequence, Union
+from typing import List, Optional, Union
 
 import torch
 

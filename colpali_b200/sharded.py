@@ -16,7 +16,7 @@ so the host-side logic (sharding, padding, id offsets, merge) can be exercised u
 
 from __future__ import annotations
 
-from typing import Callable, List, Optional, Sequence, Tuple
+from typing import Callable, List, Optional, Tuple
 
 import torch
 import torch.distributed as dist

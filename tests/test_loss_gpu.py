@@ -2,7 +2,6 @@
 outputs (tests/golden/loss_*.npz) and the CPU oracle."""
 import math
 
-import numpy as np
 import pytest
 import torch
 

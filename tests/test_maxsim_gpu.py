@@ -1,6 +1,5 @@
 """GPU parity: the fused sm_100a MaxSim kernel, called through the C ABI, against the CPU oracle, the
 reference-generated golden vectors, and size-independent properties at the full BASELINE size."""
-import numpy as np
 import pytest
 import torch
 
