@@ -6,6 +6,7 @@ Public names mirror the reference (illuin-tech/colpali):
   fused_head                                 <- custom_text_proj + norm + mask tail of every Col* model forward
 """
 
+from . import exchange
 from ._lib import ColpaliB200Error
 from .head import fused_head
 from .install import install, uninstall
@@ -28,6 +29,7 @@ __all__ = [
     "ColbertSigmoidLoss",
     "ColpaliB200Error",
     "DocBank",
+    "exchange",
     "fused_head",
     "install",
     "uninstall",
