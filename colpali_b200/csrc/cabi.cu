@@ -18,6 +18,9 @@ cudaError_t maxsim_launch(const CUtensorMap& tq, const CUtensorMap& td, const CU
                           int r, bool argmax, int grid, cudaStream_t stream);
 int maxsim_max_clusters(int r, int cluster);
 int maxsim_tile_n();
+cudaError_t maxsim_kpipe_launch(const CUtensorMap& tq, const CUtensorMap& td, const CUtensorMap& tt, const MaxSimParams& p,
+                                int dim_panels, bool argmax, int grid, cudaStream_t stream);
+int maxsim_kpipe_max_clusters(int dim_panels, int cluster);
 cudaError_t wait_flags_launch(const uint32_t* flags, int n, uint32_t value, cudaStream_t stream);
 cudaError_t maxsim_reduce_segments(const float* partial, float* out, int64_t plane, int nseg, int round_ref,
                                    cudaStream_t stream);
@@ -431,6 +434,62 @@ int cpb_head_fwd(const void* d_hidden, int64_t n_tokens, int hidden, const void*
   const int64_t pairs = (n_tokens + 255) / 256;
   const int grid = static_cast<int>(pairs < di.sm_count ? pairs : di.sm_count);
   CPB_CUDA(cpb::head_launch(th, tw, p, grid, static_cast<cudaStream_t>(stream_)));
+  return CPB_OK;
+}
+
+// DRAFT (r2-drafts): MaxSim forward for embedding dims 192 / 256 / 320 (K-pipelined kernel, one query tile per CTA).
+// dim must be a multiple of 64 in (128, 320]; queries and documents are [rows, dim] bf16.  No balancing, no fused gather yet.
+int cpb_maxsim_fwd_dim(const void* d_q, int n_queries, int nq_pad, const void* d_docs, int64_t doc_rows,
+                       const int32_t* d_doc_start, const int32_t* d_doc_len, const float* d_doc_floor, int n_docs,
+                       float* d_scores, int32_t* d_argmax, float* d_workspace, uint32_t flags, int dim, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (dim <= 128 || dim > 320 || (dim % 64) != 0) return fail(CPB_E_UNSUPPORTED, "dim=%d: this entry point serves 192, 256 and 320", dim);
+  if (n_queries <= 0 || n_docs <= 0) return fail(CPB_E_INVALID, "n_queries=%d and n_docs=%d must be positive", n_queries, n_docs);
+  if (nq_pad <= 0 || (nq_pad % 32) != 0) return fail(CPB_E_INVALID, "nq_pad=%d must be a positive multiple of 32", nq_pad);
+  if (!d_q || !d_docs || !d_doc_start || !d_doc_len || !d_scores) return fail(CPB_E_INVALID, "null device pointer");
+  if (doc_rows <= 0 || doc_rows > 0x7fffffffLL) return fail(CPB_E_INVALID, "doc_rows out of range");
+  const int nseg = nq_pad / 32;
+  if (nseg > 1 && !d_workspace) return fail(CPB_E_INVALID, "nq_pad=%d needs a workspace", nq_pad);
+  DevInfo di;
+  int rc = current_device_info(&di);
+  if (rc != CPB_OK) return rc;
+  if (di.major != 10) return fail(CPB_E_DEVICE, "device is sm_%d%d; this library needs sm_100 (B200)", di.major, di.minor);
+  const int panels = dim / 64;
+  cpb::MaxSimParams p{};
+  p.q = d_q;
+  p.doc_start = d_doc_start;
+  p.doc_len = d_doc_len;
+  p.doc_floor = d_doc_floor;
+  p.argmax = d_argmax;
+  p.plane_stride = static_cast<int64_t>(n_queries) * n_docs;
+  p.n_queries = n_queries;
+  p.nq_pad = nq_pad;
+  p.q_rows = n_queries * nq_pad;
+  p.n_docs = n_docs;
+  p.num_qtiles = (p.q_rows + 127) / 128;
+  p.scores = (nseg == 1) ? d_scores : d_workspace;
+  p.q_groups = p.num_qtiles;  // one query tile per CTA
+  int cluster = (p.q_groups >= 2) ? 2 : 1;
+  int max_clusters = cpb::maxsim_kpipe_max_clusters(panels, cluster);
+  if (max_clusters <= 0) return fail(CPB_E_CUDA, "K-pipelined kernel cannot be resident on this device");
+  p.cluster = cluster;
+  p.group_sets = (p.q_groups + cluster - 1) / cluster;
+  int parts = max_clusters / p.group_sets;
+  if (parts < 1) parts = 1;
+  if (parts > n_docs) parts = n_docs;
+  p.doc_parts = parts;
+  p.flags = flags | g_opt_debug_flags;
+  const int grid = p.group_sets * p.doc_parts * cluster;
+  CUtensorMap tq, td, tt;
+  rc = make_bf16_rowmajor_map(&tq, d_q, p.q_rows, dim, 128);
+  if (rc != CPB_OK) return rc;
+  rc = make_bf16_rowmajor_map(&td, d_docs, doc_rows, dim, 256 / cluster);
+  if (rc != CPB_OK) return rc;
+  rc = make_bf16_rowmajor_map(&tt, d_docs, doc_rows, dim, 32);
+  if (rc != CPB_OK) return rc;
+  CPB_CUDA(cpb::maxsim_kpipe_launch(tq, td, tt, p, panels, d_argmax != nullptr, grid, stream));
+  if (nseg > 1)
+    CPB_CUDA(cpb::maxsim_reduce_segments(d_workspace, d_scores, p.plane_stride, nseg, (flags & CPB_FLAG_ROUND_BF16) ? 1 : 0, stream));
   return CPB_OK;
 }
 

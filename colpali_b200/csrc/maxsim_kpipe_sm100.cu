@@ -721,7 +721,36 @@ static cudaError_t launch_variant(const CUtensorMap& tq, const CUtensorMap& td, 
   return cudaLaunchKernelEx(&cfg, kern, tq, td, tt, p);
 }
 
+template <int KP>
+static int max_clusters_variant(int cluster) {
+  auto kern = maxsim_kpipe_kernel<KP, false>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<KP>::kAlloc) != cudaSuccess) return 0;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(cluster));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = SmemLayout<KP>::kAlloc;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = static_cast<unsigned>(cluster);
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) return 0;
+  return n;
+}
+
 }  // namespace kpipe
+
+int maxsim_kpipe_max_clusters(int dim_panels, int cluster) {
+  switch (dim_panels) {
+    case 3: return kpipe::max_clusters_variant<3>(cluster);
+    case 4: return kpipe::max_clusters_variant<4>(cluster);
+    case 5: return kpipe::max_clusters_variant<5>(cluster);
+    default: return 0;
+  }
+}
 
 // dim_panels = padded embedding dim / 64 (3, 4 or 5; dims <= 128 use maxsim_sm100.cu)
 cudaError_t maxsim_kpipe_launch(const CUtensorMap& tq, const CUtensorMap& td, const CUtensorMap& tt, const MaxSimParams& p,
