@@ -23,6 +23,7 @@ EXPORTED_SYMBOLS = (
     "cpb_maxsim_fwd",
     "cpb_maxsim_workspace_bytes",
     "cpb_maxsim_fwd_balanced",
+    "cpb_maxsim_fwd_dim",
     "cpb_maxsim_split_workspace_bytes",
     "cpb_maxsim_fwd_allgather",
     "cpb_wait_flags",
@@ -78,6 +79,8 @@ def load() -> ctypes.CDLL:
         c_vp, c_vp, c_vp,  # d_scores, d_argmax, d_workspace
         c_u32, c_vp,  # flags, stream
     ]
+    lib.cpb_maxsim_fwd_dim.restype = c_i
+    lib.cpb_maxsim_fwd_dim.argtypes = lib.cpb_maxsim_fwd.argtypes[:-1] + [c_i, c_vp]
     lib.cpb_maxsim_split_workspace_bytes.restype = c_i64
     lib.cpb_maxsim_split_workspace_bytes.argtypes = [c_i, c_i]
     lib.cpb_maxsim_fwd_balanced.restype = c_i

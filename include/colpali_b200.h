@@ -133,6 +133,16 @@ int cpb_maxsim_fwd_allgather(const void* d_q, int n_queries, int nq_pad,
 /* Enqueue a wait on `stream` until d_flags[0..n) all equal `value` (consumer side of cpb_maxsim_fwd_allgather). */
 int cpb_wait_flags(const uint32_t* d_flags, int n, uint32_t value, void* stream);
 
+/*
+ * DRAFT: cpb_maxsim_fwd for embedding dims 192 / 256 / 320 (ColQwen3: models/qwen3/colqwen3/modeling_colqwen3.py:48).
+ * d_q and d_docs are [rows, dim] bf16; every other argument as cpb_maxsim_fwd.  Whole-document partitions only.
+ */
+int cpb_maxsim_fwd_dim(const void* d_q, int n_queries, int nq_pad,
+                       const void* d_docs, int64_t doc_rows,
+                       const int32_t* d_doc_start, const int32_t* d_doc_len, const float* d_doc_floor, int n_docs,
+                       float* d_scores, int32_t* d_argmax, float* d_workspace,
+                       uint32_t flags, int dim, void* stream);
+
 /* Bytes of d_workspace cpb_maxsim_fwd needs for this shape (0 when nq_pad == 32). */
 int64_t cpb_maxsim_workspace_bytes(int n_queries, int nq_pad, int n_docs);
 
