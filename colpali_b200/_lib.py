@@ -30,6 +30,9 @@ EXPORTED_SYMBOLS = (
     "cpb_colbert_loss_fwd",
     "cpb_colbert_neg_loss_fwd",
     "cpb_maxsim_bwd",
+    "cpb_maxsim_bwd_dim",
+    "cpb_colbert_loss_fwd_dim",
+    "cpb_colbert_neg_loss_fwd_dim",
     "cpb_head_fwd",
 )
 
@@ -107,6 +110,10 @@ def load() -> ctypes.CDLL:
         c_f, c_i, c_i, c_f, c_f, c_f, c_i,  # temperature, normalize, filter, threshold, factor, in_batch_weight, offset
         c_vp, c_vp, c_vp, c_vp,  # d_loss, d_grad_scores, d_grad_neg_scores, stream
     ]
+    for name in ("cpb_colbert_loss_fwd", "cpb_colbert_neg_loss_fwd"):  # DRAFT: ..., dim, stream
+        fn = getattr(lib, name + "_dim")
+        fn.restype = c_i
+        fn.argtypes = getattr(lib, name).argtypes[:-1] + [c_i, c_vp]
     lib.cpb_maxsim_bwd.restype = c_i
     lib.cpb_maxsim_bwd.argtypes = [
         c_vp, c_vp, c_vp,  # d_grad_scores, d_grad_out, d_argmax
@@ -114,6 +121,8 @@ def load() -> ctypes.CDLL:
         c_vp, c_i64, c_vp, c_i,  # d_docs, doc_rows, d_doc_start, n_docs
         c_vp, c_vp, c_vp,  # d_dq, d_dd, stream
     ]
+    lib.cpb_maxsim_bwd_dim.restype = c_i
+    lib.cpb_maxsim_bwd_dim.argtypes = lib.cpb_maxsim_bwd.argtypes[:-1] + [c_i, c_vp]  # ..., dim, stream
     lib.cpb_head_fwd.restype = c_i
     lib.cpb_head_fwd.argtypes = [
         c_vp, c_i64, c_i,  # d_hidden, n_tokens, hidden

@@ -281,7 +281,9 @@ static int loss_fwd_impl(const float* d_scores, const void* d_q, int n_queries, 
                          float temperature, int normalize_scores, int pos_aware_negative_filtering,
                          float filter_threshold, float filter_factor, int offset, const float* d_neg_scores, int n_neg,
                          float in_batch_weight, float* d_loss, float* d_grad_scores, float* d_grad_neg,
-                         float* d_bounds, void* stream_) {
+                         float* d_bounds, int q_dim, void* stream_) {
+  if (q_dim != 128 && q_dim != 192 && q_dim != 256 && q_dim != 320)
+    return fail(CPB_E_UNSUPPORTED, "embedding dim %d is not supported by this build (128, 192, 256, 320)", q_dim);
   if (n_queries <= 0 || n_docs <= 0) return fail(CPB_E_INVALID, "n_queries=%d and n_docs=%d must be positive", n_queries, n_docs);
   if (nq_pad <= 0 || (nq_pad % 32) != 0) return fail(CPB_E_INVALID, "nq_pad=%d must be a positive multiple of 32", nq_pad);
   if (mode != CPB_LOSS_CE && mode != CPB_LOSS_PAIRWISE && mode != CPB_LOSS_SIGMOID) return fail(CPB_E_INVALID, "unknown loss mode %d", mode);
@@ -296,6 +298,7 @@ static int loss_fwd_impl(const float* d_scores, const void* d_q, int n_queries, 
   cpb::LossParams p{};
   p.scores = d_scores;
   p.q = static_cast<const __nv_bfloat16*>(d_q);
+  p.q_dim = q_dim;
   p.loss = d_loss;
   p.grad = d_grad_scores;
   p.bounds = d_bounds;
@@ -323,7 +326,16 @@ int cpb_colbert_loss_fwd(const float* d_scores, const void* d_q, int n_queries, 
                          float* d_bounds, void* stream_) {
   return loss_fwd_impl(d_scores, d_q, n_queries, nq_pad, n_docs, mode, temperature, normalize_scores,
                        pos_aware_negative_filtering, filter_threshold, filter_factor, offset, nullptr, 0, 1.f, d_loss,
-                       d_grad_scores, nullptr, d_bounds, stream_);
+                       d_grad_scores, nullptr, d_bounds, 128, stream_);
+}
+
+int cpb_colbert_loss_fwd_dim(const float* d_scores, const void* d_q, int n_queries, int nq_pad, int n_docs, int mode,
+                             float temperature, int normalize_scores, int pos_aware_negative_filtering,
+                             float filter_threshold, float filter_factor, int offset, float* d_loss,
+                             float* d_grad_scores, float* d_bounds, int dim, void* stream_) {
+  return loss_fwd_impl(d_scores, d_q, n_queries, nq_pad, n_docs, mode, temperature, normalize_scores,
+                       pos_aware_negative_filtering, filter_threshold, filter_factor, offset, nullptr, 0, 1.f, d_loss,
+                       d_grad_scores, nullptr, d_bounds, dim, stream_);
 }
 
 int cpb_maxsim_fwd(const void* d_q, int n_queries, int nq_pad, const void* d_docs, int64_t doc_rows,
@@ -375,12 +387,32 @@ int cpb_colbert_neg_loss_fwd(const float* d_scores, const float* d_neg_scores, c
   if (!d_neg_scores) return fail(CPB_E_INVALID, "null device pointer");
   return loss_fwd_impl(d_scores, d_q, n_queries, nq_pad, n_docs, inner_mode, temperature, normalize_scores,
                        pos_aware_negative_filtering, filter_threshold, filter_factor, offset, d_neg_scores, n_neg,
-                       in_batch_term_weight, d_loss, d_grad_scores, d_grad_neg_scores, nullptr, stream_);
+                       in_batch_term_weight, d_loss, d_grad_scores, d_grad_neg_scores, nullptr, 128, stream_);
+}
+
+int cpb_colbert_neg_loss_fwd_dim(const float* d_scores, const float* d_neg_scores, const void* d_q, int n_queries,
+                                 int nq_pad, int n_docs, int n_neg, int inner_mode, float temperature,
+                                 int normalize_scores, int pos_aware_negative_filtering, float filter_threshold,
+                                 float filter_factor, float in_batch_term_weight, int offset, float* d_loss,
+                                 float* d_grad_scores, float* d_grad_neg_scores, int dim, void* stream_) {
+  if (!d_neg_scores) return fail(CPB_E_INVALID, "null device pointer");
+  return loss_fwd_impl(d_scores, d_q, n_queries, nq_pad, n_docs, inner_mode, temperature, normalize_scores,
+                       pos_aware_negative_filtering, filter_threshold, filter_factor, offset, d_neg_scores, n_neg,
+                       in_batch_term_weight, d_loss, d_grad_scores, d_grad_neg_scores, nullptr, dim, stream_);
 }
 
 int cpb_maxsim_bwd(const float* d_grad_scores, const float* d_grad_out, const int32_t* d_argmax, const void* d_q,
                    int n_queries, int nq_pad, const void* d_docs, int64_t doc_rows, const int32_t* d_doc_start,
                    int n_docs, float* d_dq, float* d_dd, void* stream_) {
+  return cpb_maxsim_bwd_dim(d_grad_scores, d_grad_out, d_argmax, d_q, n_queries, nq_pad, d_docs, doc_rows, d_doc_start,
+                            n_docs, d_dq, d_dd, 128, stream_);
+}
+
+int cpb_maxsim_bwd_dim(const float* d_grad_scores, const float* d_grad_out, const int32_t* d_argmax, const void* d_q,
+                       int n_queries, int nq_pad, const void* d_docs, int64_t doc_rows, const int32_t* d_doc_start,
+                       int n_docs, float* d_dq, float* d_dd, int dim, void* stream_) {
+  if (dim != 128 && dim != 192 && dim != 256 && dim != 320)
+    return fail(CPB_E_UNSUPPORTED, "embedding dim %d is not supported by this build (128, 192, 256, 320)", dim);
   if (n_queries <= 0 || n_docs <= 0) return fail(CPB_E_INVALID, "n_queries=%d and n_docs=%d must be positive", n_queries, n_docs);
   if (nq_pad <= 0 || (nq_pad % 32) != 0) return fail(CPB_E_INVALID, "nq_pad=%d must be a positive multiple of 32", nq_pad);
   if (!d_grad_scores || !d_argmax || !d_q || !d_docs || !d_doc_start) return fail(CPB_E_INVALID, "null device pointer");
@@ -401,6 +433,7 @@ int cpb_maxsim_bwd(const float* d_grad_scores, const float* d_grad_out, const in
   p.C = n_docs;
   p.nq_pad = nq_pad;
   p.q_rows = n_queries * nq_pad;
+  p.dim = dim;
   CPB_CUDA(cpb::maxsim_bwd_launch(p, static_cast<cudaStream_t>(stream_)));
   return CPB_OK;
 }

@@ -205,6 +205,23 @@ int cpb_maxsim_bwd(const float* d_grad_scores, const float* d_grad_out, const in
                    const void* d_docs, int64_t doc_rows, const int32_t* d_doc_start, int n_docs,
                    float* d_dq, float* d_dd, void* stream);
 
+/* DRAFT: the two loss entry points for d_q of shape [n_queries * nq_pad, dim], dim in {128, 192, 256, 320}. */
+int cpb_colbert_loss_fwd_dim(const float* d_scores, const void* d_q, int n_queries, int nq_pad, int n_docs, int mode,
+                             float temperature, int normalize_scores, int pos_aware_negative_filtering,
+                             float filter_threshold, float filter_factor, int offset,
+                             float* d_loss, float* d_grad_scores, float* d_bounds, int dim, void* stream);
+int cpb_colbert_neg_loss_fwd_dim(const float* d_scores, const float* d_neg_scores, const void* d_q, int n_queries,
+                                 int nq_pad, int n_docs, int n_neg, int inner_mode, float temperature,
+                                 int normalize_scores, int pos_aware_negative_filtering, float filter_threshold,
+                                 float filter_factor, float in_batch_term_weight, int offset,
+                                 float* d_loss, float* d_grad_scores, float* d_grad_neg_scores, int dim, void* stream);
+
+/* DRAFT: cpb_maxsim_bwd for [rows, dim] operands and gradients, dim in {128, 192, 256, 320} (see cpb_maxsim_fwd_dim). */
+int cpb_maxsim_bwd_dim(const float* d_grad_scores, const float* d_grad_out, const int32_t* d_argmax,
+                       const void* d_q, int n_queries, int nq_pad,
+                       const void* d_docs, int64_t doc_rows, const int32_t* d_doc_start, int n_docs,
+                       float* d_dq, float* d_dd, int dim, void* stream);
+
 /* flags for cpb_head_fwd */
 #define CPB_HEAD_CLAMP_NORM 1u      /* norm = max(norm, 1e-12): ColModernVBert variant (modeling_colmodernvbert.py:59) */
 #define CPB_HEAD_SINGLE_ROUNDING 2u /* keep fp32 until the final store instead of emulating the reference's
