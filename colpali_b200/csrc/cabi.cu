@@ -32,6 +32,7 @@ thread_local char g_err[512] = "";
 
 // tuning knobs (cpb_set_option); 0 = choose automatically
 int g_opt_cluster = 0;
+static int g_head_cluster = 0;  // DRAFT: 0 = auto (2 when there are at least two token tiles), 1, 2
 int g_opt_qtiles_per_cta = 0;
 unsigned g_opt_debug_flags = 0;
 int g_opt_mma_split = 6;
@@ -143,6 +144,9 @@ int cpb_set_option(const char* name, int value) {
   } else if (!strcmp(name, "mma_split")) {
     if (value < 5 || value > 8) return fail(CPB_E_INVALID, "mma_split must be 5..8");
     g_opt_mma_split = value;
+  } else if (!strcmp(name, "head_cluster")) {
+    if (value < 0 || value > 2) return fail(CPB_E_INVALID, "head_cluster must be 0, 1 or 2");
+    g_head_cluster = value;
   } else if (!strcmp(name, "balanced")) {
     g_opt_balanced = value != 0;
   } else if (!strcmp(name, "debug_delay")) {
@@ -443,7 +447,9 @@ int cpb_head_fwd(const void* d_hidden, int64_t n_tokens, int hidden, const void*
                  void* stream_) {
   if (n_tokens <= 0) return fail(CPB_E_INVALID, "n_tokens=%lld must be positive", static_cast<long long>(n_tokens));
   if (n_tokens > 0x7fffff00LL) return fail(CPB_E_INVALID, "n_tokens too large");
-  if (dim != 128) return fail(CPB_E_UNSUPPORTED, "projection dim %d is not supported by this build (128 only)", dim);
+  const bool wide = dim > 128;  // DRAFT: head_wide_sm100.cu
+  if (dim != 128 && !(wide && dim <= 320 && (dim % 32) == 0))
+    return fail(CPB_E_UNSUPPORTED, "projection dim %d is not supported by this build (128, or a multiple of 32 up to 320)", dim);
   if (hidden <= 0 || (hidden % 64) != 0) return fail(CPB_E_UNSUPPORTED, "hidden size %d must be a positive multiple of 64", hidden);
   if (!d_hidden || !d_weight || !d_out) return fail(CPB_E_INVALID, "null device pointer");
   if (reinterpret_cast<uintptr_t>(d_out) & 15u) return fail(CPB_E_INVALID, "d_out is not 16-byte aligned");
@@ -454,7 +460,7 @@ int cpb_head_fwd(const void* d_hidden, int64_t n_tokens, int hidden, const void*
   CUtensorMap th, tw;
   rc = make_bf16_rowmajor_map(&th, d_hidden, n_tokens, hidden, 128);
   if (rc != CPB_OK) return rc;
-  rc = make_bf16_rowmajor_map(&tw, d_weight, dim, hidden, 128);
+  rc = make_bf16_rowmajor_map(&tw, d_weight, dim, hidden, wide ? dim / 2 : 128);
   if (rc != CPB_OK) return rc;
   cpb::HeadParams p{};
   p.bias = static_cast<const __nv_bfloat16*>(d_bias);
@@ -464,6 +470,18 @@ int cpb_head_fwd(const void* d_hidden, int64_t n_tokens, int hidden, const void*
   p.n_tokens = n_tokens;
   p.hidden = hidden;
   p.flags = flags;
+  p.dim = dim;
+  if (wide) {
+    p.stages = cpb::head_wide_stages(dim);
+    if (p.stages < 2) return fail(CPB_E_UNSUPPORTED, "projection dim %d does not fit the shared-memory ring", dim);
+    const int64_t tiles = (n_tokens + 127) / 128;
+    p.cluster = (g_head_cluster == 1 || tiles < 2) ? 1 : 2;
+    const int64_t rounds = (tiles + p.cluster - 1) / p.cluster;
+    const int64_t max_clusters = di.sm_count / p.cluster;
+    const int grid = static_cast<int>((rounds < max_clusters ? rounds : max_clusters) * p.cluster);
+    CPB_CUDA(cpb::head_wide_launch(th, tw, p, grid, static_cast<cudaStream_t>(stream_)));
+    return CPB_OK;
+  }
   const int64_t pairs = (n_tokens + 255) / 256;
   const int grid = static_cast<int>(pairs < di.sm_count ? pairs : di.sm_count);
   CPB_CUDA(cpb::head_launch(th, tw, p, grid, static_cast<cudaStream_t>(stream_)));
