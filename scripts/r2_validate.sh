@@ -8,8 +8,8 @@ run() { echo "== $1"; shift; timeout "$@" 2>&1 | tail -8; echo "-- exit ${PIPEST
 run "validated suite" 900 python -m pytest tests -m gpu -x -q --deselect tests/test_maxsim_gpu.py::test_wide_embeddings_k_pipelined_kernel \
     --deselect tests/test_loss_gpu.py::test_wide_embeddings_loss_and_gradients --deselect tests/test_head_gpu.py::test_wide_projection_dims_against_oracle
 # 1. drafts, smallest first; -x inside each file so the first failure is reported with its traceback
-run "wide head, cluster 1" 300 python -m pytest tests/test_head_gpu.py -q -x -k "wide_projection and 1]"
-run "wide head, cluster 2" 300 python -m pytest tests/test_head_gpu.py -q -x -k "wide_projection and 2]"
+run "wide head, cluster 1" 300 python -m pytest tests/test_head_gpu.py -q -x -k "wide_projection and cluster1"
+run "wide head, cluster 2" 300 python -m pytest tests/test_head_gpu.py -q -x -k "wide_projection and cluster2"
 run "K-pipelined scorer" 300 python -m pytest tests/test_maxsim_gpu.py -q -x -k wide_embeddings
 run "wide loss + backward" 300 python -m pytest tests/test_loss_gpu.py -q -x -k wide_embeddings
 # 2. timings

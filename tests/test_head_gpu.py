@@ -89,7 +89,7 @@ def test_unsupported_shapes_fail_loudly():
                       torch.zeros(200, 128, dtype=torch.bfloat16, device=DEV), None)      # dim % 32 != 0
 
 
-@pytest.mark.parametrize("head_cluster", (1, 2))
+@pytest.mark.parametrize("head_cluster", (1, 2), ids=("cluster1", "cluster2"))
 @pytest.mark.parametrize("tokens,hidden,dim", [(5000, 2560, 320), (777, 2048, 320), (130, 64, 320), (1000, 1536, 192),
                                                (1000, 1536, 256), (127, 128, 160)])
 def test_wide_projection_dims_against_oracle(tokens, hidden, dim, head_cluster):
