@@ -118,3 +118,17 @@ def test_wide_projection_dims_against_oracle(tokens, hidden, dim, head_cluster):
         assert torch.allclose(got3.double(), exact, rtol=0, atol=2 ** -9 + 1e-6)
     finally:
         _lib.set_option("head_cluster", 0)
+
+
+def test_wide_dim320_reference_model_forward_golden():
+    """DRAFT (r2): head of a random-init reference ColQwen3 (dim 320), captured by oracle/make_golden.py wide."""
+    g = load_golden("wide_dim320.npz")
+    mask = torch.from_numpy(g["h_mask"])
+    h = from_bits(g["h_h"]).reshape(3, 24, -1)
+    w = from_bits(g["h_w"]).reshape(320, -1)
+    b = from_bits(g["h_b"])
+    want = from_bits(g["h_out"]).reshape(3, 24, 320)
+    got = cb.fused_head(h.to(DEV), w.to(DEV), b.to(DEV), mask.to(DEV)).cpu()
+    assert got.shape == want.shape and (got[mask == 0] == 0).all()
+    assert bit_identical_fraction(got, want) > 0.995
+    assert torch.allclose(got.float(), want.float(), rtol=0, atol=2 ** -8)

@@ -215,3 +215,15 @@ def test_wide_embeddings_loss_and_gradients(dim):
     assert abs(float(loss) - float(ref)) < LOSS_TOL
     for got, want in ((qq.grad, qo.grad), (dd.grad, do.grad), (nn.grad, no.grad)):
         assert torch.allclose(got.float().cpu(), want, rtol=2e-2, atol=want.abs().max().item() * 1e-2)
+
+
+@pytest.mark.parametrize("name,make", (("colbert", lambda: cb.ColbertLoss()), ("pairwise", lambda: cb.ColbertPairwiseCELoss())))
+def test_wide_dim320_losses_against_reference_golden(name, make):
+    """DRAFT (r2): loss and gradients at dim 320 against the reference's own numbers (bf16-representable inputs)."""
+    g = load_golden("wide_dim320.npz")
+    q, d = torch.from_numpy(g["l_q"]), torch.from_numpy(g["l_d"])
+    loss, dq, dd = _run(make(), q, d, offset=1)
+    assert abs(float(loss) - float(g[f"l_{name}_loss"])) < 2e-5
+    real_q, real_d = q.abs().sum(-1) > 0, d.abs().sum(-1) > 0
+    assert torch.allclose(dq[real_q], torch.from_numpy(g[f"l_{name}_dq"])[real_q], rtol=1e-4, atol=2e-6)
+    assert torch.allclose(dd[real_d], torch.from_numpy(g[f"l_{name}_dd"])[real_d], rtol=1e-4, atol=2e-6)

@@ -305,3 +305,18 @@ def test_wide_embeddings_k_pipelined_kernel(dim):
     got_d = cb.score_multi_vector(q, dense, device=dev)
     want_d = torch.einsum("bnd,csd->bcns", q.to(dev).float(), dense.to(dev).float()).amax(3).sum(2).cpu()
     assert torch.allclose(got_d, want_d, rtol=1e-5, atol=2e-4)
+
+
+def test_wide_dim320_against_reference_golden():
+    """DRAFT (r2): K-pipelined scorer at ColQwen3's dim against the reference's own outputs (ragged, N_q up to 32)."""
+    g = load_golden("wide_dim320.npz")
+    qs = split_rows(from_bits(g["s_q"], (-1, 320)), g["s_qlen"])
+    ps = split_rows(from_bits(g["s_p"], (-1, 320)), g["s_plen"])
+    got = cb.score_multi_vector(qs, ps, device=DEV)
+    want = torch.from_numpy(g["s_fp32"])
+    assert rel_err(got, want) < 1e-4
+    assert torch.equal(got.argmax(1), want.argmax(1))
+    got_bf = cb.score_multi_vector(qs, ps, device=DEV, round_bf16=True)
+    want_bf = torch.from_numpy(g["s_bf16"])
+    ulp = want_bf.abs().clamp_min(1e-3) * 2.0 ** -7
+    assert ((got_bf - want_bf).abs() <= ulp).all()
