@@ -23,12 +23,16 @@ EXPORTED_SYMBOLS = (
     "cpb_maxsim_fwd",
     "cpb_maxsim_workspace_bytes",
     "cpb_maxsim_fwd_balanced",
+    "cpb_maxsim_fwd_dim",
     "cpb_maxsim_split_workspace_bytes",
     "cpb_maxsim_fwd_allgather",
     "cpb_wait_flags",
     "cpb_colbert_loss_fwd",
     "cpb_colbert_neg_loss_fwd",
     "cpb_maxsim_bwd",
+    "cpb_maxsim_bwd_dim",
+    "cpb_colbert_loss_fwd_dim",
+    "cpb_colbert_neg_loss_fwd_dim",
     "cpb_head_fwd",
 )
 
@@ -78,6 +82,8 @@ def load() -> ctypes.CDLL:
         c_vp, c_vp, c_vp,  # d_scores, d_argmax, d_workspace
         c_u32, c_vp,  # flags, stream
     ]
+    lib.cpb_maxsim_fwd_dim.restype = c_i
+    lib.cpb_maxsim_fwd_dim.argtypes = lib.cpb_maxsim_fwd.argtypes[:-1] + [c_i, c_vp]
     lib.cpb_maxsim_split_workspace_bytes.restype = c_i64
     lib.cpb_maxsim_split_workspace_bytes.argtypes = [c_i, c_i]
     lib.cpb_maxsim_fwd_balanced.restype = c_i
@@ -104,6 +110,10 @@ def load() -> ctypes.CDLL:
         c_f, c_i, c_i, c_f, c_f, c_f, c_i,  # temperature, normalize, filter, threshold, factor, in_batch_weight, offset
         c_vp, c_vp, c_vp, c_vp,  # d_loss, d_grad_scores, d_grad_neg_scores, stream
     ]
+    for name in ("cpb_colbert_loss_fwd", "cpb_colbert_neg_loss_fwd"):  # DRAFT: ..., dim, stream
+        fn = getattr(lib, name + "_dim")
+        fn.restype = c_i
+        fn.argtypes = getattr(lib, name).argtypes[:-1] + [c_i, c_vp]
     lib.cpb_maxsim_bwd.restype = c_i
     lib.cpb_maxsim_bwd.argtypes = [
         c_vp, c_vp, c_vp,  # d_grad_scores, d_grad_out, d_argmax
@@ -111,6 +121,8 @@ def load() -> ctypes.CDLL:
         c_vp, c_i64, c_vp, c_i,  # d_docs, doc_rows, d_doc_start, n_docs
         c_vp, c_vp, c_vp,  # d_dq, d_dd, stream
     ]
+    lib.cpb_maxsim_bwd_dim.restype = c_i
+    lib.cpb_maxsim_bwd_dim.argtypes = lib.cpb_maxsim_bwd.argtypes[:-1] + [c_i, c_vp]  # ..., dim, stream
     lib.cpb_head_fwd.restype = c_i
     lib.cpb_head_fwd.argtypes = [
         c_vp, c_i64, c_i,  # d_hidden, n_tokens, hidden

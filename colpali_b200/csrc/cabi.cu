@@ -18,6 +18,9 @@ cudaError_t maxsim_launch(const CUtensorMap& tq, const CUtensorMap& td, const CU
                           int r, bool argmax, int grid, cudaStream_t stream);
 int maxsim_max_clusters(int r, int cluster);
 int maxsim_tile_n();
+cudaError_t maxsim_kpipe_launch(const CUtensorMap& tq, const CUtensorMap& td, const CUtensorMap& tt, const MaxSimParams& p,
+                                int dim_panels, bool argmax, int grid, cudaStream_t stream);
+int maxsim_kpipe_max_clusters(int dim_panels, int cluster);
 cudaError_t wait_flags_launch(const uint32_t* flags, int n, uint32_t value, cudaStream_t stream);
 cudaError_t maxsim_reduce_segments(const float* partial, float* out, int64_t plane, int nseg, int round_ref,
                                    cudaStream_t stream);
@@ -29,6 +32,7 @@ thread_local char g_err[512] = "";
 
 // tuning knobs (cpb_set_option); 0 = choose automatically
 int g_opt_cluster = 0;
+static int g_head_cluster = 0;  // DRAFT: 0 = auto (2 when there are at least two token tiles), 1, 2
 int g_opt_qtiles_per_cta = 0;
 unsigned g_opt_debug_flags = 0;
 int g_opt_mma_split = 6;
@@ -140,6 +144,9 @@ int cpb_set_option(const char* name, int value) {
   } else if (!strcmp(name, "mma_split")) {
     if (value < 5 || value > 8) return fail(CPB_E_INVALID, "mma_split must be 5..8");
     g_opt_mma_split = value;
+  } else if (!strcmp(name, "head_cluster")) {
+    if (value < 0 || value > 2) return fail(CPB_E_INVALID, "head_cluster must be 0, 1 or 2");
+    g_head_cluster = value;
   } else if (!strcmp(name, "balanced")) {
     g_opt_balanced = value != 0;
   } else if (!strcmp(name, "debug_delay")) {
@@ -278,7 +285,9 @@ static int loss_fwd_impl(const float* d_scores, const void* d_q, int n_queries, 
                          float temperature, int normalize_scores, int pos_aware_negative_filtering,
                          float filter_threshold, float filter_factor, int offset, const float* d_neg_scores, int n_neg,
                          float in_batch_weight, float* d_loss, float* d_grad_scores, float* d_grad_neg,
-                         float* d_bounds, void* stream_) {
+                         float* d_bounds, int q_dim, void* stream_) {
+  if (q_dim != 128 && q_dim != 192 && q_dim != 256 && q_dim != 320)
+    return fail(CPB_E_UNSUPPORTED, "embedding dim %d is not supported by this build (128, 192, 256, 320)", q_dim);
   if (n_queries <= 0 || n_docs <= 0) return fail(CPB_E_INVALID, "n_queries=%d and n_docs=%d must be positive", n_queries, n_docs);
   if (nq_pad <= 0 || (nq_pad % 32) != 0) return fail(CPB_E_INVALID, "nq_pad=%d must be a positive multiple of 32", nq_pad);
   if (mode != CPB_LOSS_CE && mode != CPB_LOSS_PAIRWISE && mode != CPB_LOSS_SIGMOID) return fail(CPB_E_INVALID, "unknown loss mode %d", mode);
@@ -293,6 +302,7 @@ static int loss_fwd_impl(const float* d_scores, const void* d_q, int n_queries, 
   cpb::LossParams p{};
   p.scores = d_scores;
   p.q = static_cast<const __nv_bfloat16*>(d_q);
+  p.q_dim = q_dim;
   p.loss = d_loss;
   p.grad = d_grad_scores;
   p.bounds = d_bounds;
@@ -320,7 +330,16 @@ int cpb_colbert_loss_fwd(const float* d_scores, const void* d_q, int n_queries, 
                          float* d_bounds, void* stream_) {
   return loss_fwd_impl(d_scores, d_q, n_queries, nq_pad, n_docs, mode, temperature, normalize_scores,
                        pos_aware_negative_filtering, filter_threshold, filter_factor, offset, nullptr, 0, 1.f, d_loss,
-                       d_grad_scores, nullptr, d_bounds, stream_);
+                       d_grad_scores, nullptr, d_bounds, 128, stream_);
+}
+
+int cpb_colbert_loss_fwd_dim(const float* d_scores, const void* d_q, int n_queries, int nq_pad, int n_docs, int mode,
+                             float temperature, int normalize_scores, int pos_aware_negative_filtering,
+                             float filter_threshold, float filter_factor, int offset, float* d_loss,
+                             float* d_grad_scores, float* d_bounds, int dim, void* stream_) {
+  return loss_fwd_impl(d_scores, d_q, n_queries, nq_pad, n_docs, mode, temperature, normalize_scores,
+                       pos_aware_negative_filtering, filter_threshold, filter_factor, offset, nullptr, 0, 1.f, d_loss,
+                       d_grad_scores, nullptr, d_bounds, dim, stream_);
 }
 
 int cpb_maxsim_fwd(const void* d_q, int n_queries, int nq_pad, const void* d_docs, int64_t doc_rows,
@@ -372,12 +391,32 @@ int cpb_colbert_neg_loss_fwd(const float* d_scores, const float* d_neg_scores, c
   if (!d_neg_scores) return fail(CPB_E_INVALID, "null device pointer");
   return loss_fwd_impl(d_scores, d_q, n_queries, nq_pad, n_docs, inner_mode, temperature, normalize_scores,
                        pos_aware_negative_filtering, filter_threshold, filter_factor, offset, d_neg_scores, n_neg,
-                       in_batch_term_weight, d_loss, d_grad_scores, d_grad_neg_scores, nullptr, stream_);
+                       in_batch_term_weight, d_loss, d_grad_scores, d_grad_neg_scores, nullptr, 128, stream_);
+}
+
+int cpb_colbert_neg_loss_fwd_dim(const float* d_scores, const float* d_neg_scores, const void* d_q, int n_queries,
+                                 int nq_pad, int n_docs, int n_neg, int inner_mode, float temperature,
+                                 int normalize_scores, int pos_aware_negative_filtering, float filter_threshold,
+                                 float filter_factor, float in_batch_term_weight, int offset, float* d_loss,
+                                 float* d_grad_scores, float* d_grad_neg_scores, int dim, void* stream_) {
+  if (!d_neg_scores) return fail(CPB_E_INVALID, "null device pointer");
+  return loss_fwd_impl(d_scores, d_q, n_queries, nq_pad, n_docs, inner_mode, temperature, normalize_scores,
+                       pos_aware_negative_filtering, filter_threshold, filter_factor, offset, d_neg_scores, n_neg,
+                       in_batch_term_weight, d_loss, d_grad_scores, d_grad_neg_scores, nullptr, dim, stream_);
 }
 
 int cpb_maxsim_bwd(const float* d_grad_scores, const float* d_grad_out, const int32_t* d_argmax, const void* d_q,
                    int n_queries, int nq_pad, const void* d_docs, int64_t doc_rows, const int32_t* d_doc_start,
                    int n_docs, float* d_dq, float* d_dd, void* stream_) {
+  return cpb_maxsim_bwd_dim(d_grad_scores, d_grad_out, d_argmax, d_q, n_queries, nq_pad, d_docs, doc_rows, d_doc_start,
+                            n_docs, d_dq, d_dd, 128, stream_);
+}
+
+int cpb_maxsim_bwd_dim(const float* d_grad_scores, const float* d_grad_out, const int32_t* d_argmax, const void* d_q,
+                       int n_queries, int nq_pad, const void* d_docs, int64_t doc_rows, const int32_t* d_doc_start,
+                       int n_docs, float* d_dq, float* d_dd, int dim, void* stream_) {
+  if (dim != 128 && dim != 192 && dim != 256 && dim != 320)
+    return fail(CPB_E_UNSUPPORTED, "embedding dim %d is not supported by this build (128, 192, 256, 320)", dim);
   if (n_queries <= 0 || n_docs <= 0) return fail(CPB_E_INVALID, "n_queries=%d and n_docs=%d must be positive", n_queries, n_docs);
   if (nq_pad <= 0 || (nq_pad % 32) != 0) return fail(CPB_E_INVALID, "nq_pad=%d must be a positive multiple of 32", nq_pad);
   if (!d_grad_scores || !d_argmax || !d_q || !d_docs || !d_doc_start) return fail(CPB_E_INVALID, "null device pointer");
@@ -398,6 +437,7 @@ int cpb_maxsim_bwd(const float* d_grad_scores, const float* d_grad_out, const in
   p.C = n_docs;
   p.nq_pad = nq_pad;
   p.q_rows = n_queries * nq_pad;
+  p.dim = dim;
   CPB_CUDA(cpb::maxsim_bwd_launch(p, static_cast<cudaStream_t>(stream_)));
   return CPB_OK;
 }
@@ -407,7 +447,9 @@ int cpb_head_fwd(const void* d_hidden, int64_t n_tokens, int hidden, const void*
                  void* stream_) {
   if (n_tokens <= 0) return fail(CPB_E_INVALID, "n_tokens=%lld must be positive", static_cast<long long>(n_tokens));
   if (n_tokens > 0x7fffff00LL) return fail(CPB_E_INVALID, "n_tokens too large");
-  if (dim != 128) return fail(CPB_E_UNSUPPORTED, "projection dim %d is not supported by this build (128 only)", dim);
+  const bool wide = dim > 128;  // DRAFT: head_wide_sm100.cu
+  if (dim != 128 && !(wide && dim <= 320 && (dim % 32) == 0))
+    return fail(CPB_E_UNSUPPORTED, "projection dim %d is not supported by this build (128, or a multiple of 32 up to 320)", dim);
   if (hidden <= 0 || (hidden % 64) != 0) return fail(CPB_E_UNSUPPORTED, "hidden size %d must be a positive multiple of 64", hidden);
   if (!d_hidden || !d_weight || !d_out) return fail(CPB_E_INVALID, "null device pointer");
   if (reinterpret_cast<uintptr_t>(d_out) & 15u) return fail(CPB_E_INVALID, "d_out is not 16-byte aligned");
@@ -418,7 +460,7 @@ int cpb_head_fwd(const void* d_hidden, int64_t n_tokens, int hidden, const void*
   CUtensorMap th, tw;
   rc = make_bf16_rowmajor_map(&th, d_hidden, n_tokens, hidden, 128);
   if (rc != CPB_OK) return rc;
-  rc = make_bf16_rowmajor_map(&tw, d_weight, dim, hidden, 128);
+  rc = make_bf16_rowmajor_map(&tw, d_weight, dim, hidden, wide ? dim / 2 : 128);
   if (rc != CPB_OK) return rc;
   cpb::HeadParams p{};
   p.bias = static_cast<const __nv_bfloat16*>(d_bias);
@@ -428,9 +470,77 @@ int cpb_head_fwd(const void* d_hidden, int64_t n_tokens, int hidden, const void*
   p.n_tokens = n_tokens;
   p.hidden = hidden;
   p.flags = flags;
+  p.dim = dim;
+  if (wide) {
+    p.stages = cpb::head_wide_stages(dim);
+    if (p.stages < 2) return fail(CPB_E_UNSUPPORTED, "projection dim %d does not fit the shared-memory ring", dim);
+    const int64_t tiles = (n_tokens + 127) / 128;
+    p.cluster = (g_head_cluster == 1 || tiles < 2) ? 1 : 2;
+    const int64_t rounds = (tiles + p.cluster - 1) / p.cluster;
+    const int64_t max_clusters = di.sm_count / p.cluster;
+    const int grid = static_cast<int>((rounds < max_clusters ? rounds : max_clusters) * p.cluster);
+    CPB_CUDA(cpb::head_wide_launch(th, tw, p, grid, static_cast<cudaStream_t>(stream_)));
+    return CPB_OK;
+  }
   const int64_t pairs = (n_tokens + 255) / 256;
   const int grid = static_cast<int>(pairs < di.sm_count ? pairs : di.sm_count);
   CPB_CUDA(cpb::head_launch(th, tw, p, grid, static_cast<cudaStream_t>(stream_)));
+  return CPB_OK;
+}
+
+// DRAFT (r2-drafts): MaxSim forward for embedding dims 192 / 256 / 320 (K-pipelined kernel, one query tile per CTA).
+// dim must be a multiple of 64 in (128, 320]; queries and documents are [rows, dim] bf16.  No balancing, no fused gather yet.
+int cpb_maxsim_fwd_dim(const void* d_q, int n_queries, int nq_pad, const void* d_docs, int64_t doc_rows,
+                       const int32_t* d_doc_start, const int32_t* d_doc_len, const float* d_doc_floor, int n_docs,
+                       float* d_scores, int32_t* d_argmax, float* d_workspace, uint32_t flags, int dim, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (dim <= 128 || dim > 320 || (dim % 64) != 0) return fail(CPB_E_UNSUPPORTED, "dim=%d: this entry point serves 192, 256 and 320", dim);
+  if (n_queries <= 0 || n_docs <= 0) return fail(CPB_E_INVALID, "n_queries=%d and n_docs=%d must be positive", n_queries, n_docs);
+  if (nq_pad <= 0 || (nq_pad % 32) != 0) return fail(CPB_E_INVALID, "nq_pad=%d must be a positive multiple of 32", nq_pad);
+  if (!d_q || !d_docs || !d_doc_start || !d_doc_len || !d_scores) return fail(CPB_E_INVALID, "null device pointer");
+  if (doc_rows <= 0 || doc_rows > 0x7fffffffLL) return fail(CPB_E_INVALID, "doc_rows out of range");
+  const int nseg = nq_pad / 32;
+  if (nseg > 1 && !d_workspace) return fail(CPB_E_INVALID, "nq_pad=%d needs a workspace", nq_pad);
+  DevInfo di;
+  int rc = current_device_info(&di);
+  if (rc != CPB_OK) return rc;
+  if (di.major != 10) return fail(CPB_E_DEVICE, "device is sm_%d%d; this library needs sm_100 (B200)", di.major, di.minor);
+  const int panels = dim / 64;
+  cpb::MaxSimParams p{};
+  p.q = d_q;
+  p.doc_start = d_doc_start;
+  p.doc_len = d_doc_len;
+  p.doc_floor = d_doc_floor;
+  p.argmax = d_argmax;
+  p.plane_stride = static_cast<int64_t>(n_queries) * n_docs;
+  p.n_queries = n_queries;
+  p.nq_pad = nq_pad;
+  p.q_rows = n_queries * nq_pad;
+  p.n_docs = n_docs;
+  p.num_qtiles = (p.q_rows + 127) / 128;
+  p.scores = (nseg == 1) ? d_scores : d_workspace;
+  p.q_groups = p.num_qtiles;  // one query tile per CTA
+  int cluster = (p.q_groups >= 2) ? 2 : 1;
+  int max_clusters = cpb::maxsim_kpipe_max_clusters(panels, cluster);
+  if (max_clusters <= 0) return fail(CPB_E_CUDA, "K-pipelined kernel cannot be resident on this device");
+  p.cluster = cluster;
+  p.group_sets = (p.q_groups + cluster - 1) / cluster;
+  int parts = max_clusters / p.group_sets;
+  if (parts < 1) parts = 1;
+  if (parts > n_docs) parts = n_docs;
+  p.doc_parts = parts;
+  p.flags = flags | g_opt_debug_flags;
+  const int grid = p.group_sets * p.doc_parts * cluster;
+  CUtensorMap tq, td, tt;
+  rc = make_bf16_rowmajor_map(&tq, d_q, p.q_rows, dim, 128);
+  if (rc != CPB_OK) return rc;
+  rc = make_bf16_rowmajor_map(&td, d_docs, doc_rows, dim, 256 / cluster);
+  if (rc != CPB_OK) return rc;
+  rc = make_bf16_rowmajor_map(&tt, d_docs, doc_rows, dim, 32);
+  if (rc != CPB_OK) return rc;
+  CPB_CUDA(cpb::maxsim_kpipe_launch(tq, td, tt, p, panels, d_argmax != nullptr, grid, stream));
+  if (nseg > 1)
+    CPB_CUDA(cpb::maxsim_reduce_segments(d_workspace, d_scores, p.plane_stride, nseg, (flags & CPB_FLAG_ROUND_BF16) ? 1 : 0, stream));
   return CPB_OK;
 }
 

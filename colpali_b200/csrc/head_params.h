@@ -8,15 +8,19 @@
 namespace cpb {
 
 struct HeadParams {
-  const __nv_bfloat16* bias;       // [128] or nullptr
+  const __nv_bfloat16* bias;       // [dim] or nullptr
   const int64_t* attention_mask;   // [n_tokens] or nullptr
   const uint8_t* extra_mask;       // [n_tokens] or nullptr (image-token mask)
-  __nv_bfloat16* out;              // [n_tokens, 128]
+  __nv_bfloat16* out;              // [n_tokens, dim]
   int64_t n_tokens;
   int hidden;
   uint32_t flags;
+  // head_wide_sm100.cu only (DRAFT): output dim in (128, 320], ring depth, CTAs per cluster (1 or 2)
+  int dim, stages, cluster;
 };
 
 cudaError_t head_launch(const CUtensorMap& th, const CUtensorMap& tw, const HeadParams& p, int grid, cudaStream_t stream);
+int head_wide_stages(int dim);  // 0: does not fit
+cudaError_t head_wide_launch(const CUtensorMap& th, const CUtensorMap& tw, const HeadParams& p, int grid, cudaStream_t stream);
 
 }  // namespace cpb

@@ -8,7 +8,8 @@ namespace cpb {
 
 struct LossParams {
   const float* scores;        // [B, C] raw sums of per-token maxima
-  const __nv_bfloat16* q;     // [B * nq_pad, 128] padded queries (lengths are counted from column 0)
+  const __nv_bfloat16* q;     // [B * nq_pad, q_dim] padded queries (lengths are counted from column 0)
+  int q_dim;                  // row stride of q in elements (128, or 192 / 256 / 320)
   float* loss;                // [1]
   float* grad;                // [B, C] dLoss/dScores (raw), or nullptr
   float* bounds;              // [2] min / max of the normalised scores, or nullptr
@@ -34,6 +35,7 @@ struct BwdParams {
   float* dq;                  // [q_rows, 128]
   float* dd;                  // [doc_rows, 128], pre-zeroed
   int B, C, nq_pad, q_rows;
+  int dim;                    // padded embedding dim: 128 (the validated kernels) or 192 / 256 / 320 (drafts)
 };
 
 cudaError_t colbert_loss_launch(const LossParams& p, cudaStream_t stream);

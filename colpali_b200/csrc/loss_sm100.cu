@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(1024, 1) colbert_loss_kernel(const LossParams 
     // lengths = (q[:, :, 0] != 0).sum(1)                       late_interaction_losses.py:152
     float cnt = 0.f;
     for (int n = lane; n < p.nq_pad; n += 32)
-      cnt += (__bfloat162float(p.q[(static_cast<int64_t>(b) * p.nq_pad + n) * 128]) != 0.f) ? 1.f : 0.f;
+      cnt += (__bfloat162float(p.q[(static_cast<int64_t>(b) * p.nq_pad + n) * p.q_dim]) != 0.f) ? 1.f : 0.f;
     cnt = warp_sum_f(cnt);
     const float inv = p.normalize ? 1.f / cnt : 1.f;          // :155-156 -> :59-62
     const float* row = p.scores + static_cast<int64_t>(b) * p.C;
@@ -266,7 +266,85 @@ __global__ void __launch_bounds__(256) maxsim_bwd_dd_kernel(const BwdParams p) {
   atomicAdd(dst, v);  // red.global.add.v4.f32 (sm_90+)
 }
 
+// ---- wide embeddings (dim = 64 * P, P in 3..5): lane owns the bf16 pairs {lane, lane + 32, ...} of a row --------
+template <int P>
+__global__ void __launch_bounds__(256) maxsim_bwd_dq_wide_kernel(const BwdParams p) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= p.q_rows) return;
+  constexpr int kDim = 64 * P;
+  const int b = row / p.nq_pad;
+  const float scale = p.grad_out ? *p.grad_out : 1.f;
+  float2 acc[P];
+#pragma unroll
+  for (int j = 0; j < P; ++j) acc[j] = make_float2(0.f, 0.f);
+  const float* g = p.g + static_cast<int64_t>(b) * p.C;
+#pragma unroll 2
+  for (int c = 0; c < p.C; ++c) {
+    const int idx = __ldg(p.argmax + static_cast<int64_t>(c) * p.q_rows + row);
+    if (idx < 0) continue;
+    const float w = __ldg(g + c) * scale;
+    if (w == 0.f) continue;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(p.docs + (static_cast<int64_t>(__ldg(p.doc_start + c)) + idx) * kDim);
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      const uint32_t raw = __ldg(src + j * 32 + lane);
+      const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(&raw);
+      acc[j].x = fmaf(w, __low2float(v), acc[j].x);
+      acc[j].y = fmaf(w, __high2float(v), acc[j].y);
+    }
+  }
+  float2* dst = reinterpret_cast<float2*>(p.dq + static_cast<int64_t>(row) * kDim);
+#pragma unroll
+  for (int j = 0; j < P; ++j) dst[j * 32 + lane] = acc[j];
+}
+
+template <int P>
+__global__ void __launch_bounds__(256) maxsim_bwd_dd_wide_kernel(const BwdParams p) {
+  const int64_t w = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (w >= static_cast<int64_t>(p.C) * p.q_rows) return;
+  constexpr int kDim = 64 * P;
+  const int c = static_cast<int>(w / p.q_rows);
+  const int row = static_cast<int>(w % p.q_rows);
+  const int idx = __ldg(p.argmax + w);
+  if (idx < 0) return;
+  const int b = row / p.nq_pad;
+  const float scale = p.grad_out ? *p.grad_out : 1.f;
+  const float wgt = __ldg(p.g + static_cast<int64_t>(b) * p.C + c) * scale;
+  if (wgt == 0.f) return;
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(p.q + static_cast<int64_t>(row) * kDim);
+  float2* dst = reinterpret_cast<float2*>(p.dd + (static_cast<int64_t>(__ldg(p.doc_start + c)) + idx) * kDim);
+#pragma unroll
+  for (int j = 0; j < P; ++j) {
+    const uint32_t raw = __ldg(src + j * 32 + lane);
+    const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(&raw);
+    atomicAdd(dst + j * 32 + lane, make_float2(wgt * __low2float(v), wgt * __high2float(v)));  // red.global.add.v2.f32
+  }
+}
+
+template <int P>
+static cudaError_t maxsim_bwd_wide_launch(const BwdParams& p, cudaStream_t stream) {
+  const int wpb = 8;
+  if (p.dq != nullptr) {
+    maxsim_bwd_dq_wide_kernel<P><<<(p.q_rows + wpb - 1) / wpb, wpb * 32, 0, stream>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  if (p.dd != nullptr) {
+    const int64_t warps = static_cast<int64_t>(p.C) * p.q_rows;
+    maxsim_bwd_dd_wide_kernel<P><<<static_cast<unsigned>((warps + wpb - 1) / wpb), wpb * 32, 0, stream>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
 cudaError_t maxsim_bwd_launch(const BwdParams& p, cudaStream_t stream) {
+  if (p.dim == 192) return maxsim_bwd_wide_launch<3>(p, stream);
+  if (p.dim == 256) return maxsim_bwd_wide_launch<4>(p, stream);
+  if (p.dim == 320) return maxsim_bwd_wide_launch<5>(p, stream);
+  if (p.dim != 128) return cudaErrorInvalidValue;
   const int wpb = 8;  // warps per block
   if (p.dq != nullptr) {
     const int blocks = (p.q_rows + wpb - 1) / wpb;

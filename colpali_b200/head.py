@@ -24,7 +24,12 @@ import torch
 
 from . import _lib
 
-HEAD_DIM = 128
+HEAD_DIM = 128      # the validated kernel (head_sm100.cu)
+MAX_HEAD_DIM = 320  # DRAFT: multiples of 32 above 128 go through head_wide_sm100.cu (ColQwen3: 320)
+
+
+def _supported_dim(dim: int) -> bool:
+    return dim == HEAD_DIM or (HEAD_DIM < dim <= MAX_HEAD_DIM and dim % 32 == 0)
 
 
 def _reference_tail(h, weight, bias, attention_mask, extra_mask, clamp_norm):
@@ -46,8 +51,10 @@ class _FusedHeadFn(torch.autograd.Function):
         dev = h.device
         if dev.type != "cuda":
             raise _lib.ColpaliB200Error("fused_head needs CUDA tensors (sm_100a); there is no CPU path")
-        if weight.shape[0] != HEAD_DIM:
-            raise _lib.ColpaliB200Error(f"projection dim {weight.shape[0]} is not supported by this build ({HEAD_DIM} only)")
+        dim = int(weight.shape[0])
+        if not _supported_dim(dim):
+            raise _lib.ColpaliB200Error(f"projection dim {dim} is not supported by this build "
+                                        f"({HEAD_DIM}, or a multiple of 32 up to {MAX_HEAD_DIM})")
         lib = _lib.load()
         lead, hidden = h.shape[:-1], h.shape[-1]
         h2 = h.detach().reshape(-1, hidden)
@@ -63,11 +70,11 @@ class _FusedHeadFn(torch.autograd.Function):
             raise ValueError(f"attention_mask has {am.numel()} entries for {n} tokens")
         if em is not None and em.numel() != n:
             raise ValueError(f"extra mask has {em.numel()} entries for {n} tokens")
-        out = torch.empty(n, HEAD_DIM, dtype=torch.bfloat16, device=dev)
+        out = torch.empty(n, dim, dtype=torch.bfloat16, device=dev)
         flags = (_lib.CPB_HEAD_CLAMP_NORM if clamp_norm else 0) | (_lib.CPB_HEAD_SINGLE_ROUNDING if single_rounding else 0)
         with torch.cuda.device(dev):
             rc = lib.cpb_head_fwd(
-                h2.data_ptr(), n, hidden, w.data_ptr(), b.data_ptr() if b is not None else None, HEAD_DIM,
+                h2.data_ptr(), n, hidden, w.data_ptr(), b.data_ptr() if b is not None else None, dim,
                 am.data_ptr() if am is not None else None, em.data_ptr() if em is not None else None,
                 out.data_ptr(), flags, torch.cuda.current_stream(dev).cuda_stream,
             )
@@ -77,7 +84,7 @@ class _FusedHeadFn(torch.autograd.Function):
                               if attention_mask is not None else torch.empty(0, device=dev),
                               extra_mask if extra_mask is not None else torch.empty(0, device=dev))
         ctx.flags = (bias is not None, attention_mask is not None, extra_mask is not None, clamp_norm)
-        return out.view(*lead, HEAD_DIM).to(h.dtype) if h.dtype != torch.bfloat16 else out.view(*lead, HEAD_DIM)
+        return out.view(*lead, dim).to(h.dtype) if h.dtype != torch.bfloat16 else out.view(*lead, dim)
 
     @staticmethod
     def backward(ctx, grad_out):
@@ -100,7 +107,7 @@ class _FusedHeadFn(torch.autograd.Function):
 def fused_head(hidden_states: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor],
                attention_mask: Optional[torch.Tensor] = None, image_mask: Optional[torch.Tensor] = None, *,
                clamp_norm: bool = False, single_rounding: bool = False) -> torch.Tensor:
-    """``[..., hidden] -> [..., 128]`` unit-norm rows, zero rows where masked.
+    """``[..., hidden] -> [..., dim]`` unit-norm rows, zero rows where masked (dim = ``weight.shape[0]``).
 
     ``weight`` / ``bias`` are ``custom_text_proj``'s parameters; ``attention_mask`` and ``image_mask`` have the
     shape of ``hidden_states`` without the last dim.  By default the reference's three bf16 roundings are

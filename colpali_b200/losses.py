@@ -30,7 +30,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib
-from .scoring import EMBED_DIM, DocBank, QueryBlock, maxsim
+from .scoring import DocBank, QueryBlock, maxsim
 
 
 class _InBatchLossFn(torch.autograd.Function):
@@ -54,14 +54,14 @@ class _InBatchLossFn(torch.autograd.Function):
         loss = torch.empty(1, dtype=torch.float32, device=dev)
         g = torch.empty(b, c, dtype=torch.float32, device=dev) if need_grad else None
         with torch.cuda.device(dev):
-            rc = lib.cpb_colbert_loss_fwd(
+            rc = lib.cpb_colbert_loss_fwd_dim(
                 scores.data_ptr(), qb.flat.data_ptr(), b, qb.nq_pad, c, mode,
                 float(temperature), int(normalize), int(filt), float(thr), float(factor), int(offset),
                 loss.data_ptr(), g.data_ptr() if g is not None else None,
                 bounds_out.data_ptr() if bounds_out is not None else None,
-                torch.cuda.current_stream(dev).cuda_stream,
+                qb.flat.shape[1], torch.cuda.current_stream(dev).cuda_stream,
             )
-        _lib.check(rc, "cpb_colbert_loss_fwd")
+        _lib.check(rc, "cpb_colbert_loss_fwd_dim")
         _lib.count_launches(1)
         if need_grad:
             ctx.save_for_backward(qb.flat, bank.flat, bank.start, argmax, g)
@@ -75,24 +75,25 @@ class _InBatchLossFn(torch.autograd.Function):
         dev = q_flat.device
         lib = _lib.load()
         want_q, want_d = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        dq = torch.empty(b * nq_pad, EMBED_DIM, dtype=torch.float32, device=dev) if want_q else None
-        dd = torch.zeros(d_flat.shape[0], EMBED_DIM, dtype=torch.float32, device=dev) if want_d else None
+        dim = q_flat.shape[1]  # padded embedding dim (128, or 192 / 256 / 320 for wide models)
+        dq = torch.empty(b * nq_pad, dim, dtype=torch.float32, device=dev) if want_q else None
+        dd = torch.zeros(d_flat.shape[0], dim, dtype=torch.float32, device=dev) if want_d else None
         go = grad_out.detach().to(torch.float32).reshape(1).contiguous()
         with torch.cuda.device(dev):
-            rc = lib.cpb_maxsim_bwd(
+            rc = lib.cpb_maxsim_bwd_dim(
                 g.data_ptr(), go.data_ptr(), argmax.data_ptr(),
                 q_flat.data_ptr(), b, nq_pad,
                 d_flat.data_ptr(), d_flat.shape[0], d_start.data_ptr(), c,
                 dq.data_ptr() if dq is not None else None, dd.data_ptr() if dd is not None else None,
-                torch.cuda.current_stream(dev).cuda_stream,
+                dim, torch.cuda.current_stream(dev).cuda_stream,
             )
-        _lib.check(rc, "cpb_maxsim_bwd")
+        _lib.check(rc, "cpb_maxsim_bwd_dim")
         _lib.count_launches(int(want_q) + int(want_d))
         grad_q = grad_d = None
         if want_q:
-            grad_q = dq.view(b, nq_pad, EMBED_DIM)[:, : q_shape[1], : q_shape[2]].to(q_dtype)
+            grad_q = dq.view(b, nq_pad, dim)[:, : q_shape[1], : q_shape[2]].to(q_dtype)
         if want_d:
-            grad_d = dd.view(d_shape[0], d_shape[1], EMBED_DIM)[:, :, : d_shape[2]].to(d_dtype)
+            grad_d = dd.view(d_shape[0], d_shape[1], dim)[:, :, : d_shape[2]].to(d_dtype)
         return grad_q, grad_d, None, None, None, None, None, None, None, None
 
 
@@ -126,13 +127,13 @@ class _NegLossFn(torch.autograd.Function):
         g_pos = torch.empty(b, c, dtype=torch.float32, device=dev) if need_grad else None
         g_neg = torch.empty(b, b * n_neg, dtype=torch.float32, device=dev) if need_grad else None
         with torch.cuda.device(dev):
-            rc = lib.cpb_colbert_neg_loss_fwd(
+            rc = lib.cpb_colbert_neg_loss_fwd_dim(
                 s_pos.data_ptr(), s_neg.data_ptr(), qb.flat.data_ptr(), b, qb.nq_pad, c, n_neg, inner_mode,
                 float(temperature), int(normalize), int(filt), float(thr), float(factor), float(weight), int(offset),
                 loss.data_ptr(), g_pos.data_ptr() if need_grad else None, g_neg.data_ptr() if need_grad else None,
-                torch.cuda.current_stream(dev).cuda_stream,
+                qb.flat.shape[1], torch.cuda.current_stream(dev).cuda_stream,
             )
-        _lib.check(rc, "cpb_colbert_neg_loss_fwd")
+        _lib.check(rc, "cpb_colbert_neg_loss_fwd_dim")
         _lib.count_launches(1)
         if need_grad:
             ctx.save_for_backward(qb.flat, bank.flat, bank.start, am_pos, g_pos, nbank.flat, nbank.start, am_neg, g_neg)
@@ -148,16 +149,18 @@ class _NegLossFn(torch.autograd.Function):
         want_q, want_d, want_n = ctx.needs_input_grad[:3]
         go = grad_out.detach().to(torch.float32).reshape(1).contiguous()
         stream = torch.cuda.current_stream(dev).cuda_stream
+        dim = q_flat.shape[1]
 
         def bwd(g, am, flat, start, n_docs, need_dq, need_dd):
-            dq = torch.empty(b * nq_pad, EMBED_DIM, dtype=torch.float32, device=dev) if need_dq else None
-            dd = torch.zeros(flat.shape[0], EMBED_DIM, dtype=torch.float32, device=dev) if need_dd else None
+            dq = torch.empty(b * nq_pad, dim, dtype=torch.float32, device=dev) if need_dq else None
+            dd = torch.zeros(flat.shape[0], dim, dtype=torch.float32, device=dev) if need_dd else None
             if need_dq or need_dd:
                 with torch.cuda.device(dev):
-                    rc = lib.cpb_maxsim_bwd(g.data_ptr(), go.data_ptr(), am.data_ptr(), q_flat.data_ptr(), b, nq_pad,
-                                            flat.data_ptr(), flat.shape[0], start.data_ptr(), n_docs,
-                                            dq.data_ptr() if need_dq else None, dd.data_ptr() if need_dd else None, stream)
-                _lib.check(rc, "cpb_maxsim_bwd")
+                    rc = lib.cpb_maxsim_bwd_dim(g.data_ptr(), go.data_ptr(), am.data_ptr(), q_flat.data_ptr(), b, nq_pad,
+                                                flat.data_ptr(), flat.shape[0], start.data_ptr(), n_docs,
+                                                dq.data_ptr() if need_dq else None, dd.data_ptr() if need_dd else None,
+                                                dim, stream)
+                _lib.check(rc, "cpb_maxsim_bwd_dim")
                 _lib.count_launches(int(need_dq) + int(need_dd))
             return dq, dd
 
@@ -165,11 +168,11 @@ class _NegLossFn(torch.autograd.Function):
         dq2, dn = bwd(g_neg, am_neg, n_flat, n_start, cn, want_q, want_n)
         grad_q = grad_d = grad_n = None
         if want_q:
-            grad_q = (dq1 + dq2).view(b, nq_pad, EMBED_DIM)[:, : q_shape[1], : q_shape[2]].to(q_dtype)
+            grad_q = (dq1 + dq2).view(b, nq_pad, dim)[:, : q_shape[1], : q_shape[2]].to(q_dtype)
         if want_d:
-            grad_d = dd.view(d_shape[0], d_shape[1], EMBED_DIM)[:, :, : d_shape[2]].to(d_dtype)
+            grad_d = dd.view(d_shape[0], d_shape[1], dim)[:, :, : d_shape[2]].to(d_dtype)
         if want_n:
-            grad_n = dn.view(n_shape[0], n_shape[1], n_shape[2], EMBED_DIM)[..., : n_shape[3]].to(n_dtype)
+            grad_n = dn.view(n_shape[0], n_shape[1], n_shape[2], dim)[..., : n_shape[3]].to(n_dtype)
         return (grad_q, grad_d, grad_n) + (None,) * 8
 
 

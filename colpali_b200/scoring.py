@@ -44,15 +44,25 @@ def _resolve_device(device: Optional[Union[str, torch.device]]) -> torch.device:
     return device
 
 
+MAX_EMBED_DIM = 320  # ColQwen3 (DRAFT: dims above 128 go through the K-pipelined kernel, cpb_maxsim_fwd_dim)
+
+
+def _padded_dim(d: int) -> int:
+    if d <= EMBED_DIM:
+        return EMBED_DIM
+    if d > MAX_EMBED_DIM:
+        raise _lib.ColpaliB200Error(f"embedding dim {d} > {MAX_EMBED_DIM} is not supported by this build")
+    return (d + 63) // 64 * 64
+
+
 def _pad_dim(x: torch.Tensor) -> torch.Tensor:
-    """bf16, last dim zero-padded to EMBED_DIM (zero columns add nothing to a dot product)."""
+    """bf16, last dim zero-padded to 128 (or to the next multiple of 64 above 128): zero columns add nothing to a dot product."""
     d = x.shape[-1]
-    if d > EMBED_DIM:
-        raise _lib.ColpaliB200Error(f"embedding dim {d} > {EMBED_DIM} is not supported by this build")
+    target = _padded_dim(d)
     if x.dtype != torch.bfloat16:
         x = x.to(torch.bfloat16)
-    if d < EMBED_DIM:
-        x = torch.nn.functional.pad(x, (0, EMBED_DIM - d))
+    if d < target:
+        x = torch.nn.functional.pad(x, (0, target - d))
     return x
 
 
@@ -76,18 +86,20 @@ class QueryBlock:
         self.n = n
         self.nq_pad = max(32, (nq + 31) // 32 * 32)
         self.device = device
+        raw_dim = qs.shape[2] if isinstance(qs, torch.Tensor) else int(qs[0].shape[-1])
+        self.dim = _padded_dim(raw_dim)
         if (isinstance(qs, torch.Tensor) and qs.device == device and qs.dtype == torch.bfloat16 and qs.is_contiguous()
-                and nq == self.nq_pad and qs.shape[2] == EMBED_DIM and qs.data_ptr() % 16 == 0):
-            self.flat = qs.view(n * nq, EMBED_DIM)  # already in kernel layout: zero copy
+                and nq == self.nq_pad and qs.shape[2] == self.dim and qs.data_ptr() % 16 == 0):
+            self.flat = qs.view(n * nq, self.dim)  # already in kernel layout: zero copy
             return
-        flat = torch.zeros(n, self.nq_pad, EMBED_DIM, dtype=torch.bfloat16, device=device)
+        flat = torch.zeros(n, self.nq_pad, self.dim, dtype=torch.bfloat16, device=device)
         if isinstance(qs, torch.Tensor):
             flat[:, :nq] = _pad_dim(qs.to(device, non_blocking=True))
         else:
             for i, q in enumerate(qs):
                 if lens[i]:
                     flat[i, : lens[i]] = _pad_dim(q.to(device, non_blocking=True))
-        self.flat = flat.view(n * self.nq_pad, EMBED_DIM)
+        self.flat = flat.view(n * self.nq_pad, self.dim)
 
 
 _DENSE_LAYOUT_CACHE: dict = {}
@@ -133,7 +145,8 @@ class DocBank:
             if ps.dim() != 3:
                 raise ValueError(f"passage tensor must be [n, len, dim], got {tuple(ps.shape)}")
             n, L, _ = ps.shape
-            flat = _pad_dim(ps.to(device, non_blocking=True)).reshape(n * L, EMBED_DIM).contiguous()
+            flat = _pad_dim(ps.to(device, non_blocking=True))
+            flat = flat.reshape(n * L, flat.shape[-1]).contiguous()
             start, length = _dense_layout(n, L, device)
             return DocBank(flat, start, length, None, contiguous=True, uniform_len=L, max_len=L)  # equal lengths: no padding
         lens = [int(p.shape[0]) for p in ps]
@@ -141,7 +154,7 @@ class DocBank:
         # one pass over the bank: device-side cat of the per-document uploads
         flat = _pad_dim(torch.cat([p.to(device, non_blocking=True) for p in ps], dim=0)).contiguous()
         if flat.shape[0] == 0:
-            flat = torch.zeros(1, EMBED_DIM, dtype=torch.bfloat16, device=device)
+            flat = torch.zeros(1, flat.shape[-1], dtype=torch.bfloat16, device=device)
         lens_t = torch.tensor(lens, dtype=torch.int64)
         start = (torch.cumsum(lens_t, 0) - lens_t).to(torch.int32).to(device)
         length = lens_t.to(torch.int32).to(device)
@@ -179,6 +192,9 @@ def maxsim(q: QueryBlock, bank: DocBank, *, round_bf16: bool = False, want_argma
     ``[n_docs, n_queries * nq_pad]`` when asked)."""
     lib = _lib.load()
     dev = bank.device
+    dim = int(bank.flat.shape[1])
+    if q.flat.shape[1] != dim:
+        raise ValueError(f"queries have (padded) dim {q.flat.shape[1]}, documents {dim}")
     scores = torch.empty(q.n, bank.n_docs, dtype=torch.float32, device=dev)
     argmax = torch.empty(bank.n_docs, q.n * q.nq_pad, dtype=torch.int32, device=dev) if want_argmax else None
     ws_bytes = lib.cpb_maxsim_workspace_bytes(q.n, q.nq_pad, bank.n_docs)
@@ -195,7 +211,9 @@ def maxsim(q: QueryBlock, bank: DocBank, *, round_bf16: bool = False, want_argma
             ws.data_ptr() if ws is not None else None,
             flags,
         )
-        if bank.contiguous and bank.max_len > 0 and torch.cuda.current_stream(dev) == torch.cuda.default_stream(dev):
+        if dim > EMBED_DIM:  # DRAFT: K-pipelined kernel, whole-document partitions only
+            rc = lib.cpb_maxsim_fwd_dim(*common, dim, stream)
+        elif bank.contiguous and bank.max_len > 0 and torch.cuda.current_stream(dev) == torch.cuda.default_stream(dev):
             split = _split_workspace(dev, lib.cpb_maxsim_split_workspace_bytes(q.n, q.nq_pad))
             _EPOCH[0] = _EPOCH[0] % 0xFFFFFFF0 + 1
             rc = lib.cpb_maxsim_fwd_balanced(*common, bank.uniform_len, bank.max_len, split.data_ptr(), split.numel(),

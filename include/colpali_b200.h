@@ -133,6 +133,16 @@ int cpb_maxsim_fwd_allgather(const void* d_q, int n_queries, int nq_pad,
 /* Enqueue a wait on `stream` until d_flags[0..n) all equal `value` (consumer side of cpb_maxsim_fwd_allgather). */
 int cpb_wait_flags(const uint32_t* d_flags, int n, uint32_t value, void* stream);
 
+/*
+ * DRAFT: cpb_maxsim_fwd for embedding dims 192 / 256 / 320 (ColQwen3: models/qwen3/colqwen3/modeling_colqwen3.py:48).
+ * d_q and d_docs are [rows, dim] bf16; every other argument as cpb_maxsim_fwd.  Whole-document partitions only.
+ */
+int cpb_maxsim_fwd_dim(const void* d_q, int n_queries, int nq_pad,
+                       const void* d_docs, int64_t doc_rows,
+                       const int32_t* d_doc_start, const int32_t* d_doc_len, const float* d_doc_floor, int n_docs,
+                       float* d_scores, int32_t* d_argmax, float* d_workspace,
+                       uint32_t flags, int dim, void* stream);
+
 /* Bytes of d_workspace cpb_maxsim_fwd needs for this shape (0 when nq_pad == 32). */
 int64_t cpb_maxsim_workspace_bytes(int n_queries, int nq_pad, int n_docs);
 
@@ -194,6 +204,23 @@ int cpb_maxsim_bwd(const float* d_grad_scores, const float* d_grad_out, const in
                    const void* d_q, int n_queries, int nq_pad,
                    const void* d_docs, int64_t doc_rows, const int32_t* d_doc_start, int n_docs,
                    float* d_dq, float* d_dd, void* stream);
+
+/* DRAFT: the two loss entry points for d_q of shape [n_queries * nq_pad, dim], dim in {128, 192, 256, 320}. */
+int cpb_colbert_loss_fwd_dim(const float* d_scores, const void* d_q, int n_queries, int nq_pad, int n_docs, int mode,
+                             float temperature, int normalize_scores, int pos_aware_negative_filtering,
+                             float filter_threshold, float filter_factor, int offset,
+                             float* d_loss, float* d_grad_scores, float* d_bounds, int dim, void* stream);
+int cpb_colbert_neg_loss_fwd_dim(const float* d_scores, const float* d_neg_scores, const void* d_q, int n_queries,
+                                 int nq_pad, int n_docs, int n_neg, int inner_mode, float temperature,
+                                 int normalize_scores, int pos_aware_negative_filtering, float filter_threshold,
+                                 float filter_factor, float in_batch_term_weight, int offset,
+                                 float* d_loss, float* d_grad_scores, float* d_grad_neg_scores, int dim, void* stream);
+
+/* DRAFT: cpb_maxsim_bwd for [rows, dim] operands and gradients, dim in {128, 192, 256, 320} (see cpb_maxsim_fwd_dim). */
+int cpb_maxsim_bwd_dim(const float* d_grad_scores, const float* d_grad_out, const int32_t* d_argmax,
+                       const void* d_q, int n_queries, int nq_pad,
+                       const void* d_docs, int64_t doc_rows, const int32_t* d_doc_start, int n_docs,
+                       float* d_dq, float* d_dd, int dim, void* stream);
 
 /* flags for cpb_head_fwd */
 #define CPB_HEAD_CLAMP_NORM 1u      /* norm = max(norm, 1e-12): ColModernVBert variant (modeling_colmodernvbert.py:59) */

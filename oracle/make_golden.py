@@ -250,6 +250,61 @@ def head_small():
     print("head_small ok")
 
 
+def wide_dims():
+    """DRAFT (r2): ColQwen3's embedding dim 320 -- scorer (ragged, bf16 and fp32 inputs), ColbertLoss with gradients,
+    and the head of a tiny random-init reference ColQwen3 (models/qwen3/colqwen3/modeling_colqwen3.py)."""
+    from transformers.models.qwen3_vl import Qwen3VLConfig
+
+    from colpali_engine.models import ColQwen3
+
+    out = {}
+    g = torch.Generator().manual_seed(13)
+    qlen = [5, 32, 17, 20]
+    plen = [1, 16, 255, 256, 257, 600, 1030, 64]
+    qs = [torch.nn.functional.normalize(torch.randn(n, 320, generator=g), dim=-1).bfloat16() for n in qlen]
+    ps = [torch.nn.functional.normalize(torch.randn(n, 320, generator=g), dim=-1).bfloat16() for n in plen]
+    out["s_q"], out["s_qlen"], out["s_p"], out["s_plen"] = bits(torch.cat(qs)), np.array(qlen), bits(torch.cat(ps)), np.array(plen)
+    out["s_bf16"] = ref_score(qs, ps).numpy()
+    out["s_fp32"] = ref_score([x.float() for x in qs], [x.float() for x in ps]).numpy()
+    assert torch.equal(O.score_multi_vector_port(qs, ps), torch.from_numpy(out["s_bf16"]))
+    assert torch.equal(O.score_multi_vector_port([x.float() for x in qs], [x.float() for x in ps]), torch.from_numpy(out["s_fp32"]))
+
+    q = torch.nn.functional.normalize(torch.randn(4, 6, 320, generator=g), dim=-1).bfloat16().float()
+    d = torch.nn.functional.normalize(torch.randn(6, 40, 320, generator=g), dim=-1).bfloat16().float()
+    q[1, 4:] = 0
+    d[0, :3] = 0
+    out["l_q"], out["l_d"] = q.numpy().copy(), d.numpy().copy()
+    for name, mod in (("colbert", ColbertLoss()), ("pairwise", ColbertPairwiseCELoss())):
+        qq, dd = q.clone().requires_grad_(True), d.clone().requires_grad_(True)
+        loss = mod(qq, dd, offset=1)
+        loss.backward()
+        out[f"l_{name}_loss"], out[f"l_{name}_dq"], out[f"l_{name}_dd"] = loss.detach().numpy(), qq.grad.numpy(), dd.grad.numpy()
+    assert torch.allclose(O.colbert_loss_port(q, d, offset=1), torch.from_numpy(out["l_colbert_loss"]))
+
+    torch.manual_seed(0)
+    cfg = Qwen3VLConfig(
+        text_config=dict(hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=4,
+                         num_key_value_heads=2, head_dim=64, vocab_size=512,
+                         rope_scaling={"rope_type": "default", "mrope_section": [8, 12, 12]}),
+        vision_config=dict(depth=1, hidden_size=32, intermediate_size=64, num_heads=2, patch_size=14,
+                           out_hidden_size=256, deepstack_visual_indexes=[0]),
+    )
+    model = ColQwen3(cfg).to(torch.bfloat16).eval()
+    captured = {}
+    model.custom_text_proj.register_forward_hook(lambda m, i, o: captured.__setitem__("h", i[0].detach()))
+    ids = torch.randint(0, 500, (3, 24))
+    mask = torch.ones(3, 24, dtype=torch.long)
+    mask[0, :7] = 0
+    mask[2, :3] = 0
+    with torch.no_grad():
+        emb = model(input_ids=ids, attention_mask=mask)
+    h, w, b = captured["h"], model.custom_text_proj.weight.detach(), model.custom_text_proj.bias.detach()
+    assert emb.shape == (3, 24, 320) and torch.equal(O.head_port(h, w, b, mask), emb)
+    out["h_h"], out["h_w"], out["h_b"], out["h_out"], out["h_mask"] = bits(h), bits(w), bits(b), bits(emb), mask.numpy()
+    np.savez_compressed(os.path.join(GOLD, "wide_dim320.npz"), **out)
+    print("wide_dim320 ok")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
     which = set(sys.argv[1:]) or {"scorer_small", "cfg1", "cfg2", "loss_small", "loss_neg_small", "loss_cfg3", "head_small"}
@@ -267,3 +322,5 @@ if __name__ == "__main__":
         loss_cfg3()
     if "head_small" in which:
         head_small()
+    if "wide" in which:  # DRAFT fixture, not in the default set
+        wide_dims()

@@ -79,8 +79,10 @@ def test_every_entry_point_validates_before_touching_cuda(lib):
     # head
     rc = lib.cpb_head_fwd(None, 0, 1536, None, None, 128, None, None, None, 0, None)
     assert rc == INVALID
-    rc = lib.cpb_head_fwd(None, 10, 1536, None, None, 320, None, None, None, 0, None)
-    assert rc == UNSUPPORTED and b"320" in lib.cpb_last_error()                               # ColQwen3 dim: next row
+    rc = lib.cpb_head_fwd(None, 10, 1536, None, None, 352, None, None, None, 0, None)
+    assert rc == UNSUPPORTED and b"352" in lib.cpb_last_error()                               # above ColQwen3's 320
+    rc = lib.cpb_head_fwd(None, 10, 1536, None, None, 200, None, None, None, 0, None)
+    assert rc == UNSUPPORTED and b"200" in lib.cpb_last_error()                               # not a multiple of 32
     rc = lib.cpb_head_fwd(None, 10, 1000, None, None, 128, None, None, None, 0, None)
     assert rc == UNSUPPORTED and b"multiple of 64" in lib.cpb_last_error()
     # balanced / all-gather variants and their helpers

@@ -83,4 +83,52 @@ def test_unsupported_shapes_fail_loudly():
         cb.fused_head(h, torch.zeros(128, 100, dtype=torch.bfloat16, device=DEV), None)  # hidden % 64 != 0
     with pytest.raises(cb.ColpaliB200Error):
         cb.fused_head(torch.zeros(4, 128, dtype=torch.bfloat16, device=DEV),
-                      torch.zeros(320, 128, dtype=torch.bfloat16, device=DEV), None)      # dim 320 (ColQwen3)
+                      torch.zeros(352, 128, dtype=torch.bfloat16, device=DEV), None)      # dim > 320
+    with pytest.raises(cb.ColpaliB200Error):
+        cb.fused_head(torch.zeros(4, 128, dtype=torch.bfloat16, device=DEV),
+                      torch.zeros(200, 128, dtype=torch.bfloat16, device=DEV), None)      # dim % 32 != 0
+
+
+@pytest.mark.parametrize("head_cluster", (1, 2), ids=("cluster1", "cluster2"))
+@pytest.mark.parametrize("tokens,hidden,dim", [(5000, 2560, 320), (777, 2048, 320), (130, 64, 320), (1000, 1536, 192),
+                                               (1000, 1536, 256), (127, 128, 160)])
+def test_wide_projection_dims_against_oracle(tokens, hidden, dim, head_cluster):
+    """DRAFT (r2): head_wide_sm100.cu -- ColQwen3's dim = 320 (models/qwen3/colqwen3/modeling_colqwen3.py:48) and
+    the other multiples of 32 above 128, with and without the 2-CTA W multicast."""
+    from colpali_b200 import _lib
+    gen = torch.Generator().manual_seed(hidden + dim)
+    h = (torch.randn(tokens, hidden, generator=gen) * 2).bfloat16()
+    w = (torch.randn(dim, hidden, generator=gen) / hidden ** 0.5).bfloat16()
+    b = (torch.randn(dim, generator=gen) * 0.1).bfloat16()
+    mask = (torch.rand(tokens, generator=gen) > 0.2).long()
+    img = torch.rand(tokens, generator=gen) > 0.5
+    _lib.set_option("head_cluster", head_cluster)
+    try:
+        want = O.head_port(h, w, b, mask)
+        got = cb.fused_head(h.to(DEV), w.to(DEV), b.to(DEV), mask.to(DEV)).cpu()
+        assert got.shape == (tokens, dim)
+        assert bit_identical_fraction(got, want) > 0.995
+        assert torch.allclose(got.float(), want.float(), rtol=0, atol=2 ** -8)
+        want2 = O.head_port(h, w, b, mask, image_mask=img, clamp_norm=True)
+        got2 = cb.fused_head(h.to(DEV), w.to(DEV), b.to(DEV), mask.to(DEV), img.to(DEV), clamp_norm=True).cpu()
+        assert bit_identical_fraction(got2, want2) > 0.995
+        assert (got2[(mask == 0) | ~img] == 0).all()
+        exact = torch.nn.functional.normalize(h.double() @ w.double().T, dim=-1)
+        got3 = cb.fused_head(h.to(DEV), w.to(DEV), None, single_rounding=True).cpu()
+        assert torch.allclose(got3.double(), exact, rtol=0, atol=2 ** -9 + 1e-6)
+    finally:
+        _lib.set_option("head_cluster", 0)
+
+
+def test_wide_dim320_reference_model_forward_golden():
+    """DRAFT (r2): head of a random-init reference ColQwen3 (dim 320), captured by oracle/make_golden.py wide."""
+    g = load_golden("wide_dim320.npz")
+    mask = torch.from_numpy(g["h_mask"])
+    h = from_bits(g["h_h"]).reshape(3, 24, -1)
+    w = from_bits(g["h_w"]).reshape(320, -1)
+    b = from_bits(g["h_b"])
+    want = from_bits(g["h_out"]).reshape(3, 24, 320)
+    got = cb.fused_head(h.to(DEV), w.to(DEV), b.to(DEV), mask.to(DEV)).cpu()
+    assert got.shape == want.shape and (got[mask == 0] == 0).all()
+    assert bit_identical_fraction(got, want) > 0.995
+    assert torch.allclose(got.float(), want.float(), rtol=0, atol=2 ** -8)

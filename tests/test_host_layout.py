@@ -61,4 +61,6 @@ def test_doc_bank_from_dense_tensor_is_zero_copy_and_uniform():
     with pytest.raises(ValueError, match="No passages"):
         scoring.DocBank.from_passages([], CPU)
     with pytest.raises(scoring._lib.ColpaliB200Error):
-        scoring.DocBank.from_passages(torch.randn(2, 3, 256), CPU)   # embedding dim > 128
+        scoring.DocBank.from_passages(torch.randn(2, 3, 400), CPU)   # embedding dim > 320
+    wide = scoring.DocBank.from_passages(torch.randn(2, 3, 300), CPU)  # padded to the next multiple of 64
+    assert wide.flat.shape == (6, 320) and not wide.flat[:, 300:].any()

@@ -178,7 +178,7 @@ def test_errors():
     with pytest.raises(ValueError, match="No passages"):
         cb.score_multi_vector([torch.randn(3, 128)], [], device=DEV)
     with pytest.raises(cb.ColpaliB200Error):
-        cb.score_multi_vector([torch.randn(3, 256)], [torch.randn(3, 256)], device=DEV)
+        cb.score_multi_vector([torch.randn(3, 400)], [torch.randn(3, 400)], device=DEV)
 
 
 def _torch_fp32_maxsim(q, ps, floors, dev):
@@ -280,3 +280,43 @@ def test_randomised_shapes_against_fp32_torch(seed):
     finite = torch.isfinite(want)
     assert torch.equal(torch.isfinite(got), finite), (n_q, nq, n_d, dense)
     assert torch.allclose(got[finite], want[finite], rtol=1e-5, atol=2e-4), (n_q, nq, n_d, dense)
+
+
+@pytest.mark.parametrize("dim", [192, 256, 300, 320])
+def test_wide_embeddings_k_pipelined_kernel(dim):
+    """DRAFT (r2-drafts): embedding dims above 128 (ColQwen3: 320) through cpb_maxsim_fwd_dim."""
+    dev = torch.device(DEV)
+    g = torch.Generator().manual_seed(dim)
+    lens = [int(x) for x in torch.randint(1, 700, (60,), generator=g)]
+    q = torch.nn.functional.normalize(torch.randn(9, 32, dim, generator=g), dim=-1).bfloat16()
+    bank = torch.nn.functional.normalize(torch.randn(sum(lens), dim, generator=g), dim=-1).bfloat16()
+    ps = list(torch.split(bank, lens))
+    got = cb.score_multi_vector(list(q), ps, device=dev)
+    floors = O.reference_floors(lens, 128)
+    lens_t = torch.tensor(lens, device=dev)
+    pad = torch.nn.utils.rnn.pad_sequence([p.to(dev).float() for p in ps], batch_first=True)
+    sim = torch.einsum("bnd,csd->bcns", q.to(dev).float(), pad)
+    valid = torch.arange(pad.shape[1], device=dev)[None, :] < lens_t[:, None]
+    mx = sim.masked_fill(~valid[None, :, None, :], float("-inf")).amax(dim=3)
+    mx = torch.maximum(mx, torch.tensor(floors, device=dev)[None, :, None])
+    want = mx.sum(dim=2).cpu()
+    assert torch.allclose(got, want, rtol=1e-5, atol=2e-4)
+    dense = torch.nn.functional.normalize(torch.randn(40, 515, dim, generator=g), dim=-1).bfloat16()
+    got_d = cb.score_multi_vector(q, dense, device=dev)
+    want_d = torch.einsum("bnd,csd->bcns", q.to(dev).float(), dense.to(dev).float()).amax(3).sum(2).cpu()
+    assert torch.allclose(got_d, want_d, rtol=1e-5, atol=2e-4)
+
+
+def test_wide_dim320_against_reference_golden():
+    """DRAFT (r2): K-pipelined scorer at ColQwen3's dim against the reference's own outputs (ragged, N_q up to 32)."""
+    g = load_golden("wide_dim320.npz")
+    qs = split_rows(from_bits(g["s_q"], (-1, 320)), g["s_qlen"])
+    ps = split_rows(from_bits(g["s_p"], (-1, 320)), g["s_plen"])
+    got = cb.score_multi_vector(qs, ps, device=DEV)
+    want = torch.from_numpy(g["s_fp32"])
+    assert rel_err(got, want) < 1e-4
+    assert torch.equal(got.argmax(1), want.argmax(1))
+    got_bf = cb.score_multi_vector(qs, ps, device=DEV, round_bf16=True)
+    want_bf = torch.from_numpy(g["s_bf16"])
+    ulp = want_bf.abs().clamp_min(1e-3) * 2.0 ** -7
+    assert ((got_bf - want_bf).abs() <= ulp).all()
