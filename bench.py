@@ -31,6 +31,30 @@ FLOPS_PER_STEP = 2.0 * N_QUERIES * N_Q * N_DOCS * N_D * DIM
 MIN_BYTES_PER_STEP = 2 * (N_DOCS * N_D * DIM + N_QUERIES * N_Q * DIM) + 4 * N_QUERIES * N_DOCS
 METRIC = "maxsim_queries_per_sec"
 UNIT = "queries/s"
+# identical in both arms (the driver compares the `config` objects of the two JSON lines)
+CONFIG = {"workload": "score_multi_vector 32q x 1000d x 1030p x 128d bf16 (BASELINE configs[1])",
+          "n_queries": N_QUERIES, "query_len": N_Q, "n_docs_per_gpu": N_DOCS, "doc_len": N_D, "dim": DIM}
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def reference_scorer():
+    """The CPU arm: the UNMODIFIED reference from baseline/_ref (installed by baseline/install_ref.py; it travels to
+    the GPU box) called exactly as shipped -- ``BaseVisualRetrieverProcessor.score_multi_vector(qs, ps, batch_size=128,
+    device="cpu")`` (processing_utils.py:132-187).  Falls back to the oracle port (same ATen calls) when the install is
+    absent.  Returns (callable, kind)."""
+    if os.path.isdir(os.path.join(REF_DIR, "colpali_engine")):
+        if REF_DIR not in sys.path:
+            sys.path.insert(0, REF_DIR)
+        try:
+            from colpali_engine.utils.processing_utils import BaseVisualRetrieverProcessor
+
+            return (lambda q, d: BaseVisualRetrieverProcessor.score_multi_vector(q, d, batch_size=128, device="cpu"),
+                    "reference")
+        except Exception as e:  # noqa: BLE001 - a broken install must not kill the bench; say so and use the port
+            print(f"[bench] baseline/_ref import failed ({e!r}); using the oracle port", file=sys.stderr)
+    from oracle import li_oracle as O  # bench.py's CPU-baseline leg is allowed to execute oracle/
+
+    return (lambda q, d: O.score_multi_vector_port(q, d, batch_size=128, device="cpu")), "port"
 
 
 def peaks():
@@ -117,37 +141,37 @@ def host_cores() -> int:
     return n
 
 
-def pick_cpu_threads() -> int:
+def pick_cpu_threads(fn) -> int:
     """Give the reference arm its best thread count: calibrate {cores, 2*cores} on a 1/16-size sample."""
-    from oracle import li_oracle as O
+    from oracle import li_oracle as O  # input generator only
 
     cores = host_cores()
     q, d = O.cfg2_inputs(64)
     best, best_t = cores, float("inf")
     for t in sorted({cores, min(2 * cores, os.cpu_count() or cores)}):
         torch.set_num_threads(t)
-        O.score_multi_vector_port(q, d)
+        fn(q, d)
         t0 = time.perf_counter()
-        O.score_multi_vector_port(q, d)
+        fn(q, d)
         dt = time.perf_counter() - t0
         if dt < best_t:
             best, best_t = t, dt
     return best
 
 
-def cpu_reference_arm(steps: int, warmup: int, threads: int):
-    """Times the oracle port of score_multi_vector (the reference's torch.einsum CPU path,
-    processing_utils.py:170-187) on the host cores.  Returns (queries/s, seconds/step, sample)."""
-    from oracle import li_oracle as O  # bench.py's CPU-baseline leg is allowed to execute oracle/
+def cpu_reference_arm(fn, steps: int, warmup: int, threads: int):
+    """Times the reference's score_multi_vector (torch.einsum CPU path, processing_utils.py:170-187) on the host
+    cores, inputs resident in host memory as bf16.  Returns (queries/s, seconds/step, sample)."""
+    from oracle import li_oracle as O  # input generator only (seeded cfg2 tensors)
 
     torch.set_num_threads(threads)
     q, d = O.cfg2_inputs()
     for _ in range(max(1, min(warmup, 1))):
-        O.score_multi_vector_port(q, d, batch_size=128, device="cpu")
+        fn(q, d)
     times = []
     for _ in range(steps):
         t = time.perf_counter()
-        O.score_multi_vector_port(q, d, batch_size=128, device="cpu")
+        fn(q, d)
         times.append(time.perf_counter() - t)
     times.sort()
     med = times[len(times) // 2]
@@ -158,16 +182,19 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = pick_cpu_threads()
+    fn, kind = reference_scorer()
+    threads = pick_cpu_threads(fn)
     steps = max(3, min(args.steps, 9))
-    qps, sec, sample = cpu_reference_arm(steps, args.warmup, threads)
+    qps, sec, sample = cpu_reference_arm(fn, steps, args.warmup, threads)
+    path = ("UNMODIFIED colpali_engine from baseline/_ref: BaseVisualRetrieverProcessor.score_multi_vector(qs, ps, "
+            "batch_size=128, device='cpu')" if kind == "reference"
+            else "oracle port of colpali_engine score_multi_vector (torch.einsum, CPU, batch_size=128)")
     line = {
         "impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "score_multi_vector 32q x 1000d x 1030p x 128d bf16 (BASELINE configs[1])",
-                   "path": "oracle port of colpali_engine score_multi_vector (torch.einsum, CPU, batch_size=128)"},
-        "cpu_baseline": {"value": qps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+        "config": dict(CONFIG), "details": {"path": path, "timing": "time.perf_counter around each call, median"},
+        "cpu_baseline": {"value": qps, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample,
                          "host_cores": host_cores()},
         "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

@@ -18,7 +18,8 @@ from typing import Dict, Tuple
 
 _saved: Dict[Tuple[str, str], object] = {}
 
-_LOSS_NAMES = ("ColbertModule", "ColbertLoss", "ColbertPairwiseCELoss", "ColbertNegativeCELoss",
+# the five concrete losses; the reference's ``ColbertModule`` base (helper methods only) is left alone
+_LOSS_NAMES = ("ColbertLoss", "ColbertPairwiseCELoss", "ColbertNegativeCELoss",
                "ColbertPairwiseNegativeCELoss", "ColbertSigmoidLoss")
 
 
@@ -29,15 +30,20 @@ def _swap(obj, name: str, new) -> None:
     setattr(obj, name, new)
 
 
-def install(scorer: bool = True, losses: bool = True) -> None:
-    """Patch ``colpali_engine`` in this process.  Raises ImportError if the reference is not importable."""
+def install(scorer: bool = True, losses: bool = True, single_vector: bool = False) -> None:
+    """Patch ``colpali_engine`` in this process.  Raises ImportError if the reference is not importable.
+
+    ``single_vector`` (off by default) also replaces ``score_single_vector``: the Bi* processors call it with
+    hidden-size embeddings (e.g. 1536-dim fp32), which the reference scores in the input dtype; the fused kernel
+    contracts bf16 over at most 320 dims, so that swap is opt-in."""
     from . import losses as _losses
     from . import scoring as _scoring
 
     if scorer:
         pu = importlib.import_module("colpali_engine.utils.processing_utils")
         _swap(pu.BaseVisualRetrieverProcessor, "score_multi_vector", staticmethod(_scoring.score_multi_vector))
-        _swap(pu.BaseVisualRetrieverProcessor, "score_single_vector", staticmethod(_scoring.score_single_vector))
+        if single_vector:
+            _swap(pu.BaseVisualRetrieverProcessor, "score_single_vector", staticmethod(_scoring.score_single_vector))
     if losses:
         for modname in ("colpali_engine.loss.late_interaction_losses", "colpali_engine.loss"):
             mod = importlib.import_module(modname)

@@ -2,7 +2,8 @@
 
 Mirrors ``colpali_engine/loss/late_interaction_losses.py`` (reference @ 9be8f19):
 
-* ``ColbertModule``           :6-107   (hyper-parameters + the small helper methods, kept for API parity)
+* ``ColbertModule``           :6-107   (hyper-parameters only; the reference's eager helper methods ``_aggregate`` /
+                                        ``_smooth_max`` / ``_filter_high_negatives`` live inside the kernels here)
 * ``ColbertLoss``             :110-164 (InfoNCE over in-batch documents)
 * ``ColbertPairwiseCELoss``   :255-313 (softplus(hardest in-batch negative - positive))
 * ``ColbertNegativeCELoss``   :167-252, ``ColbertPairwiseNegativeCELoss`` :316-398 (explicit negatives)
@@ -177,7 +178,7 @@ class _NegLossFn(torch.autograd.Function):
 
 
 class ColbertModule(torch.nn.Module):
-    """late_interaction_losses.py:6-107 -- hyper-parameters and helper methods of the ColBERT losses."""
+    """late_interaction_losses.py:6-31 -- the hyper-parameters shared by the ColBERT losses and the fused dispatch."""
 
     def __init__(self, max_batch_size: int = 1024, tau: float = 0.1, norm_tol: float = 1e-3,
                  filter_threshold: float = 0.95, filter_factor: float = 0.5):
@@ -190,35 +191,6 @@ class ColbertModule(torch.nn.Module):
         # set True to reproduce the reference's "Scores out of bounds after normalization" print (:64-70);
         # it costs a host sync per step, which is why it is off by default here
         self.check_bounds = False
-
-    # -- helpers kept for drop-in parity with the reference's own unit tests (tests/loss/test_li_losses.py) --
-    def _get_idx(self, batch_size: int, offset: int, device: torch.device):
-        idx = self.idx_buffer[:batch_size].to(device)
-        return idx, idx + offset
-
-    def _smooth_max(self, scores: torch.Tensor, dim: int) -> torch.Tensor:
-        return self.tau * torch.logsumexp(scores / self.tau, dim=dim)
-
-    def _apply_normalization(self, scores: torch.Tensor, lengths: torch.Tensor) -> torch.Tensor:
-        normalized = scores / lengths.unsqueeze(1) if scores.ndim == 2 else scores / lengths
-        mn, mx = torch.aminmax(normalized)
-        if mn < -self.norm_tol or mx > 1 + self.norm_tol:
-            print(f"Scores out of bounds after normalization: min={mn.item():.4f}, max={mx.item():.4f}, tol={self.norm_tol}")
-        return normalized
-
-    def _aggregate(self, scores_raw: torch.Tensor, use_smooth_max: bool, dim_max: int, dim_sum: int) -> torch.Tensor:
-        if use_smooth_max:
-            return self._smooth_max(scores_raw, dim=dim_max).sum(dim=dim_sum)
-        return scores_raw.amax(dim=dim_max).sum(dim=dim_sum)
-
-    def _filter_high_negatives(self, scores: torch.Tensor, pos_idx: torch.Tensor) -> None:
-        batch_size = scores.size(0)
-        idx = self.idx_buffer[:batch_size].to(scores.device)
-        pos_scores = scores[idx, pos_idx]
-        thresh = self.filter_threshold * pos_scores.unsqueeze(1)
-        mask = scores > thresh
-        mask[idx, pos_idx] = False
-        scores[mask] *= self.filter_factor
 
     # -- shared fused path ------------------------------------------------------------------------------
     def _fused_in_batch_loss(self, mode: int, q: torch.Tensor, d: torch.Tensor, offset: int) -> torch.Tensor:
@@ -248,7 +220,6 @@ class ColbertLoss(ColbertModule):
         self.normalize_scores = normalize_scores
         self.use_smooth_max = use_smooth_max
         self.pos_aware_negative_filtering = pos_aware_negative_filtering
-        self.ce_loss = torch.nn.CrossEntropyLoss()  # attribute kept for parity (:138); the fused kernel does the work
 
     def forward(self, query_embeddings: torch.Tensor, doc_embeddings: torch.Tensor, offset: int = 0) -> torch.Tensor:
         return self._fused_in_batch_loss(_lib.CPB_LOSS_CE, query_embeddings, doc_embeddings, offset)
@@ -282,7 +253,6 @@ class ColbertSigmoidLoss(ColbertModule):
         self.normalize_scores = normalize_scores
         self.use_smooth_max = use_smooth_max
         self.pos_aware_negative_filtering = pos_aware_negative_filtering
-        self.ce_loss = torch.nn.CrossEntropyLoss()
 
     def forward(self, query_embeddings: torch.Tensor, doc_embeddings: torch.Tensor, offset: int = 0) -> torch.Tensor:
         if offset != 0 or query_embeddings.shape[0] != doc_embeddings.shape[0]:
@@ -326,9 +296,6 @@ class ColbertNegativeCELoss(_NegativeLossBase):
                  filter_factor: float = 0.5):
         super().__init__(temperature, normalize_scores, use_smooth_max, pos_aware_negative_filtering,
                          in_batch_term_weight, max_batch_size, tau, norm_tol, filter_threshold, filter_factor)
-        self.ce_loss = torch.nn.CrossEntropyLoss()
-        self.inner_loss = ColbertLoss(temperature, normalize_scores, use_smooth_max, pos_aware_negative_filtering,
-                                      max_batch_size, tau, norm_tol, filter_threshold, filter_factor)  # parity (:203-213)
 
 
 class ColbertPairwiseNegativeCELoss(_NegativeLossBase):
@@ -343,6 +310,3 @@ class ColbertPairwiseNegativeCELoss(_NegativeLossBase):
                  filter_factor: float = 0.5):
         super().__init__(temperature, normalize_scores, use_smooth_max, pos_aware_negative_filtering,
                          in_batch_term_weight, max_batch_size, tau, norm_tol, filter_threshold, filter_factor)
-        self.inner_pairwise = ColbertPairwiseCELoss(temperature, normalize_scores, use_smooth_max,
-                                                    pos_aware_negative_filtering, max_batch_size, tau, norm_tol,
-                                                    filter_threshold, filter_factor)  # parity (:349-359)

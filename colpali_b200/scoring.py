@@ -135,6 +135,9 @@ class DocBank:
         self.n_docs = int(start.numel())
         self.device = flat.device
 
+    def __len__(self) -> int:
+        return self.n_docs
+
     @staticmethod
     def from_passages(ps: TensorOrList, device: torch.device, batch_size: int = 128,
                       reference_padding: bool = True) -> "DocBank":
@@ -239,13 +242,18 @@ def score_multi_vector(
     defines the reference's zero-padding groups, hence the result for ragged list inputs.
     Extra keyword ``round_bf16`` reproduces the reference's bf16-rounded scores for bf16 inputs.
     """
-    dev = _resolve_device(device)
     if len(qs) == 0:
         raise ValueError("No queries provided")
-    if len(ps) == 0:
-        raise ValueError("No passages provided")
-    _require_cuda(dev)
-    bank = ps if isinstance(ps, DocBank) else DocBank.from_passages(ps, dev, batch_size=batch_size)
+    if isinstance(ps, DocBank):  # a resident bank fixes the device
+        if device is not None and _resolve_device(device) != ps.device:
+            raise ValueError(f"the DocBank lives on {ps.device}, not on {device}")
+        dev, bank = ps.device, ps
+    else:
+        if len(ps) == 0:
+            raise ValueError("No passages provided")
+        dev = _resolve_device(device)
+        _require_cuda(dev)
+        bank = DocBank.from_passages(ps, dev, batch_size=batch_size)
     q = QueryBlock(qs, dev)
     scores = maxsim(q, bank, round_bf16=round_bf16)
     out = scores.cpu()  # the reference contract: scores live on the CPU (:180)

@@ -93,6 +93,7 @@ def score_sharded(
         dist.all_gather_into_tensor(gathered.view(world * nq, width), slab, group=group)
         return torch.cat([gathered[r, :, : hi - lo] for r, (lo, hi) in enumerate(bounds)], dim=1)
 
+    top_k = min(top_k, n_docs_total)  # never return (-inf, INT64_MAX) filler candidates
     k_local = min(top_k, n_local)
     s, i = torch.topk(local, k_local, dim=1)
     cand_s = torch.full((nq, top_k), float("-inf"), dtype=torch.float32, device=local.device)

@@ -1,5 +1,6 @@
 """CPU: install()/uninstall() swap exactly the reference's seams (exercised on a stub package that has the
-reference's attribute layout; the real colpali_engine is not present on the GPU box)."""
+reference's attribute layout, so it runs without the reference; tests/test_reference_replay_gpu.py does the same on the
+real package from baseline/_ref)."""
 import sys
 import textwrap
 
@@ -51,6 +52,11 @@ def test_install_and_uninstall(tmp_path, monkeypatch):
         assert L.ColbertLoss is cb.ColbertLoss and L.ColbertPairwiseCELoss is cb.ColbertPairwiseCELoss
         assert L.late_interaction_losses.ColbertLoss is cb.ColbertLoss                   # dotted-path configs resolve to it
         assert L.ColbertSigmoidLoss is cb.ColbertSigmoidLoss
+        assert L.ColbertModule is not cb.ColbertModule                                   # the helper base class stays the reference's
+        # score_single_vector (Bi* processors, hidden-size fp32 embeddings) is opt-in
+        assert pu.BaseVisualRetrieverProcessor.score_single_vector(1, 2) == "reference-single"
+        cb.install(single_vector=True)
+        assert pu.BaseVisualRetrieverProcessor.score_single_vector is cb.score_single_vector
         # constructible with the reference's keyword arguments (scripts/configs/**/*.yaml)
         L.ColbertPairwiseCELoss(temperature=0.02, normalize_scores=True, use_smooth_max=False,
                                 pos_aware_negative_filtering=False, max_batch_size=1024, tau=0.1, norm_tol=1e-3,

@@ -63,20 +63,6 @@ def test_zero_embedding_known_answers():
     assert math.isclose(float(pw(q, d)), math.log(2.0), rel_tol=1e-6)
 
 
-def test_helper_methods_known_answers():
-    """ColbertModule helpers, same KATs as tests/loss/test_li_losses.py:16-74."""
-    m = cb.ColbertModule(max_batch_size=5)
-    idx, pos = m._get_idx(3, 2, torch.device("cpu"))
-    assert idx.tolist() == [0, 1, 2] and pos.tolist() == [2, 3, 4]
-    raw = torch.tensor([[[1.0, 2.0], [3.0, 4.0]], [[5.0, 6.0], [7.0, 8.0]]])
-    assert torch.allclose(m._aggregate(raw, False, 2, 1), torch.tensor([6.0, 14.0]))
-    m2 = cb.ColbertModule(tau=1.0)
-    assert torch.allclose(m2._aggregate(torch.zeros(1, 2, 2), True, 2, 1), 2 * torch.log(torch.tensor(2.0)))
-    s = torch.tensor([[1.0, 0.96], [0.5, 1.0]])
-    cb.ColbertModule()._filter_high_negatives(s, torch.tensor([0, 1]))
-    assert s[0, 1] == pytest.approx(0.48) and s[0, 0] == 1.0 and s[1, 0] == 0.5
-
-
 def test_cfg3_loss_and_gradients():
     """B=64 pairs, N_q=32, documents 768..1030 tokens left-padded to 1030 (BASELINE configs[2])."""
     g = load_golden("loss_cfg3.npz")
