@@ -33,6 +33,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include "maxsim_epilogue.cuh"
 #include "maxsim_params.h"
 #include "sm100_ptx.cuh"
 
@@ -63,94 +64,6 @@ struct SmemLayout {
   static constexpr int kBytes = kTmemPtrOff + 16;
   static constexpr int kAlloc = kBytes + 1024;  // slack for manual 1024-B alignment
 };
-
-// A run = documents [d, e) stored back to back in the bank, rows [row0, row1): tiled without gaps.
-// With CPB_FLAG_CONTIGUOUS the caller guarantees start[j+1] == start[j] + len[j] for the whole bank, so a
-// CTA's partition is ONE run (two loads, no scan); otherwise every document is its own run.
-struct Run {
-  int e, row0, row1;
-};
-__device__ __forceinline__ Run next_run(const MaxSimParams& p, int d, int d1, int bal_r0, int bal_r1) {
-  Run r;
-  if (p.balanced) {  // the partition is the row range [bal_r0, bal_r1), whatever documents it cuts
-    r.e = d1;
-    r.row0 = bal_r0;
-    r.row1 = bal_r1;
-    return r;
-  }
-  r.row0 = __ldg(p.doc_start + d);
-  if (p.flags & CPB_FLAG_CONTIGUOUS) {
-    r.e = d1;
-    r.row1 = __ldg(p.doc_start + d1 - 1) + __ldg(p.doc_len + d1 - 1);
-  } else {
-    r.e = d + 1;
-    r.row1 = r.row0 + __ldg(p.doc_len + d);
-  }
-  return r;
-}
-
-__device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
-
-// max over 32 accumulator columns folded into m (16 FMNMX3, shallow dependency tree)
-__device__ __forceinline__ float max32(const uint32_t (&v)[32], float m) {
-  float t[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-    t[i] = fmax3(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]));
-  float u0 = fmax3(t[0], t[1], __uint_as_float(v[3]));
-  float u1 = fmax3(t[2], t[3], __uint_as_float(v[7]));
-  float u2 = fmax3(t[4], t[5], __uint_as_float(v[11]));
-  float u3 = fmax3(t[6], t[7], __uint_as_float(v[15]));
-  float w0 = fmax3(u0, __uint_as_float(v[19]), __uint_as_float(v[23]));
-  float w1 = fmax3(u1, __uint_as_float(v[27]), __uint_as_float(v[31]));
-  float x0 = fmax3(w0, w1, u2);
-  return fmax3(x0, u3, m);
-}
-
-// max of 32 accumulator columns (15 FMNMX3)
-__device__ __forceinline__ float tree32(const uint32_t (&v)[32]) {
-  float t[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-    t[i] = fmax3(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]));
-  float u0 = fmax3(t[0], t[1], __uint_as_float(v[3]));
-  float u1 = fmax3(t[2], t[3], __uint_as_float(v[7]));
-  float u2 = fmax3(t[4], t[5], __uint_as_float(v[11]));
-  float u3 = fmax3(t[6], t[7], __uint_as_float(v[15]));
-  float w0 = fmax3(u0, __uint_as_float(v[19]), __uint_as_float(v[23]));
-  float w1 = fmax3(u1, __uint_as_float(v[27]), __uint_as_float(v[31]));
-  return fmax3(fmax3(w0, w1, u2), u3, u3);
-}
-
-// max over columns lo <= i < hi of a 32-column chunk
-__device__ __forceinline__ float max32_range(const uint32_t (&v)[32], float m, int lo, int hi) {
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    float x = (i >= lo && i < hi) ? __uint_as_float(v[i]) : -INFINITY;
-    m = fmaxf(m, x);
-  }
-  return m;
-}
-
-// running (value, first index) argmax over columns lo <= i < hi; strict '>' keeps the earliest maximum,
-// which is what torch.max(dim) returns on ties.  idx0 = document-relative index of column 0 of the chunk.
-__device__ __forceinline__ void argmax32_range(const uint32_t (&v)[32], float& m, int& idx, int idx0, int lo, int hi) {
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    float x = __uint_as_float(v[i]);
-    bool take = (i >= lo) && (i < hi) && (x > m);
-    m = take ? x : m;
-    idx = take ? (idx0 + i) : idx;
-  }
-}
-
-__device__ __forceinline__ float round_bf16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
-
-__device__ __forceinline__ float warp_sum(float x) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-  return x;
-}
 
 template <int R, bool kArgmax>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -406,347 +319,9 @@ maxsim_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       }
     }
   } else {
-    // ================================ epilogue ==============================================
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may read
-    const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
-    const bool round_ref = (p.flags & CPB_FLAG_ROUND_BF16) != 0;
-    const bool skip = (p.flags & CPB_DBG_SKIP_EPILOGUE) != 0;
-
-    // document `doc` is complete for resident query tile r: fold this query segment's 32 token maxima
-    auto finalize = [&](int doc, int r, float mm, int ai) {
-      const int row0 = (g * R + r) * kTileM + quad * 32;  // first padded query row of this warp
-      const int q = row0 / p.nq_pad;
-      const int seg = (row0 % p.nq_pad) >> 5;
-      if (kArgmax && p.argmax != nullptr && row0 + lane < p.q_rows)
-        p.argmax[static_cast<int64_t>(doc) * p.q_rows + row0 + lane] = ai;
-      float x = round_ref ? round_bf16(mm) : mm;
-      x = warp_sum(x);
-      if (round_ref && p.nq_pad == 32) x = round_bf16(x);
-      if (lane == 0 && q < p.n_queries && !(p.flags & CPB_DBG_CLOCKS)) {
-        if (p.peer_scores != nullptr) {
-          // fused all-gather of the score slabs: one 4-byte store per peer GPU, straight into its copy of
-          // gathered[my_rank] through the NVLink peer mapping (no collective kernel afterwards, only a barrier)
-          const int64_t off = p.peer_slab_offset + static_cast<int64_t>(q) * p.n_docs + doc;
-          for (int pr = 0; pr < p.n_peers; ++pr) reinterpret_cast<float*>(__ldg(p.peer_scores + pr))[off] = x;
-        } else {
-          p.scores[static_cast<int64_t>(seg) * p.plane_stride + static_cast<int64_t>(q) * p.n_docs + doc] = x;
-        }
-      }
-    };
-    auto doc_init = [&](int doc) { return (p.doc_floor != nullptr) ? __ldg(p.doc_floor + doc) : -INFINITY; };
-
-    float m[R];
-    int am[R];
-    uint32_t job = 0;
-    const bool dbg = (p.flags & CPB_DBG_CLOCKS) != 0;
-    long long e_wait = 0, e_hold = 0, e_post = 0, e_hold2 = 0;
-    int n_path2 = 0;
-
-    // ---- balanced mode: which document contains the first row of my partition, and is it cut? ----------------
-    int first_doc = d0;
-    bool head_frag = false;
-    if (p.balanced) {
-      if (bal_r0 == 0) {
-        first_doc = 0;
-      } else if (p.uniform_len > 0) {
-        first_doc = bal_r0 / p.uniform_len;
-      } else {  // last document that starts at or before bal_r0 (starts are sorted in a contiguous bank)
-        int lo = 0, hi = p.n_docs - 1;
-        while (lo < hi) {
-          const int mid = (lo + hi + 1) >> 1;
-          if (__ldg(p.doc_start + mid) <= bal_r0) lo = mid; else hi = mid - 1;
-        }
-        first_doc = lo;
-      }
-      first_doc = min(first_doc, p.n_docs - 1);
-      head_frag = __ldg(p.doc_start + first_doc) < bal_r0;
-    }
-    // slot of the boundary between partitions `bp` and `bp + 1` for resident query tile r
-    auto split_slot = [&](int bp, int r) { return ((g * p.doc_parts + bp) * R + r); };
-    auto publish = [&](int r, float mm, int ai) {  // I hold the RIGHT part of a cut document
-      const int slot = split_slot(part - 1, r);
-      p.split_max[slot * 128 + quad * 32 + lane] = mm;
-      if (kArgmax) p.split_idx[slot * 128 + quad * 32 + lane] = ai;
-      __threadfence();
-      __syncwarp();
-      if (lane == 0) *reinterpret_cast<volatile uint32_t*>(p.split_flag + slot * 4 + quad) = p.epoch;
-    };
-    auto consume = [&](int r, float& mm, int& ai) {  // I hold the LEFT part: wait for the neighbour's partial, combine
-      const int slot = split_slot(part, r);
-      if (lane == 0) {
-        const volatile uint32_t* f = reinterpret_cast<volatile uint32_t*>(p.split_flag + slot * 4 + quad);
-        const uint64_t t0 = global_timer_ns();
-        while (*f != p.epoch) {
-          if (global_timer_ns() - t0 > 4000000000ull) __trap();
-        }
-      }
-      __syncwarp();
-      __threadfence();
-      const float om = __ldcg(p.split_max + slot * 128 + quad * 32 + lane);
-      const int oi = kArgmax ? __ldcg(p.split_idx + slot * 128 + quad * 32 + lane) : -1;
-      if (om > mm) {  // on a tie the earlier (left) token wins, like torch.max
-        mm = om;
-        ai = oi;
-      }
-    };
-
-    for (int d = p.balanced ? first_doc : d0; d < d1;) {
-      const Run run = next_run(p, d, d1, bal_r0, bal_r1);
-      if (run.row1 == run.row0) {
-        // nothing but empty documents: their score is the sum of the floors (balanced mode: an empty partition)
-        if (!p.balanced)
-          for (int e = d; e < run.e; ++e)
-            for (int r = 0; r < r_cnt; ++r) finalize(e, r, doc_init(e), -1);
-        d = run.e;
-        continue;
-      }
-      // state at the start of each tile: current document, its first/last bank row, running maxima
-      int cur = d;
-      int cur_row0 = p.balanced ? __ldg(p.doc_start + cur) : run.row0;
-      int cur_end = cur_row0 + __ldg(p.doc_len + cur);
-      // length and floor of the FOLLOWING document are fetched when the cursor moves, long before they are needed:
-      // a global load while the accumulator is held costs ~300 cycles of tensor idle time on boundary tiles
-      int cur_nlen = (cur + 1 < run.e) ? __ldg(p.doc_len + cur + 1) : 0;
-      float cur_ninit = (cur + 1 < run.e) ? doc_init(cur + 1) : -INFINITY;
-      {
-        const float init = doc_init(cur);
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          m[r] = init;
-          am[r] = -1;
-        }
-      }
-      for (int row = run.row0; row < run.row1; row += kTileN) {
-        const int n_valid = min(kTileN, run.row1 - row);
-        const int tile_end = row + n_valid;
-        int nxt = cur, nxt_row0 = cur_row0, nxt_end = cur_end, nxt_nlen = cur_nlen;
-        float nxt_ninit = cur_ninit;
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          if (r < r_cnt) {
-            const uint32_t a = job & 1u;
-            const uint32_t aphase = (job >> 1) & 1u;
-            const long long t0 = dbg ? clock64() : 0;
-            mbar_wait(&tmem_full[a], aphase);
-            const long long t1 = dbg ? clock64() : 0;
-            long long t2 = 0;
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + lane_base + a * kTileN;
-            float mm = m[r];
-            int ai = am[r];
-            int doc = cur, doc_row0 = cur_row0, doc_end = cur_end, doc_nlen = cur_nlen;
-            float doc_ninit = cur_ninit;
-
-            // the current document is complete: emit it and step to the next one of the run
-            auto finish_doc = [&]() {
-              if (head_frag && doc == first_doc) publish(r, mm, ai); else finalize(doc, r, mm, ai);
-              ++doc;
-              if (doc >= run.e) {
-                doc_end = 0x7fffffff;  // run exhausted
-                return;
-              }
-              doc_row0 = doc_end;
-              doc_end = doc_row0 + doc_nlen;
-              mm = doc_ninit;
-              ai = -1;
-              doc_nlen = (doc + 1 < run.e) ? __ldg(p.doc_len + doc + 1) : 0;
-              doc_ninit = (doc + 1 < run.e) ? doc_init(doc + 1) : -INFINITY;
-            };
-            auto release_acc = [&]() {  // accumulator drained: hand the TMEM stage back to the MMA warp
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&tmem_empty[a]);
-              if (dbg) t2 = clock64();
-            };
-
-            // Three warp-uniform cases.  (1) the whole 256-column tile belongs to one document: FMNMX3 trees.
-            // (2) exactly one document boundary inside a full tile: the same trees, routed to the old or the
-            // new document per 32-column chunk, plus one masked pass over the chunk that holds the boundary.
-            // (3) anything else (short documents, last tile of a run, argmax): generic masked walk.
-            int path = 3;
-            if (!kArgmax && n_valid == kTileN) {
-              if (doc_end >= tile_end) {
-                path = 1;
-              } else if (doc_end > row && doc + 1 < run.e) {
-                if (doc_end + doc_nlen >= tile_end) path = 2;
-              }
-            }
-            if (skip) {
-              if (p.dbg_delay > 0) {  // profiling aid: hold the (unread) accumulator for a fixed number of cycles
-                const long long t_start = clock64();
-                while (clock64() - t_start < p.dbg_delay) {
-                }
-              }
-              release_acc();
-              while (doc_end <= tile_end) {  // advance the cursor without reading the accumulator
-                ++doc;
-                if (doc >= run.e) { doc_end = 0x7fffffff; break; }
-                doc_row0 = doc_end;
-                doc_end = doc_row0 + doc_nlen;
-                doc_nlen = (doc + 1 < run.e) ? __ldg(p.doc_len + doc + 1) : 0;
-              }
-            } else if (path == 1) {
-              // software pipeline: the loads of columns [64k+64, 64k+128) are in flight while [64k, 64k+64) fold
-              // (TMEM reads are ~64 B/clk per lane quadrant: ~490 cycles for 128 x 256 fp32 whatever the warp count)
-              uint32_t va[32], vb[32], vc[32], vd[32];
-              tmem_ld_x32(taddr, va);
-              tmem_ld_x32(taddr + 32, vb);
-              tmem_ld_wait();
-              reg_fence32(va);
-              reg_fence32(vb);
-              tmem_ld_x32(taddr + 64, vc);
-              tmem_ld_x32(taddr + 96, vd);
-              mm = max32(va, mm);
-              mm = max32(vb, mm);
-              tmem_ld_wait();
-              reg_fence32(vc);
-              reg_fence32(vd);
-              tmem_ld_x32(taddr + 128, va);
-              tmem_ld_x32(taddr + 160, vb);
-              mm = max32(vc, mm);
-              mm = max32(vd, mm);
-              tmem_ld_wait();
-              reg_fence32(va);
-              reg_fence32(vb);
-              tmem_ld_x32(taddr + 192, vc);
-              tmem_ld_x32(taddr + 224, vd);
-              mm = max32(va, mm);
-              mm = max32(vb, mm);
-              tmem_ld_wait();
-              reg_fence32(vc);
-              reg_fence32(vd);
-              release_acc();  // every accumulator read has landed in registers
-              mm = max32(vc, mm);
-              mm = max32(vd, mm);
-              while (doc_end <= tile_end) finish_doc();  // document (and empty followers) ending at the tile end
-            } else if (path == 2) {
-              // one boundary at column b: per 32-column chunk the FMNMX3 tree goes to the old document (chunk < kb)
-              // or the new one (chunk > kb) through selects; the boundary chunk itself is re-read at the end and split
-              // element-wise after the release (branching per chunk would be if-converted into doing everything).
-              const int b = doc_end - row;
-              const int kb = b >> 5;
-              float mb = doc_ninit;
-              auto route = [&](const uint32_t (&v)[32], int c) {
-                const float t = tree32(v);
-                mm = (c < kb) ? fmaxf(mm, t) : mm;
-                mb = (c > kb) ? fmaxf(mb, t) : mb;
-              };
-              uint32_t va[32], vb[32], vc[32], vd[32];
-              tmem_ld_x32(taddr, va);
-              tmem_ld_x32(taddr + 32, vb);
-              tmem_ld_wait();
-              reg_fence32(va);
-              reg_fence32(vb);
-              tmem_ld_x32(taddr + 64, vc);
-              tmem_ld_x32(taddr + 96, vd);
-              route(va, 0);
-              route(vb, 1);
-              tmem_ld_wait();
-              reg_fence32(vc);
-              reg_fence32(vd);
-              tmem_ld_x32(taddr + 128, va);
-              tmem_ld_x32(taddr + 160, vb);
-              route(vc, 2);
-              route(vd, 3);
-              tmem_ld_wait();
-              reg_fence32(va);
-              reg_fence32(vb);
-              tmem_ld_x32(taddr + 192, vc);
-              tmem_ld_x32(taddr + 224, vd);
-              route(va, 4);
-              route(vb, 5);
-              tmem_ld_wait();
-              reg_fence32(vc);
-              reg_fence32(vd);
-              tmem_ld_x32(taddr + kb * 32, va);  // the boundary chunk again
-              route(vc, 6);
-              route(vd, 7);
-              tmem_ld_wait();
-              reg_fence32(va);
-              release_acc();
-              {
-                const int bl = b & 31;
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                  const float x = __uint_as_float(va[i]);
-                  if (i < bl) mm = fmaxf(mm, x); else mb = fmaxf(mb, x);
-                }
-              }
-              finish_doc();  // old document (running max mm); the cursor moves to the new one, whose max is mb
-              mm = mb;
-              while (doc_end <= tile_end) finish_doc();
-            } else {
-#pragma unroll 1
-              for (int cb = 0; cb < n_valid; cb += 32) {
-                uint32_t v[32];
-                tmem_ld_x32(taddr + cb, v);
-                tmem_ld_wait();
-                reg_fence32(v);
-                const int abs0 = row + cb;
-                const int abs1 = min(abs0 + 32, tile_end);
-                int pos = abs0;
-                while (true) {
-                  const int seg_end = min(doc_end, abs1);
-                  if (seg_end > pos) {
-                    if constexpr (kArgmax) {
-                      argmax32_range(v, mm, ai, abs0 - doc_row0, pos - abs0, seg_end - abs0);
-                    } else {
-                      mm = max32_range(v, mm, pos - abs0, seg_end - abs0);
-                    }
-                  }
-                  pos = seg_end;
-                  if (doc_end > abs1) break;  // the current document continues past this chunk
-                  finish_doc();
-                }
-              }
-              release_acc();
-            }
-            if (dbg) {
-              const long long t3 = clock64();
-              e_wait += t1 - t0;
-              e_post += t3 - t2;
-              if (path == 2) { e_hold2 += t2 - t1; ++n_path2; } else { e_hold += t2 - t1; }
-            }
-            m[r] = mm;
-            am[r] = ai;
-            nxt = doc;
-            nxt_row0 = doc_row0;
-            nxt_end = doc_end;
-            nxt_nlen = doc_nlen;
-            nxt_ninit = doc_ninit;
-            ++job;
-          }
-        }
-        cur = nxt;
-        cur_row0 = nxt_row0;
-        cur_end = nxt_end;
-        cur_nlen = nxt_nlen;
-        cur_ninit = nxt_ninit;
-      }
-      if (p.balanced && !skip && cur < p.n_docs && cur_end != 0x7fffffff && cur_row0 < bal_r1 && cur_end > bal_r1) {
-        // my last document continues in the next partition: combine with the neighbour's partial and emit it
-        for (int r = 0; r < r_cnt; ++r) {
-          float mm = m[r];
-          int ai = am[r];
-          if (head_frag && cur == first_doc) {
-            // (a document longer than a whole partition is excluded by the host: it would need a chain)
-            __trap();
-          }
-          consume(r, mm, ai);
-          finalize(cur, r, mm, ai);
-        }
-      }
-      d = run.e;
-    }
-    if (dbg && warp == 2 && lane == 0) {  // epilogue: blocked on MMA / holding the accumulator / after release
-      float* o = p.scores + 512 + 8 * blockIdx.x;
-      o[2] = static_cast<float>(e_wait);
-      o[3] = static_cast<float>(e_hold);
-      o[4] = static_cast<float>(e_post);
-      o[5] = static_cast<float>(e_hold2);
-      o[6] = static_cast<float>(n_path2);
-      o[7] = static_cast<float>(job);
-    }
+    // ================================ epilogue (maxsim_epilogue.cuh) ==========================
+    const CtaSlice sl{g, part, r_cnt, d0, d1, bal_r0, bal_r1};
+    maxsim_epilogue<R, kArgmax>(p, sl, tmem_base, tmem_full, tmem_empty, warp, lane);
   }
 
   // ---- teardown ---------------------------------------------------------------------------
