@@ -202,6 +202,37 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(local: int):
+    """Run this rank (and therefore first-touch its pinned host buffers) on the NUMA node its GPU hangs off.  Round 1:
+    eight ranks pushing 264 MB each from buffers placed on one node made the 8-GPU end-to-end leg slower than the
+    4-GPU one.  Best effort; returns a short record for the JSON line."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:  # NVML pads the PCI domain to 8 hex digits, sysfs uses 4
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return {"node": None, "why": "no NUMA information for this device"}
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return {"node": node, "why": "none of the node's CPUs are in this process's affinity mask"}
+        os.sched_setaffinity(0, allowed)
+        return {"node": node, "cpus": len(allowed)}
+    except Exception as e:  # noqa: BLE001
+        return {"node": None, "why": repr(e)[:120]}
+
+
 def run_b200(args):
     import torch.distributed as dist
 
@@ -211,6 +242,7 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    numa = bind_to_gpu_numa_node(local) if world > 1 else {"node": None, "why": "single rank: not bound"}
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -228,17 +260,16 @@ def run_b200(args):
     if world > 1 and os.environ.get("COLPALI_B200_NCCL_GATHER") != "1":
         from colpali_b200.sharded import FusedGatherScorer
 
-        ok = torch.tensor([int(FusedGatherScorer.available(dev))], device=dev)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if int(ok):
+        if FusedGatherScorer.available(dev):  # agreed across ranks
             fused = FusedGatherScorer(N_QUERIES, N_DOCS, dev)
+    independent = os.environ.get("COLPALI_B200_DEPENDENT") != "1"  # every step scores the same resident inputs
 
     def step():
         if fused is not None:
-            # all-gather fused into the kernel epilogue (NVLink peer stores) + a device-side barrier
-            # (a per-launch completion word is stored into every peer by the last CTA; consumers wait on it)
-            return fused.score(qb, bank)
-        s = cb.maxsim(qb, bank)
+            # all-gather fused into the kernel epilogue (NVSwitch multicast / NVLink peer stores); completion is a
+            # per-CTA release-add on every rank's counters, the write-after-read guard an in-kernel wait on them
+            return fused.score(qb, bank, independent=independent)
+        s = cb.maxsim(qb, bank, independent=independent)
         if world > 1:
             dist.all_gather_into_tensor(gathered.view(world * N_QUERIES, N_DOCS), s)
         return s
@@ -272,7 +303,7 @@ def run_b200(args):
     value = world * N_QUERIES / (ms_step * 1e-3)
 
     # ---- the dominant kernel alone: roofline numerator -------------------------------------------------------------
-    # At N = 1 a step IS one launch of the kernel, so the timed region above is the measurement; with a collective in
+    # At N = 1 a step IS one launch of the kernel, so the timed region above is the measurement; with the exchange in
     # the step (N > 1) the kernel is timed again on its own.
     if world == 1:
         ms_kernel = ms_step
@@ -281,73 +312,120 @@ def run_b200(args):
         sync_all()
         e0.record()
         for _ in range(k_steps):
-            cb.maxsim(qb, bank)
+            cb.maxsim(qb, bank, independent=independent)
         e1.record()
         torch.cuda.synchronize()
         ms_kernel = e0.elapsed_time(e1) / k_steps
 
-    # ---- end to end through the reference-facing API, host buffers in, host scores out ----------
+    # ---- end to end through the public API: host buffers in, host scores out ----------------------------------------
+    # N = 1: colpali_b200.score_multi_vector (the reference's scorer signature).  N > 1: the sharded API -- every rank
+    # uploads ITS shard and the queries, scores with the fused gather and reads the WHOLE [world, 32, 1000] result back.
+    # "cold" re-uploads the bank every step (what the reference does for every call); "warm" keeps the DocBank resident.
     q_host = q.cpu().pin_memory()
     d_host = d.cpu().pin_memory()
     e2e_steps = max(3, min(args.steps, 10))
-    cb.score_multi_vector(q_host, d_host, device=dev)
-    sync_all()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        out = cb.score_multi_vector(q_host, d_host, device=dev)
-    torch.cuda.synchronize()
-    e2e_s = torch.tensor([(time.perf_counter() - t0) / e2e_steps], device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = world * N_QUERIES / float(e2e_s)
-    if fused is not None:  # outside the timed region: the fused gather must equal an NCCL all-gather of the local slabs
-        local = cb.maxsim(qb, bank)
-        dist.all_gather_into_tensor(gathered.view(world * N_QUERIES, N_DOCS), local)
+
+    def e2e_step(cold: bool):
+        if world == 1:
+            return cb.score_multi_vector(q_host, d_host if cold else bank, device=dev)
+        b = cb.DocBank.from_passages(d_host, dev) if cold else bank
+        qq = cb.QueryBlock(q_host, dev)
+        if fused is not None:
+            view = fused.score(qq, b)
+            fused.wait()
+            return view.cpu()
+        s = cb.maxsim(qq, b)
+        dist.all_gather_into_tensor(gathered.view(world * N_QUERIES, N_DOCS), s)
+        return gathered.cpu()
+
+    e2e = {}
+    for name, cold in (("cold", True), ("warm", False)):
+        out = e2e_step(cold)
         sync_all()
-        got = fused.score(qb, bank)
-        fused.wait()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            out = e2e_step(cold)
         torch.cuda.synchronize()
-        assert torch.equal(got, gathered), "fused all-gather disagrees with NCCL"
-    assert out.shape == (N_QUERIES, N_DOCS) and out.device.type == "cpu"
+        sec = torch.tensor([(time.perf_counter() - t0) / e2e_steps], device=dev)
+        if world > 1:
+            dist.all_reduce(sec, op=dist.ReduceOp.MAX)
+        e2e[name] = world * N_QUERIES / float(sec)
+    assert out.device.type == "cpu" and out.shape[-2:] == (N_QUERIES, N_DOCS)
+
+    # ---- self-test carried by the bench run (the driver's GPU test box has one GPU; this is where N > 1 is checked) ---
+    selftest = None
+    if world > 1:
+        n_check = 20
+        qbs = [cb.QueryBlock(torch.nn.functional.normalize(
+            torch.randn(N_QUERIES, N_Q, DIM, device=dev, generator=gq), dim=-1).bfloat16(), dev) for _ in range(n_check)]
+        want = torch.empty(n_check, world, N_QUERIES, N_DOCS, device=dev)
+        for i, x in enumerate(qbs):
+            dist.all_gather_into_tensor(want[i].view(world * N_QUERIES, N_DOCS), cb.maxsim(x, bank))
+        if fused is not None:
+            got = torch.empty_like(want)
+            for i, x in enumerate(qbs):  # back to back, different queries, no host synchronisation in between
+                view = fused.score(x, bank)
+                fused.wait()
+                got[i].copy_(view)
+            torch.cuda.synchronize()
+            fused.check_status()
+            ok = torch.tensor([int(torch.equal(got, want))], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            assert int(ok), "fused all-gather disagrees with NCCL on back-to-back launches"
+            selftest = {"fused_gather_equals_nccl_allgather": f"{n_check}/{n_check} back-to-back launches, all ranks",
+                        "store_path": "multimem.st (NVSwitch multicast)" if fused.mc_base else "per-peer st.global"}
 
     if rank == 0:
         pk = peaks()
         achieved = FLOPS_PER_STEP / (ms_kernel * 1e-3) / 1e12
-        traffic = None
+        traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "maxsim_traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as f:
                 traffic = json.load(f).get("dram_bytes_per_launch")
+            traffic_src = "profiles/maxsim_traffic.json (static: one ncu --set full capture, not measured in this run)"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {
-                "workload": "score_multi_vector 32q x 1000d x 1030p x 128d bf16 (BASELINE configs[1]) per GPU",
+            "config": dict(CONFIG),
+            "details": {
                 "parallelism": (f"corpus-sharded x{world}: 1000 docs/rank, score slabs all-gathered by "
-                                + ("NVLink peer stores fused into the kernel epilogue + per-launch completion words" if fused is not None
+                                + (("NVSwitch multicast stores" if fused.mc_base else "NVLink peer stores")
+                                   + " fused into the kernel epilogue, per-CTA completion counters" if fused is not None
                                    else "NCCL all_gather_into_tensor")) if world > 1 else "single GPU",
+                "launches": "independent (CPB_FLAG_INDEPENDENT: a step reads nothing the previous step wrote)"
+                            if independent else "stream-ordered",
                 "l2": "document bank (264 MB) exceeds L2 (126 MB); no explicit flush",
                 "timing": "CUDA events on the launching stream, max over ranks",
+                "numa": numa,
             },
             "roofline": {
                 "bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": achieved / pk["bf16_tflops"], "traffic": traffic, "peak_source": pk["source"] + " burst",
+                "frac": achieved / pk["bf16_tflops"], "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": pk["source"] + " burst",
                 "kernel_ms": ms_kernel, "algorithmic_flops_per_launch": FLOPS_PER_STEP,
                 "algorithmic_bytes_per_launch": MIN_BYTES_PER_STEP,
                 "hbm_gbs_achieved": MIN_BYTES_PER_STEP / (ms_kernel * 1e-3) / 1e9,
             },
-            "e2e": {"value": e2e_value, "unit": UNIT,
+            "e2e": {"value": e2e["cold"], "unit": UNIT,
                     "h2d_bytes_per_step": q_host.numel() * 2 + d_host.numel() * 2,
-                    "d2h_bytes_per_step": N_QUERIES * N_DOCS * 4, "steps": e2e_steps,
-                    "api": "colpali_b200.score_multi_vector(pinned host q, pinned host docs) -> CPU fp32"},
+                    "d2h_bytes_per_step": world * N_QUERIES * N_DOCS * 4, "steps": e2e_steps,
+                    "warm_bank_value": e2e["warm"], "warm_bank_h2d_bytes_per_step": q_host.numel() * 2,
+                    "api": ("colpali_b200.score_multi_vector(pinned host q, pinned host docs | resident DocBank) -> CPU fp32"
+                            if world == 1 else
+                            "per rank: DocBank.from_passages(pinned host shard) + QueryBlock(pinned host q) -> "
+                            "FusedGatherScorer.score/wait -> gathered [world, 32, 1000] .cpu()")},
             "gpu_launches": launches,
             "clocks": clk.summary(),
         }
+        if selftest:
+            line["selftest"] = selftest
         if not args.no_cpu and world == 1:
-            threads = pick_cpu_threads()
-            qps, sec, sample = cpu_reference_arm(5, 1, threads)
-            line["cpu_baseline"] = {"value": qps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+            fn, kind = reference_scorer()
+            threads = pick_cpu_threads(fn)
+            qps, sec, sample = cpu_reference_arm(fn, 5, 1, threads)
+            line["cpu_baseline"] = {"value": qps, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample,
                                     "seconds_per_step": sec, "host_cores": host_cores()}
         print(json.dumps(line), flush=True)
     if world > 1:

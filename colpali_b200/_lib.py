@@ -20,29 +20,84 @@ EXPORTED_SYMBOLS = (
     "cpb_last_error",
     "cpb_device_info",
     "cpb_set_option",
+    "cpb_colbert_loss_launch",
+    "cpb_maxsim_launch",
     "cpb_maxsim_fwd",
     "cpb_maxsim_workspace_bytes",
-    "cpb_maxsim_fwd_balanced",
-    "cpb_maxsim_fwd_dim",
     "cpb_maxsim_split_workspace_bytes",
-    "cpb_maxsim_fwd_allgather",
     "cpb_wait_flags",
-    "cpb_colbert_loss_fwd",
-    "cpb_colbert_neg_loss_fwd",
-    "cpb_maxsim_bwd",
-    "cpb_maxsim_bwd_dim",
-    "cpb_colbert_loss_fwd_dim",
-    "cpb_colbert_neg_loss_fwd_dim",
+    "cpb_maxsim_bwd_launch",
     "cpb_head_fwd",
 )
 
+CPB_ABI_VERSION = 2
 CPB_FLAG_ROUND_BF16 = 1
 CPB_FLAG_CONTIGUOUS = 2
+CPB_FLAG_INDEPENDENT = 4
 CPB_HEAD_CLAMP_NORM = 1
 CPB_HEAD_SINGLE_ROUNDING = 2
 CPB_LOSS_CE = 0
 CPB_LOSS_PAIRWISE = 1
 CPB_LOSS_SIGMOID = 2
+
+c_vp, c_i, c_i64, c_u32, c_u64, c_f = (ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32, ctypes.c_uint64,
+                                       ctypes.c_float)
+
+
+class LossDesc(ctypes.Structure):
+    """``cpb_loss_desc`` (include/colpali_b200.h)."""
+
+    _fields_ = [
+        ("struct_size", c_u32), ("mode", c_i), ("normalize_scores", c_i), ("pos_aware_negative_filtering", c_i),
+        ("offset", c_i), ("temperature", c_f), ("filter_threshold", c_f), ("filter_factor", c_f),
+        ("d_neg_scores", c_vp), ("n_neg", c_i), ("in_batch_term_weight", c_f),
+        ("d_loss", c_vp), ("d_grad_scores", c_vp), ("d_grad_neg_scores", c_vp), ("d_bounds", c_vp),
+    ]
+
+    def __init__(self, **kw):
+        super().__init__(**kw)
+        self.struct_size = ctypes.sizeof(LossDesc)
+
+
+class MaxSimArgs(ctypes.Structure):
+    """``cpb_maxsim_args`` (include/colpali_b200.h)."""
+
+    _fields_ = [
+        ("struct_size", c_u32), ("flags", c_u32), ("stream", c_vp),
+        ("d_q", c_vp), ("n_queries", c_i), ("nq_pad", c_i), ("nq_real", c_i), ("dim", c_i),
+        ("d_docs", c_vp), ("doc_rows", c_i64), ("d_doc_start", c_vp), ("d_doc_len", c_vp), ("d_doc_floor", c_vp),
+        ("n_docs", c_i), ("uniform_len", c_i), ("max_doc_len", c_i),
+        ("d_scores", c_vp), ("d_argmax", c_vp), ("d_lse", c_vp), ("d_workspace", c_vp),
+        ("d_split_ws", c_vp), ("split_ws_bytes", c_i64), ("epoch", c_u32),
+        ("smooth_tau", c_f),
+        ("d_peer_bases", c_vp), ("mc_base", c_u64), ("n_peers", c_i), ("slab_word_offset", c_i64),
+        ("flag_word_offset", c_i64),
+        ("d_wait_flags", c_vp), ("n_wait", c_i), ("wait_value", c_u32),
+        ("loss", ctypes.POINTER(LossDesc)), ("d_done_counter", c_vp),
+        ("grid_out", c_i),
+    ]
+
+    def __init__(self, **kw):
+        super().__init__(**kw)
+        self.struct_size = ctypes.sizeof(MaxSimArgs)
+
+
+class MaxSimBwdArgs(ctypes.Structure):
+    """``cpb_maxsim_bwd_args`` (include/colpali_b200.h)."""
+
+    _fields_ = [
+        ("struct_size", c_u32), ("flags", c_u32), ("stream", c_vp),
+        ("d_grad_scores", c_vp), ("d_grad_out", c_vp), ("d_argmax", c_vp), ("d_lse", c_vp), ("smooth_tau", c_f),
+        ("d_q", c_vp), ("n_queries", c_i), ("nq_pad", c_i), ("nq_real", c_i), ("dim", c_i),
+        ("d_docs", c_vp), ("doc_rows", c_i64), ("d_doc_start", c_vp), ("d_doc_len", c_vp), ("n_docs", c_i),
+        ("max_doc_len", c_i),
+        ("d_dq", c_vp), ("d_dd", c_vp),
+    ]
+
+    def __init__(self, **kw):
+        super().__init__(**kw)
+        self.struct_size = ctypes.sizeof(MaxSimBwdArgs)
+
 
 _lib: Optional[ctypes.CDLL] = None
 
@@ -62,75 +117,52 @@ def load() -> ctypes.CDLL:
             "Run `python -m colpali_b200.build` (needs nvcc). There is no CPU fallback."
         )
     lib = ctypes.CDLL(LIB_PATH)
-    c_vp, c_i, c_i64, c_u32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_uint32
+    ci = ctypes.c_int
 
-    lib.cpb_abi_version.restype = c_i
+    lib.cpb_abi_version.restype = ci
     lib.cpb_abi_version.argtypes = []
+    if lib.cpb_abi_version() != CPB_ABI_VERSION:
+        raise ColpaliB200Error(f"{LIB_PATH} has ABI version {lib.cpb_abi_version()}, this package needs {CPB_ABI_VERSION}: "
+                               "rebuild with `python -m colpali_b200.build --force`")
     lib.cpb_last_error.restype = ctypes.c_char_p
     lib.cpb_last_error.argtypes = []
-    lib.cpb_device_info.restype = c_i
-    lib.cpb_device_info.argtypes = [c_i, ctypes.POINTER(c_i), ctypes.POINTER(c_i), ctypes.POINTER(c_i)]
-    lib.cpb_set_option.restype = c_i
-    lib.cpb_set_option.argtypes = [ctypes.c_char_p, c_i]
+    lib.cpb_device_info.restype = ci
+    lib.cpb_device_info.argtypes = [ci, ctypes.POINTER(ci), ctypes.POINTER(ci), ctypes.POINTER(ci)]
+    lib.cpb_set_option.restype = ci
+    lib.cpb_set_option.argtypes = [ctypes.c_char_p, ci]
     lib.cpb_maxsim_workspace_bytes.restype = c_i64
-    lib.cpb_maxsim_workspace_bytes.argtypes = [c_i, c_i, c_i]
-    lib.cpb_maxsim_fwd.restype = c_i
+    lib.cpb_maxsim_workspace_bytes.argtypes = [ci, ci, ci]
+    lib.cpb_maxsim_split_workspace_bytes.restype = c_i64
+    lib.cpb_maxsim_split_workspace_bytes.argtypes = [ci, ci]
+    lib.cpb_maxsim_launch.restype = ci
+    lib.cpb_maxsim_launch.argtypes = [ctypes.POINTER(MaxSimArgs)]
+    lib.cpb_maxsim_fwd.restype = ci
     lib.cpb_maxsim_fwd.argtypes = [
-        c_vp, c_i, c_i,  # d_q, n_queries, nq_pad
+        c_vp, ci, ci,  # d_q, n_queries, nq_pad
         c_vp, c_i64,  # d_docs, doc_rows
-        c_vp, c_vp, c_vp, c_i,  # d_doc_start, d_doc_len, d_doc_floor, n_docs
+        c_vp, c_vp, c_vp, ci,  # d_doc_start, d_doc_len, d_doc_floor, n_docs
         c_vp, c_vp, c_vp,  # d_scores, d_argmax, d_workspace
         c_u32, c_vp,  # flags, stream
     ]
-    lib.cpb_maxsim_fwd_dim.restype = c_i
-    lib.cpb_maxsim_fwd_dim.argtypes = lib.cpb_maxsim_fwd.argtypes[:-1] + [c_i, c_vp]
-    lib.cpb_maxsim_split_workspace_bytes.restype = c_i64
-    lib.cpb_maxsim_split_workspace_bytes.argtypes = [c_i, c_i]
-    lib.cpb_maxsim_fwd_balanced.restype = c_i
-    lib.cpb_maxsim_fwd_balanced.argtypes = lib.cpb_maxsim_fwd.argtypes[:-1] + [c_i, c_i, c_vp, c_i64, c_u32, c_vp]
-    lib.cpb_maxsim_fwd_allgather.restype = c_i
-    lib.cpb_maxsim_fwd_allgather.argtypes = [
-        c_vp, c_i, c_i, c_vp, c_i64, c_vp, c_vp, c_vp, c_i,  # q, n_queries, nq_pad, docs, rows, start, len, floor, n_docs
-        c_vp, c_i, c_i, c_u32,  # d_peer_slabs, n_peers, my_rank, flags
-        c_i, c_i, c_vp, c_i64, c_u32,  # uniform_len, max_doc_len, d_split_ws, split_ws_bytes, epoch
-        c_vp, c_i64, c_u32, c_vp,  # d_done_counter, flag_word_offset, signal_value, stream
-    ]
-    lib.cpb_wait_flags.restype = c_i
-    lib.cpb_wait_flags.argtypes = [c_vp, c_i, c_u32, c_vp]
-    c_f = ctypes.c_float
-    lib.cpb_colbert_loss_fwd.restype = c_i
-    lib.cpb_colbert_loss_fwd.argtypes = [
-        c_vp, c_vp, c_i, c_i, c_i, c_i,  # d_scores, d_q, n_queries, nq_pad, n_docs, mode
-        c_f, c_i, c_i, c_f, c_f, c_i,  # temperature, normalize, filter, threshold, factor, offset
-        c_vp, c_vp, c_vp, c_vp,  # d_loss, d_grad_scores, d_bounds, stream
-    ]
-    lib.cpb_colbert_neg_loss_fwd.restype = c_i
-    lib.cpb_colbert_neg_loss_fwd.argtypes = [
-        c_vp, c_vp, c_vp, c_i, c_i, c_i, c_i, c_i,  # d_scores, d_neg_scores, d_q, n_queries, nq_pad, n_docs, n_neg, inner_mode
-        c_f, c_i, c_i, c_f, c_f, c_f, c_i,  # temperature, normalize, filter, threshold, factor, in_batch_weight, offset
-        c_vp, c_vp, c_vp, c_vp,  # d_loss, d_grad_scores, d_grad_neg_scores, stream
-    ]
-    for name in ("cpb_colbert_loss_fwd", "cpb_colbert_neg_loss_fwd"):  # DRAFT: ..., dim, stream
-        fn = getattr(lib, name + "_dim")
-        fn.restype = c_i
-        fn.argtypes = getattr(lib, name).argtypes[:-1] + [c_i, c_vp]
-    lib.cpb_maxsim_bwd.restype = c_i
-    lib.cpb_maxsim_bwd.argtypes = [
-        c_vp, c_vp, c_vp,  # d_grad_scores, d_grad_out, d_argmax
-        c_vp, c_i, c_i,  # d_q, n_queries, nq_pad
-        c_vp, c_i64, c_vp, c_i,  # d_docs, doc_rows, d_doc_start, n_docs
-        c_vp, c_vp, c_vp,  # d_dq, d_dd, stream
-    ]
-    lib.cpb_maxsim_bwd_dim.restype = c_i
-    lib.cpb_maxsim_bwd_dim.argtypes = lib.cpb_maxsim_bwd.argtypes[:-1] + [c_i, c_vp]  # ..., dim, stream
-    lib.cpb_head_fwd.restype = c_i
+    lib.cpb_colbert_loss_launch.restype = ci
+    lib.cpb_colbert_loss_launch.argtypes = [ctypes.POINTER(LossDesc), c_vp, c_vp, ci, ci, ci, ci, c_vp]
+    lib.cpb_wait_flags.restype = ci
+    lib.cpb_wait_flags.argtypes = [c_vp, ci, c_u32, c_vp, c_vp]
+    lib.cpb_maxsim_bwd_launch.restype = ci
+    lib.cpb_maxsim_bwd_launch.argtypes = [ctypes.POINTER(MaxSimBwdArgs)]
+    lib.cpb_head_fwd.restype = ci
     lib.cpb_head_fwd.argtypes = [
-        c_vp, c_i64, c_i,  # d_hidden, n_tokens, hidden
-        c_vp, c_vp, c_i,  # d_weight, d_bias, dim
+        c_vp, c_i64, ci,  # d_hidden, n_tokens, hidden
+        c_vp, c_vp, ci,  # d_weight, d_bias, dim
         c_vp, c_vp,  # d_attention_mask, d_extra_mask
         c_vp, c_u32, c_vp,  # d_out, flags, stream
     ]
     _lib = lib
+    # experiment switch: COLPALI_B200_OPTS="pdl=0,boundary_mode=0" applies cpb_set_option pairs at load time
+    for pair in filter(None, os.environ.get("COLPALI_B200_OPTS", "").split(",")):
+        name, _, value = pair.partition("=")
+        if lib.cpb_set_option(name.strip().encode(), int(value)) != 0:
+            raise ColpaliB200Error(f"COLPALI_B200_OPTS: {lib.cpb_last_error().decode()}")
     return lib
 
 
@@ -141,7 +173,7 @@ def check(rc: int, what: str) -> None:
 
 
 def set_option(name: str, value: int) -> None:
-    """Tuning knob passthrough (cpb_set_option): 'cluster', 'qtiles_per_cta', 'debug_flags'."""
+    """Tuning knob passthrough (cpb_set_option), e.g. 'cluster', 'qtiles_per_cta', 'balanced', 'pdl'."""
     check(load().cpb_set_option(name.encode(), int(value)), f"cpb_set_option({name})")
 
 

@@ -1,6 +1,9 @@
 // extern "C" surface of libcolpali_b200.so (declared in include/colpali_b200.h).
 // Host-side only: argument validation, TMA tensor-map encoding, grid sizing, launches.
+#include <atomic>
+#include <cmath>
 #include <cstdarg>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -15,13 +18,14 @@
 
 namespace cpb {
 cudaError_t maxsim_launch(const CUtensorMap& tq, const CUtensorMap& td, const CUtensorMap& tt, const MaxSimParams& p,
-                          int r, bool argmax, int grid, cudaStream_t stream);
+                          const LossParams& lp, int r, int mode, int grid, cudaStream_t stream);
 int maxsim_max_clusters(int r, int cluster);
 int maxsim_tile_n();
 cudaError_t maxsim_kpipe_launch(const CUtensorMap& tq, const CUtensorMap& td, const CUtensorMap& tt, const MaxSimParams& p,
-                                int dim_panels, bool argmax, int grid, cudaStream_t stream);
+                                const LossParams& lp, int dim_panels, int mode, int grid, cudaStream_t stream);
 int maxsim_kpipe_max_clusters(int dim_panels, int cluster);
-cudaError_t wait_flags_launch(const uint32_t* flags, int n, uint32_t value, cudaStream_t stream);
+cudaError_t wait_flags_launch(const uint32_t* flags, const uint32_t* values, int n, uint32_t value, uint32_t timeout_ms,
+                              uint32_t* status, cudaStream_t stream);
 cudaError_t maxsim_reduce_segments(const float* partial, float* out, int64_t plane, int nseg, int round_ref,
                                    cudaStream_t stream);
 }  // namespace cpb
@@ -30,14 +34,17 @@ namespace {
 
 thread_local char g_err[512] = "";
 
-// tuning knobs (cpb_set_option); 0 = choose automatically
-int g_opt_cluster = 0;
-static int g_head_cluster = 0;  // DRAFT: 0 = auto (2 when there are at least two token tiles), 1, 2
-int g_opt_qtiles_per_cta = 0;
-unsigned g_opt_debug_flags = 0;
-int g_opt_mma_split = 6;
-int g_opt_dbg_delay = 0;
-int g_opt_balanced = 1;
+// tuning knobs (cpb_set_option): atomics, read once per launch; 0 = choose automatically
+std::atomic<int> g_opt_cluster{0};
+std::atomic<int> g_head_cluster{0};
+std::atomic<int> g_opt_qtiles_per_cta{0};
+std::atomic<unsigned> g_opt_debug_flags{0};
+std::atomic<int> g_opt_dbg_delay{0};
+std::atomic<int> g_opt_balanced{1};
+std::atomic<int> g_opt_pdl{1};
+std::atomic<int> g_opt_boundary_mode{1};
+std::atomic<int> g_opt_wait_timeout_ms{120000};
+std::mutex g_cache_mu;  // guards the device-property / occupancy caches below
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -52,6 +59,9 @@ int fail(int code, const char* fmt, ...) {
     cudaError_t _e = (expr);                                                                   \
     if (_e != cudaSuccess) return fail(CPB_E_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
   } while (0)
+
+// a struct member is present if the caller's struct (struct_size bytes) reaches past it
+#define CPB_HAS(args, T, member) ((args)->struct_size >= offsetof(T, member) + sizeof((args)->member))
 
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -97,6 +107,7 @@ int current_device_info(DevInfo* out) {
   int dev = 0;
   CPB_CUDA(cudaGetDevice(&dev));
   static DevInfo cache[64];
+  std::lock_guard<std::mutex> lock(g_cache_mu);
   if (dev >= 0 && dev < 64 && cache[dev].sm_count > 0) {
     *out = cache[dev];
     return CPB_OK;
@@ -105,6 +116,60 @@ int current_device_info(DevInfo* out) {
   CPB_CUDA(cudaDeviceGetAttribute(&out->major, cudaDevAttrComputeCapabilityMajor, dev));
   CPB_CUDA(cudaDeviceGetAttribute(&out->minor, cudaDevAttrComputeCapabilityMinor, dev));
   if (dev >= 0 && dev < 64) cache[dev] = *out;
+  return CPB_OK;
+}
+
+
+// co-resident cluster count of a kernel variant: a property of (device, variant, cluster size), queried once
+int max_clusters_cached(int dev, int variant, int cluster) {  // variant: 1 / 2 = R of the dim-128 kernel, 3..5 = K panels
+  static int cache[64][6][5];
+  std::lock_guard<std::mutex> lock(g_cache_mu);
+  int* slot = (dev >= 0 && dev < 64) ? &cache[dev][variant][cluster] : nullptr;
+  if (slot && *slot != 0) return *slot;
+  const int n = variant <= 2 ? cpb::maxsim_max_clusters(variant, cluster) : cpb::maxsim_kpipe_max_clusters(variant, cluster);
+  if (slot) *slot = n;
+  return n;
+}
+
+int fill_loss_params(cpb::LossParams* p, const cpb_loss_desc* d, const float* d_scores, const void* d_q, int n_queries,
+                     int nq_pad, int n_docs, int dim) {
+  if (!d || d->struct_size < offsetof(cpb_loss_desc, d_bounds) + sizeof(float*))
+    return fail(CPB_E_INVALID, "cpb_loss_desc is null or its struct_size is too small");
+  if (n_queries <= 0 || n_docs <= 0) return fail(CPB_E_INVALID, "n_queries=%d and n_docs=%d must be positive", n_queries, n_docs);
+  if (nq_pad <= 0 || (nq_pad % 32) != 0) return fail(CPB_E_INVALID, "nq_pad=%d must be a positive multiple of 32", nq_pad);
+  if (dim != 128 && dim != 192 && dim != 256 && dim != 320)
+    return fail(CPB_E_UNSUPPORTED, "embedding dim %d is not supported by this build (128, 192, 256, 320)", dim);
+  const int mode = d->mode;
+  if (mode != CPB_LOSS_CE && mode != CPB_LOSS_PAIRWISE && mode != CPB_LOSS_SIGMOID) return fail(CPB_E_INVALID, "unknown loss mode %d", mode);
+  if (mode == CPB_LOSS_SIGMOID && (n_docs != n_queries || d->offset != 0))
+    return fail(CPB_E_INVALID, "the sigmoid loss needs n_docs == n_queries and offset == 0 (got %d, %d, %d)", n_docs, n_queries, d->offset);
+  if (d->d_neg_scores && (d->n_neg <= 0 || mode == CPB_LOSS_SIGMOID || d->in_batch_term_weight < 0.f || d->in_batch_term_weight > 1.f))
+    return fail(CPB_E_INVALID, "bad explicit-negative arguments (n_neg=%d, mode=%d, weight=%g)", d->n_neg, mode, static_cast<double>(d->in_batch_term_weight));
+  if (d->offset < 0 || d->offset + n_queries > n_docs)
+    return fail(CPB_E_INVALID, "positive index out of range: offset=%d + n_queries=%d > n_docs=%d", d->offset, n_queries, n_docs);
+  if (!(d->temperature > 0.f)) return fail(CPB_E_INVALID, "temperature must be positive");
+  if (!d_scores || !d_q || !d->d_loss) return fail(CPB_E_INVALID, "null device pointer");
+  *p = cpb::LossParams{};
+  p->scores = d_scores;
+  p->q = static_cast<const __nv_bfloat16*>(d_q);
+  p->q_dim = dim;
+  p->loss = d->d_loss;
+  p->grad = d->d_grad_scores;
+  p->bounds = d->d_bounds;
+  p->B = n_queries;
+  p->C = n_docs;
+  p->nq_pad = nq_pad;
+  p->offset = d->offset;
+  p->mode = mode;
+  p->normalize = d->normalize_scores;
+  p->filter = d->pos_aware_negative_filtering;
+  p->temperature = d->temperature;
+  p->filter_threshold = d->filter_threshold;
+  p->filter_factor = d->filter_factor;
+  p->neg_scores = d->d_neg_scores;
+  p->grad_neg = d->d_grad_neg_scores;
+  p->n_neg = d->n_neg;
+  p->in_batch_weight = d->d_neg_scores ? d->in_batch_term_weight : 1.f;
   return CPB_OK;
 }
 
@@ -141,14 +206,20 @@ int cpb_set_option(const char* name, int value) {
   } else if (!strcmp(name, "qtiles_per_cta")) {
     if (value < 0 || value > 2) return fail(CPB_E_INVALID, "qtiles_per_cta must be 0, 1 or 2");
     g_opt_qtiles_per_cta = value;
-  } else if (!strcmp(name, "mma_split")) {
-    if (value < 5 || value > 8) return fail(CPB_E_INVALID, "mma_split must be 5..8");
-    g_opt_mma_split = value;
+  } else if (!strcmp(name, "balanced")) {
+    g_opt_balanced = value != 0;
+  } else if (!strcmp(name, "pdl")) {
+    if (value < 0 || value > 1) return fail(CPB_E_INVALID, "pdl must be 0 or 1");
+    g_opt_pdl = value;
+  } else if (!strcmp(name, "boundary_mode")) {
+    if (value < 0 || value > 1) return fail(CPB_E_INVALID, "boundary_mode must be 0 or 1");
+    g_opt_boundary_mode = value;
   } else if (!strcmp(name, "head_cluster")) {
     if (value < 0 || value > 2) return fail(CPB_E_INVALID, "head_cluster must be 0, 1 or 2");
     g_head_cluster = value;
-  } else if (!strcmp(name, "balanced")) {
-    g_opt_balanced = value != 0;
+  } else if (!strcmp(name, "wait_timeout_ms")) {
+    if (value <= 0) return fail(CPB_E_INVALID, "wait_timeout_ms must be positive");
+    g_opt_wait_timeout_ms = value;
   } else if (!strcmp(name, "debug_delay")) {
     g_opt_dbg_delay = value;
   } else if (!strcmp(name, "debug_flags")) {
@@ -164,218 +235,6 @@ int64_t cpb_maxsim_workspace_bytes(int n_queries, int nq_pad, int n_docs) {
   return static_cast<int64_t>(nq_pad / 32) * n_queries * n_docs * 4;
 }
 
-static int maxsim_fwd_impl(const void* d_q, int n_queries, int nq_pad, const void* d_docs, int64_t doc_rows,
-                           const int32_t* d_doc_start, const int32_t* d_doc_len, const float* d_doc_floor, int n_docs,
-                           float* d_scores, int32_t* d_argmax, float* d_workspace, uint32_t flags, int uniform_len,
-                           int max_doc_len, void* d_split_ws, int64_t split_ws_bytes, uint32_t epoch,
-                           const uint64_t* d_peer_ptrs, int n_peers, int my_rank, uint32_t* d_done_counter,
-                           int64_t flag_word_offset, uint32_t signal_value, void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (n_queries <= 0 || n_docs <= 0) return fail(CPB_E_INVALID, "n_queries=%d and n_docs=%d must be positive", n_queries, n_docs);
-  if (nq_pad <= 0 || (nq_pad % 32) != 0) return fail(CPB_E_INVALID, "nq_pad=%d must be a positive multiple of 32", nq_pad);
-  if (reinterpret_cast<uintptr_t>(d_q) & 15u) return fail(CPB_E_INVALID, "d_q is not 16-byte aligned");
-  if (!d_q || !d_docs || !d_doc_start || !d_doc_len || (!d_scores && !d_peer_ptrs)) return fail(CPB_E_INVALID, "null device pointer");
-  if (doc_rows <= 0 || doc_rows > 0x7fffffffLL) return fail(CPB_E_INVALID, "doc_rows=%lld out of range (1..2^31-1)", static_cast<long long>(doc_rows));
-  const int nseg = nq_pad / 32;
-  if (nseg > 1 && !d_workspace) return fail(CPB_E_INVALID, "nq_pad=%d needs a workspace (cpb_maxsim_workspace_bytes)", nq_pad);
-  const int64_t q_rows64 = static_cast<int64_t>(n_queries) * nq_pad;
-  if (q_rows64 > 0x7fffffffLL) return fail(CPB_E_INVALID, "too many query rows");
-
-  DevInfo di;
-  int rc = current_device_info(&di);
-  if (rc != CPB_OK) return rc;
-  if (di.major != 10) return fail(CPB_E_DEVICE, "device is sm_%d%d; this library needs sm_100 (B200)", di.major, di.minor);
-
-  cpb::MaxSimParams p{};
-  p.q = d_q;
-  p.doc_start = d_doc_start;
-  p.doc_len = d_doc_len;
-  p.doc_floor = d_doc_floor;
-  p.argmax = d_argmax;
-  p.plane_stride = static_cast<int64_t>(n_queries) * n_docs;
-  p.n_queries = n_queries;
-  p.nq_pad = nq_pad;
-  p.q_rows = static_cast<int>(q_rows64);
-  p.n_docs = n_docs;
-  p.num_qtiles = (p.q_rows + 127) / 128;
-  p.flags = flags;
-  p.scores = (nseg == 1) ? d_scores : d_workspace;
-  if (d_peer_ptrs) {
-    if (nseg != 1) return fail(CPB_E_UNSUPPORTED, "the fused all-gather needs queries of at most 32 tokens (nq_pad == 32)");
-    if (n_peers < 1 || n_peers > 64 || my_rank < 0 || my_rank >= n_peers) return fail(CPB_E_INVALID, "bad peer arguments (%d peers, rank %d)", n_peers, my_rank);
-    p.peer_scores = d_peer_ptrs;
-    p.n_peers = n_peers;
-    p.peer_slab_offset = static_cast<int64_t>(my_rank) * n_queries * n_docs;
-    p.done_counter = d_done_counter;
-    p.peer_flag_offset = flag_word_offset;
-    p.signal_value = signal_value;
-    p.my_rank = my_rank;
-  }
-
-  // Two resident query tiles per CTA halve the L2->SMEM traffic per flop; a single tile only
-  // when there is just one.
-  int R = (p.num_qtiles >= 2) ? 2 : 1;
-  if (g_opt_qtiles_per_cta == 1 || g_opt_qtiles_per_cta == 2) R = g_opt_qtiles_per_cta;
-  p.q_groups = (p.num_qtiles + R - 1) / R;
-  // CTAs of a cluster hold different query-tile groups and share every document tile through TMA
-  // multicast.  Pairs tile the 148 SMs exactly; clusters of 4 strand SMs in GPCs whose SM count is
-  // not a multiple of 4, so they are opt-in.
-  int cluster = (p.q_groups >= 2) ? 2 : 1;
-  if (g_opt_cluster == 1 || g_opt_cluster == 2 || g_opt_cluster == 4) cluster = g_opt_cluster;
-  // co-resident cluster count is a property of (device, R, cluster): query the driver once
-  static int occ_cache[3][5] = {};
-  auto max_clusters_cached = [&](int r, int c) {
-    if (occ_cache[r][c] == 0) occ_cache[r][c] = cpb::maxsim_max_clusters(r, c);
-    return occ_cache[r][c];
-  };
-  int max_clusters = max_clusters_cached(R, cluster);
-  if (max_clusters <= 0) {
-    if (cluster == 1) return fail(CPB_E_CUDA, "kernel cannot be resident on this device (shared memory?)");
-    cluster = 1;
-    max_clusters = max_clusters_cached(R, 1);
-    if (max_clusters <= 0) return fail(CPB_E_CUDA, "kernel cannot be resident on this device (shared memory?)");
-  }
-  p.cluster = cluster;
-  p.group_sets = (p.q_groups + cluster - 1) / cluster;
-  int parts = max_clusters / p.group_sets;
-  if (parts < 1) parts = 1;
-  if (parts > n_docs) parts = n_docs;
-  // tile-balanced partitions (a document may be cut between two partitions): contiguous banks only, every
-  // partition at least as long as the longest document, caller-provided exchange workspace
-  const int64_t tiles = (doc_rows + 255) / 256;
-  if (g_opt_balanced && (flags & CPB_FLAG_CONTIGUOUS) && d_split_ws && max_doc_len > 0 && doc_rows <= 0x7fffffffLL) {
-    int bparts = parts;
-    if (bparts > tiles) bparts = static_cast<int>(tiles);
-    const int64_t min_rows = 256 * (tiles / (bparts > 0 ? bparts : 1));
-    const int64_t need = static_cast<int64_t>(p.group_sets) * cluster * bparts * R * (128 * 8 + 16);
-    if (bparts > 1 && min_rows >= max_doc_len && need <= split_ws_bytes) {
-      parts = bparts;
-      p.balanced = 1;
-      p.bank_rows = static_cast<int>(doc_rows);
-      p.uniform_len = uniform_len;
-      const int64_t slots = static_cast<int64_t>(p.group_sets) * cluster * bparts * R;
-      p.split_max = static_cast<float*>(d_split_ws);
-      p.split_idx = reinterpret_cast<int32_t*>(p.split_max + slots * 128);
-      p.split_flag = reinterpret_cast<uint32_t*>(p.split_idx + slots * 128);
-      p.epoch = epoch;
-    }
-  }
-  p.doc_parts = parts;
-  p.flags = flags | g_opt_debug_flags;
-  p.mma_split = g_opt_mma_split;
-  p.dbg_delay = g_opt_dbg_delay;
-  const int grid = p.group_sets * p.doc_parts * cluster;
-
-  CUtensorMap tq, td, tt;
-  rc = make_bf16_rowmajor_map(&tq, d_q, q_rows64, 128, 128);
-  if (rc != CPB_OK) return rc;
-  rc = make_bf16_rowmajor_map(&td, d_docs, doc_rows, 128, cpb::maxsim_tile_n() / cluster);
-  if (rc != CPB_OK) return rc;
-  rc = make_bf16_rowmajor_map(&tt, d_docs, doc_rows, 128, 32);
-  if (rc != CPB_OK) return rc;
-
-  CPB_CUDA(cpb::maxsim_launch(tq, td, tt, p, R, d_argmax != nullptr, grid, stream));
-  if (nseg > 1)
-    CPB_CUDA(cpb::maxsim_reduce_segments(d_workspace, d_scores, p.plane_stride, nseg,
-                                         (flags & CPB_FLAG_ROUND_BF16) ? 1 : 0, stream));
-  return CPB_OK;
-}
-
-static int loss_fwd_impl(const float* d_scores, const void* d_q, int n_queries, int nq_pad, int n_docs, int mode,
-                         float temperature, int normalize_scores, int pos_aware_negative_filtering,
-                         float filter_threshold, float filter_factor, int offset, const float* d_neg_scores, int n_neg,
-                         float in_batch_weight, float* d_loss, float* d_grad_scores, float* d_grad_neg,
-                         float* d_bounds, int q_dim, void* stream_) {
-  if (q_dim != 128 && q_dim != 192 && q_dim != 256 && q_dim != 320)
-    return fail(CPB_E_UNSUPPORTED, "embedding dim %d is not supported by this build (128, 192, 256, 320)", q_dim);
-  if (n_queries <= 0 || n_docs <= 0) return fail(CPB_E_INVALID, "n_queries=%d and n_docs=%d must be positive", n_queries, n_docs);
-  if (nq_pad <= 0 || (nq_pad % 32) != 0) return fail(CPB_E_INVALID, "nq_pad=%d must be a positive multiple of 32", nq_pad);
-  if (mode != CPB_LOSS_CE && mode != CPB_LOSS_PAIRWISE && mode != CPB_LOSS_SIGMOID) return fail(CPB_E_INVALID, "unknown loss mode %d", mode);
-  if (mode == CPB_LOSS_SIGMOID && (n_docs != n_queries || offset != 0))
-    return fail(CPB_E_INVALID, "the sigmoid loss needs n_docs == n_queries and offset == 0 (got %d, %d, %d)", n_docs, n_queries, offset);
-  if (d_neg_scores && (n_neg <= 0 || mode == CPB_LOSS_SIGMOID || in_batch_weight < 0.f || in_batch_weight > 1.f))
-    return fail(CPB_E_INVALID, "bad explicit-negative arguments (n_neg=%d, mode=%d, weight=%g)", n_neg, mode, static_cast<double>(in_batch_weight));
-  if (offset < 0 || offset + n_queries > n_docs)
-    return fail(CPB_E_INVALID, "positive index out of range: offset=%d + n_queries=%d > n_docs=%d", offset, n_queries, n_docs);
-  if (!(temperature > 0.f)) return fail(CPB_E_INVALID, "temperature must be positive");
-  if (!d_scores || !d_q || !d_loss) return fail(CPB_E_INVALID, "null device pointer");
-  cpb::LossParams p{};
-  p.scores = d_scores;
-  p.q = static_cast<const __nv_bfloat16*>(d_q);
-  p.q_dim = q_dim;
-  p.loss = d_loss;
-  p.grad = d_grad_scores;
-  p.bounds = d_bounds;
-  p.B = n_queries;
-  p.C = n_docs;
-  p.nq_pad = nq_pad;
-  p.offset = offset;
-  p.mode = mode;
-  p.normalize = normalize_scores;
-  p.filter = pos_aware_negative_filtering;
-  p.temperature = temperature;
-  p.filter_threshold = filter_threshold;
-  p.filter_factor = filter_factor;
-  p.neg_scores = d_neg_scores;
-  p.grad_neg = d_grad_neg;
-  p.n_neg = n_neg;
-  p.in_batch_weight = in_batch_weight;
-  CPB_CUDA(cpb::colbert_loss_launch(p, static_cast<cudaStream_t>(stream_)));
-  return CPB_OK;
-}
-
-int cpb_colbert_loss_fwd(const float* d_scores, const void* d_q, int n_queries, int nq_pad, int n_docs, int mode,
-                         float temperature, int normalize_scores, int pos_aware_negative_filtering,
-                         float filter_threshold, float filter_factor, int offset, float* d_loss, float* d_grad_scores,
-                         float* d_bounds, void* stream_) {
-  return loss_fwd_impl(d_scores, d_q, n_queries, nq_pad, n_docs, mode, temperature, normalize_scores,
-                       pos_aware_negative_filtering, filter_threshold, filter_factor, offset, nullptr, 0, 1.f, d_loss,
-                       d_grad_scores, nullptr, d_bounds, 128, stream_);
-}
-
-int cpb_colbert_loss_fwd_dim(const float* d_scores, const void* d_q, int n_queries, int nq_pad, int n_docs, int mode,
-                             float temperature, int normalize_scores, int pos_aware_negative_filtering,
-                             float filter_threshold, float filter_factor, int offset, float* d_loss,
-                             float* d_grad_scores, float* d_bounds, int dim, void* stream_) {
-  return loss_fwd_impl(d_scores, d_q, n_queries, nq_pad, n_docs, mode, temperature, normalize_scores,
-                       pos_aware_negative_filtering, filter_threshold, filter_factor, offset, nullptr, 0, 1.f, d_loss,
-                       d_grad_scores, nullptr, d_bounds, dim, stream_);
-}
-
-int cpb_maxsim_fwd(const void* d_q, int n_queries, int nq_pad, const void* d_docs, int64_t doc_rows,
-                   const int32_t* d_doc_start, const int32_t* d_doc_len, const float* d_doc_floor, int n_docs,
-                   float* d_scores, int32_t* d_argmax, float* d_workspace, uint32_t flags, void* stream_) {
-  return maxsim_fwd_impl(d_q, n_queries, nq_pad, d_docs, doc_rows, d_doc_start, d_doc_len, d_doc_floor, n_docs, d_scores,
-                         d_argmax, d_workspace, flags, 0, 0, nullptr, 0, 0, nullptr, 0, 0, nullptr, 0, 0, stream_);
-}
-
-int cpb_maxsim_fwd_balanced(const void* d_q, int n_queries, int nq_pad, const void* d_docs, int64_t doc_rows,
-                            const int32_t* d_doc_start, const int32_t* d_doc_len, const float* d_doc_floor, int n_docs,
-                            float* d_scores, int32_t* d_argmax, float* d_workspace, uint32_t flags, int uniform_len,
-                            int max_doc_len, void* d_split_ws, int64_t split_ws_bytes, uint32_t epoch, void* stream_) {
-  if (epoch == 0) return fail(CPB_E_INVALID, "epoch must be non-zero (a zero-initialised workspace means 'nothing published')");
-  return maxsim_fwd_impl(d_q, n_queries, nq_pad, d_docs, doc_rows, d_doc_start, d_doc_len, d_doc_floor, n_docs, d_scores,
-                         d_argmax, d_workspace, flags, uniform_len, max_doc_len, d_split_ws, split_ws_bytes, epoch, nullptr,
-                         0, 0, nullptr, 0, 0, stream_);
-}
-
-int cpb_maxsim_fwd_allgather(const void* d_q, int n_queries, int nq_pad, const void* d_docs, int64_t doc_rows,
-                             const int32_t* d_doc_start, const int32_t* d_doc_len, const float* d_doc_floor, int n_docs,
-                             const uint64_t* d_peer_slabs, int n_peers, int my_rank, uint32_t flags, int uniform_len,
-                             int max_doc_len, void* d_split_ws, int64_t split_ws_bytes, uint32_t epoch,
-                             uint32_t* d_done_counter, int64_t flag_word_offset, uint32_t signal_value, void* stream_) {
-  if (!d_peer_slabs) return fail(CPB_E_INVALID, "null peer pointer array");
-  return maxsim_fwd_impl(d_q, n_queries, nq_pad, d_docs, doc_rows, d_doc_start, d_doc_len, d_doc_floor, n_docs, nullptr,
-                         nullptr, nullptr, flags, uniform_len, max_doc_len, d_split_ws, d_split_ws ? split_ws_bytes : 0,
-                         epoch, d_peer_slabs, n_peers, my_rank, d_done_counter, flag_word_offset, signal_value, stream_);
-}
-
-int cpb_wait_flags(const uint32_t* d_flags, int n, uint32_t value, void* stream_) {
-  if (!d_flags || n <= 0 || n > 64) return fail(CPB_E_INVALID, "bad flag array");
-  CPB_CUDA(cpb::wait_flags_launch(d_flags, n, value, static_cast<cudaStream_t>(stream_)));
-  return CPB_OK;
-}
-
 int64_t cpb_maxsim_split_workspace_bytes(int n_queries, int nq_pad) {
   // worst case: every SM is a partition of some query-tile group
   const int64_t qtiles = (static_cast<int64_t>(n_queries) * nq_pad + 127) / 128;
@@ -383,62 +242,270 @@ int64_t cpb_maxsim_split_workspace_bytes(int n_queries, int nq_pad) {
   return groups * 160 * 2 * (128 * 8 + 16);
 }
 
-int cpb_colbert_neg_loss_fwd(const float* d_scores, const float* d_neg_scores, const void* d_q, int n_queries,
-                             int nq_pad, int n_docs, int n_neg, int inner_mode, float temperature,
-                             int normalize_scores, int pos_aware_negative_filtering, float filter_threshold,
-                             float filter_factor, float in_batch_term_weight, int offset, float* d_loss,
-                             float* d_grad_scores, float* d_grad_neg_scores, void* stream_) {
-  if (!d_neg_scores) return fail(CPB_E_INVALID, "null device pointer");
-  return loss_fwd_impl(d_scores, d_q, n_queries, nq_pad, n_docs, inner_mode, temperature, normalize_scores,
-                       pos_aware_negative_filtering, filter_threshold, filter_factor, offset, d_neg_scores, n_neg,
-                       in_batch_term_weight, d_loss, d_grad_scores, d_grad_neg_scores, nullptr, 128, stream_);
-}
+int cpb_maxsim_launch(cpb_maxsim_args* a) {
+  if (!a || a->struct_size < offsetof(cpb_maxsim_args, d_workspace) + sizeof(float*))
+    return fail(CPB_E_INVALID, "cpb_maxsim_args is null or its struct_size is too small");
+  // members past d_workspace are optional (absent in a shorter struct = zero)
+  void* d_split_ws = CPB_HAS(a, cpb_maxsim_args, d_split_ws) ? a->d_split_ws : nullptr;
+  const int64_t split_ws_bytes = CPB_HAS(a, cpb_maxsim_args, split_ws_bytes) ? a->split_ws_bytes : 0;
+  const uint32_t epoch = CPB_HAS(a, cpb_maxsim_args, epoch) ? a->epoch : 0;
+  const float smooth_tau = CPB_HAS(a, cpb_maxsim_args, smooth_tau) ? a->smooth_tau : 0.f;
+  const uint64_t* d_peer_bases = CPB_HAS(a, cpb_maxsim_args, d_peer_bases) ? a->d_peer_bases : nullptr;
+  const uint64_t mc_base = CPB_HAS(a, cpb_maxsim_args, mc_base) ? a->mc_base : 0;
+  const int n_peers = CPB_HAS(a, cpb_maxsim_args, n_peers) ? a->n_peers : 0;
+  const int64_t slab_word_offset = CPB_HAS(a, cpb_maxsim_args, slab_word_offset) ? a->slab_word_offset : 0;
+  const int64_t flag_word_offset = CPB_HAS(a, cpb_maxsim_args, flag_word_offset) ? a->flag_word_offset : 0;
+  const uint32_t* d_wait_flags = CPB_HAS(a, cpb_maxsim_args, d_wait_flags) ? a->d_wait_flags : nullptr;
+  const int n_wait = CPB_HAS(a, cpb_maxsim_args, n_wait) ? a->n_wait : 0;
+  const uint32_t wait_value = CPB_HAS(a, cpb_maxsim_args, wait_value) ? a->wait_value : 0;
+  const cpb_loss_desc* loss = CPB_HAS(a, cpb_maxsim_args, loss) ? a->loss : nullptr;
+  uint32_t* d_done_counter = CPB_HAS(a, cpb_maxsim_args, d_done_counter) ? a->d_done_counter : nullptr;
 
-int cpb_colbert_neg_loss_fwd_dim(const float* d_scores, const float* d_neg_scores, const void* d_q, int n_queries,
-                                 int nq_pad, int n_docs, int n_neg, int inner_mode, float temperature,
-                                 int normalize_scores, int pos_aware_negative_filtering, float filter_threshold,
-                                 float filter_factor, float in_batch_term_weight, int offset, float* d_loss,
-                                 float* d_grad_scores, float* d_grad_neg_scores, int dim, void* stream_) {
-  if (!d_neg_scores) return fail(CPB_E_INVALID, "null device pointer");
-  return loss_fwd_impl(d_scores, d_q, n_queries, nq_pad, n_docs, inner_mode, temperature, normalize_scores,
-                       pos_aware_negative_filtering, filter_threshold, filter_factor, offset, d_neg_scores, n_neg,
-                       in_batch_term_weight, d_loss, d_grad_scores, d_grad_neg_scores, nullptr, dim, stream_);
-}
-
-int cpb_maxsim_bwd(const float* d_grad_scores, const float* d_grad_out, const int32_t* d_argmax, const void* d_q,
-                   int n_queries, int nq_pad, const void* d_docs, int64_t doc_rows, const int32_t* d_doc_start,
-                   int n_docs, float* d_dq, float* d_dd, void* stream_) {
-  return cpb_maxsim_bwd_dim(d_grad_scores, d_grad_out, d_argmax, d_q, n_queries, nq_pad, d_docs, doc_rows, d_doc_start,
-                            n_docs, d_dq, d_dd, 128, stream_);
-}
-
-int cpb_maxsim_bwd_dim(const float* d_grad_scores, const float* d_grad_out, const int32_t* d_argmax, const void* d_q,
-                       int n_queries, int nq_pad, const void* d_docs, int64_t doc_rows, const int32_t* d_doc_start,
-                       int n_docs, float* d_dq, float* d_dd, int dim, void* stream_) {
-  if (dim != 128 && dim != 192 && dim != 256 && dim != 320)
-    return fail(CPB_E_UNSUPPORTED, "embedding dim %d is not supported by this build (128, 192, 256, 320)", dim);
+  cudaStream_t stream = static_cast<cudaStream_t>(a->stream);
+  const int n_queries = a->n_queries, nq_pad = a->nq_pad, n_docs = a->n_docs, dim = a->dim;
+  const uint32_t flags = a->flags;
   if (n_queries <= 0 || n_docs <= 0) return fail(CPB_E_INVALID, "n_queries=%d and n_docs=%d must be positive", n_queries, n_docs);
   if (nq_pad <= 0 || (nq_pad % 32) != 0) return fail(CPB_E_INVALID, "nq_pad=%d must be a positive multiple of 32", nq_pad);
-  if (!d_grad_scores || !d_argmax || !d_q || !d_docs || !d_doc_start) return fail(CPB_E_INVALID, "null device pointer");
-  if (doc_rows <= 0) return fail(CPB_E_INVALID, "doc_rows must be positive");
-  if ((reinterpret_cast<uintptr_t>(d_dq) | reinterpret_cast<uintptr_t>(d_dd) | reinterpret_cast<uintptr_t>(d_q) |
-       reinterpret_cast<uintptr_t>(d_docs)) & 15u)
-    return fail(CPB_E_INVALID, "tensor pointers must be 16-byte aligned");
-  cpb::BwdParams p{};
-  p.g = d_grad_scores;
-  p.grad_out = d_grad_out;
-  p.argmax = d_argmax;
-  p.q = static_cast<const __nv_bfloat16*>(d_q);
-  p.docs = static_cast<const __nv_bfloat16*>(d_docs);
-  p.doc_start = d_doc_start;
-  p.dq = d_dq;
-  p.dd = d_dd;
-  p.B = n_queries;
-  p.C = n_docs;
+  if (dim != 128 && dim != 192 && dim != 256 && dim != 320)
+    return fail(CPB_E_UNSUPPORTED, "embedding dim %d is not supported by this build (128, 192, 256, 320)", dim);
+  if (reinterpret_cast<uintptr_t>(a->d_q) & 15u) return fail(CPB_E_INVALID, "d_q is not 16-byte aligned");
+  if (!a->d_q || !a->d_docs || !a->d_doc_start || !a->d_doc_len || (!a->d_scores && !d_peer_bases)) return fail(CPB_E_INVALID, "null device pointer");
+  if (a->doc_rows <= 0 || a->doc_rows > 0x7fffffffLL) return fail(CPB_E_INVALID, "doc_rows=%lld out of range (1..2^31-1)", static_cast<long long>(a->doc_rows));
+  const int nseg = nq_pad / 32;
+  if (nseg > 1 && !a->d_workspace) return fail(CPB_E_INVALID, "nq_pad=%d needs a workspace (cpb_maxsim_workspace_bytes)", nq_pad);
+  const int64_t q_rows64 = static_cast<int64_t>(n_queries) * nq_pad;
+  if (q_rows64 > 0x7fffffffLL) return fail(CPB_E_INVALID, "too many query rows");
+  const bool smooth = smooth_tau > 0.f;
+  if (smooth_tau < 0.f || std::isnan(smooth_tau)) return fail(CPB_E_INVALID, "smooth_tau must be >= 0");
+  if (smooth && (a->nq_real <= 0 || a->nq_real > nq_pad)) return fail(CPB_E_INVALID, "smooth max needs 0 < nq_real <= nq_pad (got %d, %d)", a->nq_real, nq_pad);
+  if (smooth && (a->d_argmax || (flags & CPB_FLAG_ROUND_BF16) || d_peer_bases))
+    return fail(CPB_E_UNSUPPORTED, "smooth max excludes argmax, bf16 rounding and the fused all-gather");
+  if (a->d_lse && !smooth) return fail(CPB_E_INVALID, "d_lse is an output of the smooth-max mode (smooth_tau > 0)");
+
+  DevInfo di;
+  int rc = current_device_info(&di);
+  if (rc != CPB_OK) return rc;
+  if (di.major != 10) return fail(CPB_E_DEVICE, "device is sm_%d%d; this library needs sm_100 (B200)", di.major, di.minor);
+  int dev = 0;
+  CPB_CUDA(cudaGetDevice(&dev));
+
+  cpb::MaxSimParams p{};
+  p.q = a->d_q;
+  p.doc_start = a->d_doc_start;
+  p.doc_len = a->d_doc_len;
+  p.doc_floor = smooth ? nullptr : a->d_doc_floor;
+  p.argmax = a->d_argmax;
+  p.lse = a->d_lse;
+  p.plane_stride = static_cast<int64_t>(n_queries) * n_docs;
+  p.n_queries = n_queries;
   p.nq_pad = nq_pad;
-  p.q_rows = n_queries * nq_pad;
+  p.nq_real = smooth ? a->nq_real : nq_pad;
+  p.q_rows = static_cast<int>(q_rows64);
+  p.n_docs = n_docs;
+  p.num_qtiles = (p.q_rows + 127) / 128;
+  p.scores = (nseg == 1) ? a->d_scores : a->d_workspace;
+  if (smooth) {
+    p.smooth_c = 1.4426950408889634f / smooth_tau;
+    p.smooth_out = smooth_tau * 0.6931471805599453f;
+  }
+  if (d_peer_bases) {
+    if (nseg != 1) return fail(CPB_E_UNSUPPORTED, "the fused all-gather needs queries of at most 32 tokens (nq_pad == 32)");
+    if (n_peers < 1 || n_peers > 64) return fail(CPB_E_INVALID, "bad peer count %d", n_peers);
+    if (slab_word_offset < 0 || flag_word_offset < 0) return fail(CPB_E_INVALID, "negative symmetric-buffer offset");
+    p.peer_scores = d_peer_bases;
+    p.mc_base = mc_base;
+    p.n_peers = n_peers;
+    p.peer_slab_offset = slab_word_offset;
+    p.peer_flag_offset = flag_word_offset;
+    if (d_wait_flags) {
+      if (n_wait < 1 || n_wait > 64) return fail(CPB_E_INVALID, "bad n_wait %d", n_wait);
+      p.wait_flags = d_wait_flags;
+      p.n_wait = n_wait;
+      p.wait_value = wait_value;
+      p.wait_timeout_ms = static_cast<uint32_t>(g_opt_wait_timeout_ms.load());
+    }
+  }
+  cpb::LossParams lp{};
+  if (loss) {
+    if (nseg != 1 || d_peer_bases || !d_done_counter || !a->d_scores || (flags & CPB_FLAG_INDEPENDENT))
+      return fail(CPB_E_UNSUPPORTED, "the fused loss needs nq_pad == 32, d_scores, d_done_counter, no fused all-gather and no CPB_FLAG_INDEPENDENT");
+    rc = fill_loss_params(&lp, loss, a->d_scores, a->d_q, n_queries, nq_pad, n_docs, dim);
+    if (rc != CPB_OK) return rc;
+    p.done_counter = d_done_counter;
+  }
+  const int mode = smooth ? 2 : (a->d_argmax ? 1 : 0);
+  p.pdl = g_opt_pdl.load() ? ((flags & CPB_FLAG_INDEPENDENT) ? 2 : 1) : 0;
+  p.boundary_mode = g_opt_boundary_mode.load();
+  p.flags = (flags & 0xffffu) | g_opt_debug_flags.load();
+  p.dbg_delay = g_opt_dbg_delay.load();
+
+  const int opt_cluster = g_opt_cluster.load(), opt_r = g_opt_qtiles_per_cta.load();
+  int grid = 0;
+  CUtensorMap tq, td, tt;
+  if (dim == 128) {
+    // Two resident query tiles per CTA halve the L2->SMEM traffic per flop; a single tile only when there is just one.
+    int R = (p.num_qtiles >= 2) ? 2 : 1;
+    if (opt_r == 1 || opt_r == 2) R = opt_r;
+    p.q_groups = (p.num_qtiles + R - 1) / R;
+    // CTAs of a cluster hold different query-tile groups and share every document tile through TMA multicast.  Pairs
+    // tile the 148 SMs exactly; clusters of 4 strand SMs in GPCs whose SM count is not a multiple of 4 (opt-in).
+    int cluster = (p.q_groups >= 2) ? 2 : 1;
+    if (opt_cluster == 1 || opt_cluster == 2 || opt_cluster == 4) cluster = opt_cluster;
+    int max_clusters = max_clusters_cached(dev, R, cluster);
+    if (max_clusters <= 0) {
+      if (cluster == 1) return fail(CPB_E_CUDA, "kernel cannot be resident on this device (shared memory?)");
+      cluster = 1;
+      max_clusters = max_clusters_cached(dev, R, 1);
+      if (max_clusters <= 0) return fail(CPB_E_CUDA, "kernel cannot be resident on this device (shared memory?)");
+    }
+    p.cluster = cluster;
+    p.group_sets = (p.q_groups + cluster - 1) / cluster;
+    int parts = max_clusters / p.group_sets;
+    if (parts < 1) parts = 1;
+    if (parts > n_docs) parts = n_docs;
+    // tile-balanced partitions (a document may be cut between two partitions): contiguous banks only, every partition
+    // at least as long as the longest document, caller-provided exchange workspace, hard max only
+    const int64_t tiles = (a->doc_rows + 255) / 256;
+    if (g_opt_balanced.load() && !smooth && (flags & CPB_FLAG_CONTIGUOUS) && d_split_ws && a->max_doc_len > 0) {
+      if (epoch == 0) return fail(CPB_E_INVALID, "epoch must be non-zero (a zero-initialised workspace means 'nothing published')");
+      int bparts = parts;
+      if (bparts > tiles) bparts = static_cast<int>(tiles);
+      const int64_t min_rows = 256 * (tiles / (bparts > 0 ? bparts : 1));
+      const int64_t slots = static_cast<int64_t>(p.group_sets) * cluster * bparts * R;
+      const int64_t need = slots * (128 * 8 + 16);
+      // launches flagged independent may overlap their predecessors: four generations of slots, picked by the epoch
+      const int gens = (p.pdl == 2) ? 4 : 1;
+      if (bparts > 1 && min_rows >= a->max_doc_len && need * gens <= split_ws_bytes) {
+        parts = bparts;
+        p.balanced = 1;
+        p.bank_rows = static_cast<int>(a->doc_rows);
+        p.uniform_len = a->uniform_len;
+        char* base = static_cast<char*>(d_split_ws) + (gens > 1 ? (epoch & 3u) * need : 0);
+        p.split_max = reinterpret_cast<float*>(base);
+        p.split_idx = reinterpret_cast<int32_t*>(p.split_max + slots * 128);
+        p.split_flag = reinterpret_cast<uint32_t*>(p.split_idx + slots * 128);
+        p.epoch = epoch;
+      }
+    }
+    p.doc_parts = parts;
+    grid = p.group_sets * p.doc_parts * cluster;
+    rc = make_bf16_rowmajor_map(&tq, a->d_q, q_rows64, 128, 128);
+    if (rc != CPB_OK) return rc;
+    rc = make_bf16_rowmajor_map(&td, a->d_docs, a->doc_rows, 128, cpb::maxsim_tile_n() / cluster);
+    if (rc != CPB_OK) return rc;
+    rc = make_bf16_rowmajor_map(&tt, a->d_docs, a->doc_rows, 128, 32);
+    if (rc != CPB_OK) return rc;
+    CPB_CUDA(cpb::maxsim_launch(tq, td, tt, p, lp, R, mode, grid, stream));
+  } else {
+    // K-pipelined kernel: one query tile per CTA, whole-document partitions
+    const int panels = dim / 64;
+    p.q_groups = p.num_qtiles;
+    int cluster = (p.q_groups >= 2) ? 2 : 1;
+    if (opt_cluster == 1 || opt_cluster == 2) cluster = opt_cluster;
+    int max_clusters = max_clusters_cached(dev, panels, cluster);
+    if (max_clusters <= 0) return fail(CPB_E_CUDA, "K-pipelined kernel cannot be resident on this device");
+    p.cluster = cluster;
+    p.group_sets = (p.q_groups + cluster - 1) / cluster;
+    int parts = max_clusters / p.group_sets;
+    if (parts < 1) parts = 1;
+    if (parts > n_docs) parts = n_docs;
+    p.doc_parts = parts;
+    grid = p.group_sets * p.doc_parts * cluster;
+    rc = make_bf16_rowmajor_map(&tq, a->d_q, q_rows64, dim, 128);
+    if (rc != CPB_OK) return rc;
+    rc = make_bf16_rowmajor_map(&td, a->d_docs, a->doc_rows, dim, 256 / cluster);
+    if (rc != CPB_OK) return rc;
+    rc = make_bf16_rowmajor_map(&tt, a->d_docs, a->doc_rows, dim, 32);
+    if (rc != CPB_OK) return rc;
+    CPB_CUDA(cpb::maxsim_kpipe_launch(tq, td, tt, p, lp, panels, mode, grid, stream));
+  }
+  if (nseg > 1)
+    CPB_CUDA(cpb::maxsim_reduce_segments(a->d_workspace, a->d_scores, p.plane_stride, nseg,
+                                         (flags & CPB_FLAG_ROUND_BF16) ? 1 : 0, stream));
+  if (CPB_HAS(a, cpb_maxsim_args, grid_out)) a->grid_out = grid;
+  return CPB_OK;
+}
+
+int cpb_maxsim_fwd(const void* d_q, int n_queries, int nq_pad, const void* d_docs, int64_t doc_rows,
+                   const int32_t* d_doc_start, const int32_t* d_doc_len, const float* d_doc_floor, int n_docs,
+                   float* d_scores, int32_t* d_argmax, float* d_workspace, uint32_t flags, void* stream_) {
+  cpb_maxsim_args a{};
+  a.struct_size = sizeof(a);
+  a.flags = flags;
+  a.stream = stream_;
+  a.d_q = d_q;
+  a.n_queries = n_queries;
+  a.nq_pad = nq_pad;
+  a.dim = 128;
+  a.d_docs = d_docs;
+  a.doc_rows = doc_rows;
+  a.d_doc_start = d_doc_start;
+  a.d_doc_len = d_doc_len;
+  a.d_doc_floor = d_doc_floor;
+  a.n_docs = n_docs;
+  a.d_scores = d_scores;
+  a.d_argmax = d_argmax;
+  a.d_workspace = d_workspace;
+  return cpb_maxsim_launch(&a);
+}
+
+int cpb_colbert_loss_launch(const cpb_loss_desc* loss, const float* d_scores, const void* d_q, int n_queries, int nq_pad,
+                            int n_docs, int dim, void* stream_) {
+  cpb::LossParams p{};
+  int rc = fill_loss_params(&p, loss, d_scores, d_q, n_queries, nq_pad, n_docs, dim);
+  if (rc != CPB_OK) return rc;
+  CPB_CUDA(cpb::colbert_loss_launch(p, static_cast<cudaStream_t>(stream_)));
+  return CPB_OK;
+}
+
+int cpb_wait_flags(const uint32_t* d_flags, int n, uint32_t value, uint32_t* d_status, void* stream_) {
+  if (!d_flags || n <= 0 || n > 64) return fail(CPB_E_INVALID, "bad flag array");
+  CPB_CUDA(cpb::wait_flags_launch(d_flags, nullptr, n, value, static_cast<uint32_t>(g_opt_wait_timeout_ms.load()), d_status,
+                                  static_cast<cudaStream_t>(stream_)));
+  return CPB_OK;
+}
+
+int cpb_maxsim_bwd_launch(const cpb_maxsim_bwd_args* a) {
+  if (!a || a->struct_size < sizeof(cpb_maxsim_bwd_args)) return fail(CPB_E_INVALID, "cpb_maxsim_bwd_args is null or its struct_size is too small");
+  const int dim = a->dim;
+  if (dim != 128 && dim != 192 && dim != 256 && dim != 320)
+    return fail(CPB_E_UNSUPPORTED, "embedding dim %d is not supported by this build (128, 192, 256, 320)", dim);
+  if (a->n_queries <= 0 || a->n_docs <= 0) return fail(CPB_E_INVALID, "n_queries=%d and n_docs=%d must be positive", a->n_queries, a->n_docs);
+  if (a->nq_pad <= 0 || (a->nq_pad % 32) != 0) return fail(CPB_E_INVALID, "nq_pad=%d must be a positive multiple of 32", a->nq_pad);
+  const bool smooth = a->d_lse != nullptr;
+  if (smooth == (a->d_argmax != nullptr)) return fail(CPB_E_INVALID, "exactly one of d_argmax (hard max) and d_lse (smooth max) must be given");
+  if (!a->d_grad_scores || !a->d_q || !a->d_docs || !a->d_doc_start || !a->d_doc_len) return fail(CPB_E_INVALID, "null device pointer");
+  if (a->doc_rows <= 0) return fail(CPB_E_INVALID, "doc_rows must be positive");
+  if ((reinterpret_cast<uintptr_t>(a->d_dq) | reinterpret_cast<uintptr_t>(a->d_dd) | reinterpret_cast<uintptr_t>(a->d_q) |
+       reinterpret_cast<uintptr_t>(a->d_docs)) & 15u)
+    return fail(CPB_E_INVALID, "tensor pointers must be 16-byte aligned");
+  if (smooth && !(a->smooth_tau > 0.f)) return fail(CPB_E_INVALID, "smooth_tau must be positive with d_lse");
+  if (smooth && dim != 128) return fail(CPB_E_UNSUPPORTED, "the smooth-max backward serves dim 128 only (got %d)", dim);
+  if (smooth && (a->nq_real <= 0 || a->nq_real > a->nq_pad)) return fail(CPB_E_INVALID, "smooth max needs 0 < nq_real <= nq_pad");
+  if (a->max_doc_len <= 0) return fail(CPB_E_INVALID, "max_doc_len must be positive");
+  cpb::BwdParams p{};
+  p.g = a->d_grad_scores;
+  p.grad_out = a->d_grad_out;
+  p.argmax = a->d_argmax;
+  p.lse = a->d_lse;
+  p.smooth_c = smooth ? 1.4426950408889634f / a->smooth_tau : 0.f;
+  p.q = static_cast<const __nv_bfloat16*>(a->d_q);
+  p.docs = static_cast<const __nv_bfloat16*>(a->d_docs);
+  p.doc_start = a->d_doc_start;
+  p.doc_len = a->d_doc_len;
+  p.dq = a->d_dq;
+  p.dd = a->d_dd;
+  p.B = a->n_queries;
+  p.C = a->n_docs;
+  p.nq_pad = a->nq_pad;
+  p.nq_real = smooth ? a->nq_real : a->nq_pad;
+  p.q_rows = a->n_queries * a->nq_pad;
   p.dim = dim;
-  CPB_CUDA(cpb::maxsim_bwd_launch(p, static_cast<cudaStream_t>(stream_)));
+  p.max_doc_len = a->max_doc_len;
+  p.contiguous = (a->flags & CPB_FLAG_CONTIGUOUS) ? 1 : 0;
+  p.doc_rows = a->doc_rows;
+  if (smooth) CPB_CUDA(cpb::smooth_bwd_launch(p, static_cast<cudaStream_t>(a->stream)));
+  else CPB_CUDA(cpb::maxsim_bwd_launch(p, static_cast<cudaStream_t>(a->stream)));
   return CPB_OK;
 }
 
@@ -447,7 +514,7 @@ int cpb_head_fwd(const void* d_hidden, int64_t n_tokens, int hidden, const void*
                  void* stream_) {
   if (n_tokens <= 0) return fail(CPB_E_INVALID, "n_tokens=%lld must be positive", static_cast<long long>(n_tokens));
   if (n_tokens > 0x7fffff00LL) return fail(CPB_E_INVALID, "n_tokens too large");
-  const bool wide = dim > 128;  // DRAFT: head_wide_sm100.cu
+  const bool wide = dim > 128;  // head_wide_sm100.cu
   if (dim != 128 && !(wide && dim <= 320 && (dim % 32) == 0))
     return fail(CPB_E_UNSUPPORTED, "projection dim %d is not supported by this build (128, or a multiple of 32 up to 320)", dim);
   if (hidden <= 0 || (hidden % 64) != 0) return fail(CPB_E_UNSUPPORTED, "hidden size %d must be a positive multiple of 64", hidden);
@@ -475,7 +542,7 @@ int cpb_head_fwd(const void* d_hidden, int64_t n_tokens, int hidden, const void*
     p.stages = cpb::head_wide_stages(dim);
     if (p.stages < 2) return fail(CPB_E_UNSUPPORTED, "projection dim %d does not fit the shared-memory ring", dim);
     const int64_t tiles = (n_tokens + 127) / 128;
-    p.cluster = (g_head_cluster == 1 || tiles < 2) ? 1 : 2;
+    p.cluster = (g_head_cluster.load() == 1 || tiles < 2) ? 1 : 2;
     const int64_t rounds = (tiles + p.cluster - 1) / p.cluster;
     const int64_t max_clusters = di.sm_count / p.cluster;
     const int grid = static_cast<int>((rounds < max_clusters ? rounds : max_clusters) * p.cluster);
@@ -485,62 +552,6 @@ int cpb_head_fwd(const void* d_hidden, int64_t n_tokens, int hidden, const void*
   const int64_t pairs = (n_tokens + 255) / 256;
   const int grid = static_cast<int>(pairs < di.sm_count ? pairs : di.sm_count);
   CPB_CUDA(cpb::head_launch(th, tw, p, grid, static_cast<cudaStream_t>(stream_)));
-  return CPB_OK;
-}
-
-// DRAFT (r2-drafts): MaxSim forward for embedding dims 192 / 256 / 320 (K-pipelined kernel, one query tile per CTA).
-// dim must be a multiple of 64 in (128, 320]; queries and documents are [rows, dim] bf16.  No balancing, no fused gather yet.
-int cpb_maxsim_fwd_dim(const void* d_q, int n_queries, int nq_pad, const void* d_docs, int64_t doc_rows,
-                       const int32_t* d_doc_start, const int32_t* d_doc_len, const float* d_doc_floor, int n_docs,
-                       float* d_scores, int32_t* d_argmax, float* d_workspace, uint32_t flags, int dim, void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (dim <= 128 || dim > 320 || (dim % 64) != 0) return fail(CPB_E_UNSUPPORTED, "dim=%d: this entry point serves 192, 256 and 320", dim);
-  if (n_queries <= 0 || n_docs <= 0) return fail(CPB_E_INVALID, "n_queries=%d and n_docs=%d must be positive", n_queries, n_docs);
-  if (nq_pad <= 0 || (nq_pad % 32) != 0) return fail(CPB_E_INVALID, "nq_pad=%d must be a positive multiple of 32", nq_pad);
-  if (!d_q || !d_docs || !d_doc_start || !d_doc_len || !d_scores) return fail(CPB_E_INVALID, "null device pointer");
-  if (doc_rows <= 0 || doc_rows > 0x7fffffffLL) return fail(CPB_E_INVALID, "doc_rows out of range");
-  const int nseg = nq_pad / 32;
-  if (nseg > 1 && !d_workspace) return fail(CPB_E_INVALID, "nq_pad=%d needs a workspace", nq_pad);
-  DevInfo di;
-  int rc = current_device_info(&di);
-  if (rc != CPB_OK) return rc;
-  if (di.major != 10) return fail(CPB_E_DEVICE, "device is sm_%d%d; this library needs sm_100 (B200)", di.major, di.minor);
-  const int panels = dim / 64;
-  cpb::MaxSimParams p{};
-  p.q = d_q;
-  p.doc_start = d_doc_start;
-  p.doc_len = d_doc_len;
-  p.doc_floor = d_doc_floor;
-  p.argmax = d_argmax;
-  p.plane_stride = static_cast<int64_t>(n_queries) * n_docs;
-  p.n_queries = n_queries;
-  p.nq_pad = nq_pad;
-  p.q_rows = n_queries * nq_pad;
-  p.n_docs = n_docs;
-  p.num_qtiles = (p.q_rows + 127) / 128;
-  p.scores = (nseg == 1) ? d_scores : d_workspace;
-  p.q_groups = p.num_qtiles;  // one query tile per CTA
-  int cluster = (p.q_groups >= 2) ? 2 : 1;
-  int max_clusters = cpb::maxsim_kpipe_max_clusters(panels, cluster);
-  if (max_clusters <= 0) return fail(CPB_E_CUDA, "K-pipelined kernel cannot be resident on this device");
-  p.cluster = cluster;
-  p.group_sets = (p.q_groups + cluster - 1) / cluster;
-  int parts = max_clusters / p.group_sets;
-  if (parts < 1) parts = 1;
-  if (parts > n_docs) parts = n_docs;
-  p.doc_parts = parts;
-  p.flags = flags | g_opt_debug_flags;
-  const int grid = p.group_sets * p.doc_parts * cluster;
-  CUtensorMap tq, td, tt;
-  rc = make_bf16_rowmajor_map(&tq, d_q, p.q_rows, dim, 128);
-  if (rc != CPB_OK) return rc;
-  rc = make_bf16_rowmajor_map(&td, d_docs, doc_rows, dim, 256 / cluster);
-  if (rc != CPB_OK) return rc;
-  rc = make_bf16_rowmajor_map(&tt, d_docs, doc_rows, dim, 32);
-  if (rc != CPB_OK) return rc;
-  CPB_CUDA(cpb::maxsim_kpipe_launch(tq, td, tt, p, panels, d_argmax != nullptr, grid, stream));
-  if (nseg > 1)
-    CPB_CUDA(cpb::maxsim_reduce_segments(d_workspace, d_scores, p.plane_stride, nseg, (flags & CPB_FLAG_ROUND_BF16) ? 1 : 0, stream));
   return CPB_OK;
 }
 

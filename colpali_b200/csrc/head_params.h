@@ -15,7 +15,7 @@ struct HeadParams {
   int64_t n_tokens;
   int hidden;
   uint32_t flags;
-  // head_wide_sm100.cu only (DRAFT): output dim in (128, 320], ring depth, CTAs per cluster (1 or 2)
+  // head_wide_sm100.cu only: output dim in (128, 320], ring depth, CTAs per cluster (1 or 2)
   int dim, stages, cluster;
 };
 

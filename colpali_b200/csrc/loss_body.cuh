@@ -1,0 +1,209 @@
+// Body of the ColBERT loss kernels: [B, C] raw MaxSim sums -> scalar loss AND dLoss/dScores in one pass.
+//   replaces late_interaction_losses.py:152 (lengths), :155-156 / :46-71 (normalise), :161-162 / :93-107 (pos-aware
+//   negative filtering), :164 (cross entropy, ColbertLoss), :309-313 (top-2 / softplus, ColbertPairwiseCELoss),
+//   :452-465 (ColbertSigmoidLoss) and the explicit-negative terms :234-250 / :380-396.
+#pragma once
+#include <cfloat>
+#include <cstdint>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "loss_params.h"
+
+namespace cpb {
+
+__device__ __forceinline__ float warp_sum_f(float x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+__device__ __forceinline__ float warp_max_f(float x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, o));
+  return x;
+}
+__device__ __forceinline__ float warp_min_f(float x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x = fminf(x, __shfl_xor_sync(0xffffffffu, x, o));
+  return x;
+}
+
+// value/index pair ordered by (value desc, index asc): the first maximal index wins, like torch.max
+struct Top {
+  float v;
+  int i;
+};
+__device__ __forceinline__ bool better(const Top& a, const Top& b) { return a.v > b.v || (a.v == b.v && a.i < b.i); }
+
+// Whole-CTA device function (every thread of the block must call it: it ends with a __syncthreads reduction).
+// Used by the stand-alone colbert_loss_kernel (loss_sm100.cu) and by the last CTA of the fused MaxSim kernels, which
+// read the score matrix other CTAs have just written (hence the L2 loads).
+__device__ __forceinline__ void colbert_loss_body(const LossParams& p) {
+  __shared__ float s_loss[32];
+  __shared__ float s_min[32];
+  __shared__ float s_max[32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = blockDim.x >> 5;
+  float loss_acc = 0.f, mn = INFINITY, mx = -INFINITY;
+  const bool has_neg = p.neg_scores != nullptr;
+  const float w_ib = has_neg ? p.in_batch_weight : 1.f;     // late_interaction_losses.py:248-250 / :394-396
+  const float w_out = has_neg ? 1.f - p.in_batch_weight : 0.f;
+
+  for (int b = warp; b < p.B; b += nwarps) {
+    // lengths = (q[:, :, 0] != 0).sum(1)                       late_interaction_losses.py:152
+    float cnt = 0.f;
+    for (int n = lane; n < p.nq_pad; n += 32)
+      cnt += (__bfloat162float(p.q[(static_cast<int64_t>(b) * p.nq_pad + n) * p.q_dim]) != 0.f) ? 1.f : 0.f;
+    cnt = warp_sum_f(cnt);
+    const float inv = p.normalize ? 1.f / cnt : 1.f;          // :155-156 -> :59-62
+    const float* row = p.scores + static_cast<int64_t>(b) * p.C;
+    const int pidx = b + p.offset;                              // :33-38
+    const float pos = __ldcg(row + pidx) * inv;
+    const float thr = p.filter_threshold * pos;                 // :101-104
+    const float invT = 1.f / p.temperature;
+    const float invB = w_ib / static_cast<float>(p.B);
+
+    // filtered score of column c and the factor it was multiplied by      (:105-107)
+    auto filtered = [&](int c, float& f) {
+      float s = __ldcg(row + c) * inv;
+      f = (p.filter && c != pidx && s > thr) ? p.filter_factor : 1.f;
+      return s * f;
+    };
+
+    if (p.mode == 0) {
+      // cross entropy of scores / T against pidx                (:164)
+      float m = -INFINITY;
+      for (int c = lane; c < p.C; c += 32) {
+        float f;
+        const float s = filtered(c, f);
+        mn = fminf(mn, __ldcg(row + c) * inv);
+        mx = fmaxf(mx, __ldcg(row + c) * inv);
+        m = fmaxf(m, s * invT);
+      }
+      m = warp_max_f(m);
+      float se = 0.f;
+      for (int c = lane; c < p.C; c += 32) {
+        float f;
+        se += __expf(filtered(c, f) * invT - m);
+      }
+      se = warp_sum_f(se);
+      const float lse = m + __logf(se);
+      loss_acc += w_ib * (lse - pos * invT);  // the positive column is never filtered
+      if (p.grad != nullptr) {
+        float* g = p.grad + static_cast<int64_t>(b) * p.C;
+        for (int c = lane; c < p.C; c += 32) {
+          float f;
+          const float s = filtered(c, f);
+          const float sm = __expf(s * invT - lse);
+          g[c] = (sm - (c == pidx ? 1.f : 0.f)) * invT * f * inv * invB;
+        }
+      }
+    } else if (p.mode == 1) {
+      // pos = diagonal(offset); top-2 of the row; neg = top1 == pos ? top2 : top1      (:309-311)
+      Top t1{-INFINITY, 0x7fffffff}, t2{-INFINITY, 0x7fffffff};
+      for (int c = lane; c < p.C; c += 32) {
+        float f;
+        const Top x{filtered(c, f), c};
+        mn = fminf(mn, __ldcg(row + c) * inv);
+        mx = fmaxf(mx, __ldcg(row + c) * inv);
+        if (better(x, t1)) {
+          t2 = t1;
+          t1 = x;
+        } else if (better(x, t2)) {
+          t2 = x;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        Top a1{__shfl_xor_sync(0xffffffffu, t1.v, o), __shfl_xor_sync(0xffffffffu, t1.i, o)};
+        Top a2{__shfl_xor_sync(0xffffffffu, t2.v, o), __shfl_xor_sync(0xffffffffu, t2.i, o)};
+        // merge two sorted pairs
+        if (better(a1, t1)) {
+          t2 = better(t1, a2) ? t1 : a2;
+          t1 = a1;
+        } else {
+          t2 = better(a1, t2) ? a1 : t2;
+        }
+      }
+      const Top neg = (t1.v == pos) ? t2 : t1;
+      const float x = (neg.v - pos) * invT;
+      loss_acc += w_ib * (fmaxf(x, 0.f) + log1pf(__expf(-fabsf(x))));   // softplus           (:313)
+      if (p.grad != nullptr) {
+        const float sig = 1.f / (1.f + __expf(-x));
+        float* g = p.grad + static_cast<int64_t>(b) * p.C;
+        float fneg;
+        (void)filtered(neg.i < p.C ? neg.i : pidx, fneg);
+        for (int c = lane; c < p.C; c += 32) {
+          float v = 0.f;
+          if (c == neg.i) v += sig * invT * fneg * inv * invB;
+          if (c == pidx) v -= sig * invT * inv * invB;
+          g[c] = v;
+        }
+      }
+    } else {
+      // sigmoid loss: softplus(-s/T * m), m = +1 on the diagonal, -1 elsewhere; mean over B*B   (:452-465)
+      float* g = p.grad ? p.grad + static_cast<int64_t>(b) * p.C : nullptr;
+      const float invBB = invB / static_cast<float>(p.C);
+      float part = 0.f;  // per-lane partial sum, reduced below (loss_acc must stay warp-uniform)
+      for (int c = lane; c < p.C; c += 32) {
+        float f;
+        const float s = filtered(c, f);
+        mn = fminf(mn, __ldcg(row + c) * inv);
+        mx = fmaxf(mx, __ldcg(row + c) * inv);
+        const float msk = (c == b) ? 1.f : -1.f;
+        const float z = -s * invT * msk;
+        part += (fmaxf(z, 0.f) + log1pf(__expf(-fabsf(z)))) / static_cast<float>(p.C);
+        if (g) g[c] = -msk * invT * f * inv * invBB / (1.f + __expf(-z));
+      }
+      loss_acc += warp_sum_f(part);
+    }
+
+    if (has_neg) {
+      // softplus((neg - pos) / T) over this query's own negatives, mean over B * n_neg          (:235-246, :381-392)
+      const float* nrow = p.neg_scores + static_cast<int64_t>(b) * p.B * p.n_neg;
+      float* gn = p.grad_neg ? p.grad_neg + static_cast<int64_t>(b) * p.B * p.n_neg : nullptr;
+      const float scale = w_out / (static_cast<float>(p.B) * static_cast<float>(p.n_neg));
+      float gpos = 0.f, part = 0.f;
+      for (int c = lane; c < p.B * p.n_neg; c += 32) {
+        float gv = 0.f;
+        if (c / p.n_neg == b) {
+          const float x = (__ldcg(nrow + c) * inv - pos) * invT;
+          part += (fmaxf(x, 0.f) + log1pf(__expf(-fabsf(x)))) * w_out / static_cast<float>(p.n_neg);
+          gv = scale * invT * inv / (1.f + __expf(-x));
+          gpos -= gv;
+        }
+        if (gn) gn[c] = gv;
+      }
+      gpos = warp_sum_f(gpos);
+      loss_acc += warp_sum_f(part);
+      if (p.grad != nullptr && lane == (pidx & 31)) p.grad[static_cast<int64_t>(b) * p.C + pidx] += gpos;
+    }
+  }
+
+  // mean over the batch (CrossEntropyLoss default reduction / .mean())
+  mn = warp_min_f(mn);
+  mx = warp_max_f(mx);
+  if (lane == 0) {
+    s_loss[warp] = loss_acc;
+    s_min[warp] = mn;
+    s_max[warp] = mx;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float l = (lane < nwarps) ? s_loss[lane] : 0.f;
+    float a = (lane < nwarps) ? s_min[lane] : INFINITY;
+    float z = (lane < nwarps) ? s_max[lane] : -INFINITY;
+    l = warp_sum_f(l);
+    a = warp_min_f(a);
+    z = warp_max_f(z);
+    if (lane == 0) {
+      p.loss[0] = l / static_cast<float>(p.B);
+      if (p.bounds != nullptr) {
+        p.bounds[0] = a;
+        p.bounds[1] = z;
+      }
+    }
+  }
+}
+
+}  // namespace cpb

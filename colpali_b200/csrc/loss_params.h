@@ -28,17 +28,24 @@ struct LossParams {
 struct BwdParams {
   const float* g;             // [B, C]
   const float* grad_out;      // scalar upstream gradient, or nullptr (= 1)
-  const int32_t* argmax;      // [C, q_rows] document-relative token index, -1 = floor (no gradient)
-  const __nv_bfloat16* q;     // [q_rows, 128]
-  const __nv_bfloat16* docs;  // [doc_rows, 128]
+  const int32_t* argmax;      // hard max: [C, q_rows] document-relative token index, -1 = floor (no gradient)
+  const float* lse;           // smooth max: [C, q_rows] tau * logsumexp per (document, query row)
+  float smooth_c;             // log2(e) / tau
+  const __nv_bfloat16* q;     // [q_rows, dim]
+  const __nv_bfloat16* docs;  // [doc_rows, dim]
   const int32_t* doc_start;   // [C]
-  float* dq;                  // [q_rows, 128]
-  float* dd;                  // [doc_rows, 128], pre-zeroed
-  int B, C, nq_pad, q_rows;
-  int dim;                    // padded embedding dim: 128 (the validated kernels) or 192 / 256 / 320 (drafts)
+  const int32_t* doc_len;     // [C]
+  float* dq;                  // [q_rows, dim] written
+  float* dd;                  // [doc_rows, dim] written (every row of every document)
+  int B, C, nq_pad, nq_real, q_rows;
+  int dim;                    // padded embedding dim: 128, 192, 256 or 320
+  int max_doc_len;            // longest document
+  int contiguous;             // documents back to back and covering the bank: no row of dd is outside a document
+  int64_t doc_rows;
 };
 
 cudaError_t colbert_loss_launch(const LossParams& p, cudaStream_t stream);
 cudaError_t maxsim_bwd_launch(const BwdParams& p, cudaStream_t stream);
+cudaError_t smooth_bwd_launch(const BwdParams& p, cudaStream_t stream);
 
 }  // namespace cpb

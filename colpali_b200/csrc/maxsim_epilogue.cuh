@@ -9,6 +9,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "loss_body.cuh"
 #include "maxsim_params.h"
 #include "sm100_ptx.cuh"
 
@@ -114,12 +115,74 @@ struct CtaSlice {
   int bal_r0, bal_r1;  // balanced mode: bank rows [bal_r0, bal_r1)
 };
 
+// Aggregation over a document's tokens
+constexpr int kModeMax = 0;     // running maximum (scorer, losses without gradient)
+constexpr int kModeArgmax = 1;  // maximum + index of the first maximal token (training forward)
+constexpr int kModeSmooth = 2;  // tau * logsumexp(raw / tau): online (max, sum) pair per query row
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// online log-sum-exp over columns lo <= i < hi of a 32-column chunk, in base-2 units scaled by c = log2(e) / tau:
+// (m, l) <- (max(m, max_i y_i), l * 2^(m - m') + sum_i 2^(y_i - m')) with y_i = c * v_i
+__device__ __forceinline__ void lse32_range(const uint32_t (&v)[32], float& m, float& l, float c, int lo, int hi) {
+  float y[32];
+  float cm = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    y[i] = (i >= lo && i < hi) ? __uint_as_float(v[i]) * c : -INFINITY;
+    cm = fmaxf(cm, y[i]);
+  }
+  const float mn = fmaxf(m, cm);
+  const float ms = (mn == -INFINITY) ? 0.f : mn;  // nothing seen yet: every term below is 2^(-inf) = 0, never NaN
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) acc += ex2_approx(y[i] - ms);
+  l = l * ex2_approx(m - ms) + acc;
+  m = mn;
+}
+// the same over a whole chunk (no masks): FMNMX3 tree for the maximum, one FFMA + MUFU.EX2 + FADD per element
+__device__ __forceinline__ void lse32_full(const uint32_t (&v)[32], float& m, float& l, float c) {
+  float t[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    t[i] = fmax3(fmax3(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2])),
+                 __uint_as_float(v[4 * i + 3]), __uint_as_float(v[4 * i + 3]));
+  const float cm = fmax3(fmax3(t[0], t[1], t[2]), fmax3(t[3], t[4], t[5]), fmaxf(t[6], t[7])) * c;  // c > 0
+  const float mn = fmaxf(m, cm);
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    a0 += ex2_approx(fmaf(__uint_as_float(v[i]), c, -mn));
+    a1 += ex2_approx(fmaf(__uint_as_float(v[i + 1]), c, -mn));
+    a2 += ex2_approx(fmaf(__uint_as_float(v[i + 2]), c, -mn));
+    a3 += ex2_approx(fmaf(__uint_as_float(v[i + 3]), c, -mn));
+  }
+  l = l * ex2_approx(m - mn) + ((a0 + a1) + (a2 + a3));  // m = -inf the first time: 2^(-inf) = 0
+  m = mn;
+}
+
+// one fp32 to every rank's copy of the symmetric buffer through the NVSwitch multicast mapping
+__device__ __forceinline__ void multimem_st_f32(uint64_t mc_addr, float x) {
+  asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(mc_addr), "f"(x) : "memory");
+}
+
 // Runs on warps 2..5 (one TMEM lane quadrant each).  R = resident query tiles per CTA.
-template <int R, bool kArgmax>
+template <int R, int kMode>
 __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const CtaSlice& sl, uint32_t tmem_base,
                                                 uint64_t* tmem_full, uint64_t* tmem_empty, int warp, int lane) {
   constexpr int kTileM = kEpiTileM;
   constexpr int kTileN = kEpiTileN;
+  constexpr bool kArgmax = (kMode == kModeArgmax);
+  constexpr bool kSmooth = (kMode == kModeSmooth);
   const int g = sl.g, part = sl.part, r_cnt = sl.r_cnt, d0 = sl.d0, d1 = sl.d1, bal_r0 = sl.bal_r0, bal_r1 = sl.bal_r1;
   const int quad = warp & 3;  // TMEM lane quadrant this warp may read
   const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
@@ -127,29 +190,47 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
   const bool skip = (p.flags & CPB_DBG_SKIP_EPILOGUE) != 0;
 
   // document `doc` is complete for resident query tile r: fold this query segment's 32 token maxima
-  auto finalize = [&](int doc, int r, float mm, int ai) {
+  // (smooth mode: mm / ll are the online log-sum-exp pair in base-2 units, late_interaction_losses.py:40-44)
+  auto finalize = [&](int doc, int r, float mm, int ai, float ll) {
     const int row0 = (g * R + r) * kTileM + quad * 32;  // first padded query row of this warp
     const int q = row0 / p.nq_pad;
     const int seg = (row0 % p.nq_pad) >> 5;
     if (kArgmax && p.argmax != nullptr && row0 + lane < p.q_rows)
       p.argmax[static_cast<int64_t>(doc) * p.q_rows + row0 + lane] = ai;
-    float x = round_ref ? round_bf16(mm) : mm;
-    x = warp_sum(x);
-    if (round_ref && p.nq_pad == 32) x = round_bf16(x);
+    float x;
+    if constexpr (kSmooth) {
+      // tau * ln(sum_s exp(raw_s / tau)); EVERY row of the query tensor counts (an all-zero row adds tau * ln N_d,
+      // as in the reference) except the rows QueryBlock appended to reach a multiple of 32
+      const float v = (mm + lg2_approx(ll)) * p.smooth_out;
+      const int rowi = row0 + lane;
+      if (p.lse != nullptr && rowi < p.q_rows) p.lse[static_cast<int64_t>(doc) * p.q_rows + rowi] = v;
+      x = warp_sum(((rowi % p.nq_pad) < p.nq_real && rowi < p.q_rows) ? v : 0.f);
+    } else {
+      x = round_ref ? round_bf16(mm) : mm;
+      x = warp_sum(x);
+      if (round_ref && p.nq_pad == 32) x = round_bf16(x);
+    }
     if (lane == 0 && q < p.n_queries && !(p.flags & CPB_DBG_CLOCKS)) {
       if (p.peer_scores != nullptr) {
-        // fused all-gather of the score slabs: one 4-byte store per peer GPU, straight into its copy of
-        // gathered[my_rank] through the NVLink peer mapping (no collective kernel afterwards, only a barrier)
+        // fused all-gather of the score slabs: the score goes straight into every rank's copy of
+        // gathered[parity][my_rank] -- one multimem.st through the NVSwitch multicast mapping, or one 4-byte store
+        // per peer mapping (no collective kernel afterwards; completion is signalled per CTA in the teardown)
         const int64_t off = p.peer_slab_offset + static_cast<int64_t>(q) * p.n_docs + doc;
-        for (int pr = 0; pr < p.n_peers; ++pr) reinterpret_cast<float*>(__ldg(p.peer_scores + pr))[off] = x;
+        if (p.mc_base != 0) {
+          multimem_st_f32(p.mc_base + 4ull * static_cast<uint64_t>(off), x);
+        } else {
+          for (int pr = 0; pr < p.n_peers; ++pr) reinterpret_cast<float*>(__ldg(p.peer_scores + pr))[off] = x;
+        }
       } else {
         p.scores[static_cast<int64_t>(seg) * p.plane_stride + static_cast<int64_t>(q) * p.n_docs + doc] = x;
       }
     }
   };
-  auto doc_init = [&](int doc) { return (p.doc_floor != nullptr) ? __ldg(p.doc_floor + doc) : -INFINITY; };
+  auto doc_init = [&](int doc) {
+    return (!kSmooth && p.doc_floor != nullptr) ? __ldg(p.doc_floor + doc) : -INFINITY;
+  };
 
-  float m[R];
+  float m[R], ls[R];
   int am[R];
   uint32_t job = 0;
   const bool dbg = (p.flags & CPB_DBG_CLOCKS) != 0;
@@ -210,7 +291,7 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
       // nothing but empty documents: their score is the sum of the floors (balanced mode: an empty partition)
       if (!p.balanced)
         for (int e = d; e < run.e; ++e)
-          for (int r = 0; r < r_cnt; ++r) finalize(e, r, doc_init(e), -1);
+          for (int r = 0; r < r_cnt; ++r) finalize(e, r, doc_init(e), -1, 0.f);
       d = run.e;
       continue;
     }
@@ -228,6 +309,7 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
       for (int r = 0; r < R; ++r) {
         m[r] = init;
         am[r] = -1;
+        ls[r] = 0.f;
       }
     }
     for (int row = run.row0; row < run.row1; row += kTileN) {
@@ -246,14 +328,14 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
           long long t2 = 0;
           tc_fence_after();
           const uint32_t taddr = tmem_base + lane_base + a * kTileN;
-          float mm = m[r];
+          float mm = m[r], ll = ls[r];
           int ai = am[r];
           int doc = cur, doc_row0 = cur_row0, doc_end = cur_end, doc_nlen = cur_nlen;
           float doc_ninit = cur_ninit;
 
           // the current document is complete: emit it and step to the next one of the run
           auto finish_doc = [&]() {
-            if (head_frag && doc == first_doc) publish(r, mm, ai); else finalize(doc, r, mm, ai);
+            if (head_frag && doc == first_doc) publish(r, mm, ai); else finalize(doc, r, mm, ai, ll);
             ++doc;
             if (doc >= run.e) {
               doc_end = 0x7fffffff;  // run exhausted
@@ -263,6 +345,7 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
             doc_end = doc_row0 + doc_nlen;
             mm = doc_ninit;
             ai = -1;
+            ll = 0.f;
             doc_nlen = (doc + 1 < run.e) ? __ldg(p.doc_len + doc + 1) : 0;
             doc_ninit = (doc + 1 < run.e) ? doc_init(doc + 1) : -INFINITY;
           };
@@ -278,7 +361,7 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
           // new document per 32-column chunk, plus one masked pass over the chunk that holds the boundary.
           // (3) anything else (short documents, last tile of a run, argmax): generic masked walk.
           int path = 3;
-          if (!kArgmax && n_valid == kTileN) {
+          if (!kArgmax && !kSmooth && n_valid == kTileN) {
             if (doc_end >= tile_end) {
               path = 1;
             } else if (doc_end > row && doc + 1 < run.e) {
@@ -333,6 +416,58 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
             mm = max32(vc, mm);
             mm = max32(vd, mm);
             while (doc_end <= tile_end) finish_doc();  // document (and empty followers) ending at the tile end
+          } else if (path == 2 && p.boundary_mode == 1 && doc_end - row >= 32 && doc_end - row <= kTileN - 32) {
+            // one boundary at column b, at least 32 columns from either edge: read the tile as 32-column chunks
+            // ALIGNED TO THE BOUNDARY -- the old document's columns [0, b) as chunks at min(32 i, b - 32), the new
+            // one's [b, 256) at min(b + 32 j, 224).  Chunks of one document may overlap (a maximum is idempotent), so
+            // every chunk is a plain FMNMX3 tree: no element-wise split, no re-read.  8 or 9 chunks (a 9th slot
+            // that is not needed repeats the last chunk).
+            const int b = doc_end - row;
+            const int n_old = (b + 31) >> 5;
+            float mb = doc_ninit;
+            auto col = [&](int i) { return (i < n_old) ? min(32 * i, b - 32) : min(b + 32 * (i - n_old), kTileN - 32); };
+            auto route = [&](const uint32_t (&v)[32], int i) {
+              const float t = tree32(v);
+              mm = (i < n_old) ? fmaxf(mm, t) : mm;
+              mb = (i >= n_old) ? fmaxf(mb, t) : mb;
+            };
+            uint32_t va[32], vb[32], vc[32], vd[32];
+            tmem_ld_x32(taddr + col(0), va);
+            tmem_ld_x32(taddr + col(1), vb);
+            tmem_ld_wait();
+            reg_fence32(va);
+            reg_fence32(vb);
+            tmem_ld_x32(taddr + col(2), vc);
+            tmem_ld_x32(taddr + col(3), vd);
+            route(va, 0);
+            route(vb, 1);
+            tmem_ld_wait();
+            reg_fence32(vc);
+            reg_fence32(vd);
+            tmem_ld_x32(taddr + col(4), va);
+            tmem_ld_x32(taddr + col(5), vb);
+            route(vc, 2);
+            route(vd, 3);
+            tmem_ld_wait();
+            reg_fence32(va);
+            reg_fence32(vb);
+            tmem_ld_x32(taddr + col(6), vc);
+            tmem_ld_x32(taddr + col(7), vd);
+            route(va, 4);
+            route(vb, 5);
+            tmem_ld_wait();
+            reg_fence32(vc);
+            reg_fence32(vd);
+            tmem_ld_x32(taddr + col(8), va);
+            route(vc, 6);
+            route(vd, 7);
+            tmem_ld_wait();
+            reg_fence32(va);
+            release_acc();
+            route(va, 8);
+            finish_doc();  // old document (running max mm); the cursor moves to the new one, whose max is mb
+            mm = mb;
+            while (doc_end <= tile_end) finish_doc();
           } else if (path == 2) {
             // one boundary at column b: per 32-column chunk the FMNMX3 tree goes to the old document (chunk < kb)
             // or the new one (chunk > kb) through selects; the boundary chunk itself is re-read at the end and split
@@ -402,7 +537,10 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
               while (true) {
                 const int seg_end = min(doc_end, abs1);
                 if (seg_end > pos) {
-                  if constexpr (kArgmax) {
+                  if constexpr (kSmooth) {
+                    if (pos == abs0 && seg_end == abs0 + 32) lse32_full(v, mm, ll, p.smooth_c);
+                    else lse32_range(v, mm, ll, p.smooth_c, pos - abs0, seg_end - abs0);
+                  } else if constexpr (kArgmax) {
                     argmax32_range(v, mm, ai, abs0 - doc_row0, pos - abs0, seg_end - abs0);
                   } else {
                     mm = max32_range(v, mm, pos - abs0, seg_end - abs0);
@@ -423,6 +561,7 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
           }
           m[r] = mm;
           am[r] = ai;
+          ls[r] = ll;
           nxt = doc;
           nxt_row0 = doc_row0;
           nxt_end = doc_end;
@@ -447,7 +586,7 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
           __trap();
         }
         consume(r, mm, ai);
-        finalize(cur, r, mm, ai);
+        finalize(cur, r, mm, ai, 0.f);
       }
     }
     d = run.e;
@@ -460,6 +599,67 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
     o[5] = static_cast<float>(e_hold2);
     o[6] = static_cast<float>(n_path2);
     o[7] = static_cast<float>(job);
+  }
+}
+
+// Programmatic dependent launch: let the next kernel of the stream be scheduled as SMs free up, and (mode 1) wait for
+// the previous kernel's completion + memory flush before this one touches global memory.  Mode 2 never waits: only for
+// launches that do not consume anything the previous kernel wrote.
+__device__ __forceinline__ void maxsim_pdl_entry(const MaxSimParams& p) {
+  if (p.pdl != 0) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (p.pdl == 1) asm volatile("griddepcontrol.wait;" ::: "memory");
+  }
+  if (p.wait_flags != nullptr) {  // fused all-gather: the peers must be done with the slab this launch overwrites
+    if (static_cast<int>(threadIdx.x) < p.n_wait) {
+      const uint32_t* f = p.wait_flags + threadIdx.x;
+      const uint64_t t0 = global_timer_ns();
+      const uint64_t limit = static_cast<uint64_t>(p.wait_timeout_ms) * 1000000ull;
+      while (true) {
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+        if (static_cast<int32_t>(v - p.wait_value) >= 0) break;
+        if (global_timer_ns() - t0 > limit) __trap();  // a peer is gone: proceeding would corrupt its unread results
+        __nanosleep(32);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// End of the kernel, called by ALL threads of the CTA after their role code: makes the CTA's results visible, signals
+// the fused all-gather's consumers, and lets the last CTA of the grid turn the score matrix into the loss.
+__device__ __forceinline__ void maxsim_finish(const MaxSimParams& p, const LossParams& lp, int cluster, int warp) {
+  __shared__ int s_last;
+  const bool fused_loss = lp.loss != nullptr && p.done_counter != nullptr;
+  if (fused_loss && warp >= 2) __threadfence();  // this warp's score stores are visible device-wide before the count
+  tc_fence_before();
+  // no CTA may exit while a peer can still multicast into its shared memory or signal its barriers
+  if (cluster > 1) cluster_sync_all(); else __syncthreads();
+  if (p.peer_scores != nullptr && threadIdx.x == 0) {
+    // fused all-gather completion.  Every score store of this CTA happened before the barrier above, so ONE release at
+    // system scope (cumulative) publishes them; the flag word of every rank then grows by one per CTA.
+    if (p.mc_base != 0) {
+      asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(p.mc_base + 4ull * static_cast<uint64_t>(p.peer_flag_offset)), "r"(1u) : "memory");
+    } else {
+      for (int pr = 0; pr < p.n_peers; ++pr) {
+        uint32_t* f = reinterpret_cast<uint32_t*>(__ldg(p.peer_scores + pr)) + p.peer_flag_offset;
+        asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(f), "r"(1u) : "memory");
+      }
+    }
+  }
+  if (fused_loss) {
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned prev = atomicAdd(p.done_counter, 1u);
+      s_last = (prev + 1u == gridDim.x) ? 1 : 0;
+      if (s_last) *p.done_counter = 0u;  // ready for the next launch (stream ordered)
+    }
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      colbert_loss_body(lp);  // reads the [B, C] scores through L2 (__ldcg)
+    }
   }
 }
 

@@ -1,7 +1,6 @@
 // K-pipelined fused MaxSim for embedding dims up to 320 (ColQwen3: colpali_engine/models/qwen3/colqwen3/modeling_colqwen3.py:48).
 //
-// DRAFT (branch r2-drafts): compiles for sm_100a, NOT yet run on a GPU.  Same contract, epilogue and partitioning as
-// maxsim_sm100.cu (the epilogue / teardown text below is carved verbatim from it, R = 1); what differs is the K loop:
+// Same contract, epilogue (maxsim_epilogue.cuh, R = 1) and partitioning as maxsim_sm100.cu; what differs is the K loop:
 //   * the embedding dim is KP panels of 64 (KP = 1..5); ONE 128-row query tile per CTA stays resident in shared memory
 //     (KP x 16 KiB); a ring stage holds ONE K-panel of a 256-row document tile (32 KiB), 4 stages;
 //   * per document tile the issuer runs KP x 4 tcgen05.mma 128x256x16 into one 256-column accumulator (two
@@ -43,10 +42,10 @@ struct SmemLayout {
   static constexpr int kAlloc = kBytes + 1024;
 };
 
-template <int KP, bool kArgmax>
+template <int KP, int kMode>
 __global__ void __launch_bounds__(kThreads, 1)
 maxsim_kpipe_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_d,
-                    const __grid_constant__ CUtensorMap tmap_tail, const MaxSimParams p) {
+                    const __grid_constant__ CUtensorMap tmap_tail, const MaxSimParams p, const LossParams lp) {
   using L = SmemLayout<KP>;
   constexpr int S = kStages;
 
@@ -106,6 +105,7 @@ maxsim_kpipe_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   if (C > 1) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  maxsim_pdl_entry(p);
   const long long dbg_c0 = clock64();
   const uint64_t dbg_t0 = global_timer_ns();
 
@@ -242,31 +242,14 @@ maxsim_kpipe_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   } else {
     // ================================ epilogue (maxsim_epilogue.cuh) ==========================
     const CtaSlice sl{g, part, r_cnt, d0, d1, bal_r0, bal_r1};
-    maxsim_epilogue<R, kArgmax>(p, sl, tmem_base, tmem_full, tmem_empty, warp, lane);
+    maxsim_epilogue<R, kMode>(p, sl, tmem_base, tmem_full, tmem_empty, warp, lane);
   }
 
   // ---- teardown ---------------------------------------------------------------------------
-  if (p.peer_scores != nullptr && p.done_counter != nullptr && warp >= 2)
-    __threadfence_system();  // my peer stores are ordered before the completion signal below
-  tc_fence_before();
-  // no CTA may exit while a peer can still multicast into its shared memory or signal its barriers
-  if (C > 1) cluster_sync_all(); else __syncthreads();
+  maxsim_finish(p, lp, C, warp);
   if ((p.flags & CPB_DBG_CLOCKS) && threadIdx.x == 0) {
     p.scores[2 * blockIdx.x] = static_cast<float>(clock64() - dbg_c0);
     p.scores[2 * blockIdx.x + 1] = static_cast<float>(global_timer_ns() - dbg_t0);
-  }
-  if (p.peer_scores != nullptr && p.done_counter != nullptr && threadIdx.x == 0) {
-    // fused all-gather completion: the last CTA of the grid tells every peer that this rank's slab is complete
-    __threadfence();
-    const unsigned prev = atomicAdd(p.done_counter, 1u);
-    if (prev + 1u == gridDim.x) {
-      *p.done_counter = 0u;  // ready for the next launch (stream ordered)
-      __threadfence_system();
-      for (int pr = 0; pr < p.n_peers; ++pr) {
-        volatile uint32_t* f = reinterpret_cast<volatile uint32_t*>(__ldg(p.peer_scores + pr)) + p.peer_flag_offset + p.my_rank;
-        *f = p.signal_value;
-      }
-    }
   }
   if (warp == 1) {
     tc_fence_after();
@@ -275,45 +258,55 @@ maxsim_kpipe_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 }
 
 
-template <int KP, bool kArgmax>
-static cudaError_t launch_variant(const CUtensorMap& tq, const CUtensorMap& td, const CUtensorMap& tt,
-                                  const MaxSimParams& p, int grid, cudaStream_t stream) {
-  auto kern = maxsim_kpipe_kernel<KP, kArgmax>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<KP>::kAlloc);
-  if (e != cudaSuccess) return e;
-  cudaLaunchConfig_t cfg{};
+static void fill_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int grid, int cluster, int smem,
+                     cudaStream_t stream, int pdl) {
   cfg.gridDim = dim3(static_cast<unsigned>(grid));
   cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = SmemLayout<KP>::kAlloc;
+  cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = static_cast<unsigned>(p.cluster);
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, tq, td, tt, p);
-}
-
-template <int KP>
-static int max_clusters_variant(int cluster) {
-  auto kern = maxsim_kpipe_kernel<KP, false>;
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<KP>::kAlloc) != cudaSuccess) return 0;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(static_cast<unsigned>(cluster));
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = SmemLayout<KP>::kAlloc;
-  cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = static_cast<unsigned>(cluster);
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (pdl != 0) {
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
+}
+
+template <int KP, int kMode>
+static cudaError_t launch_variant(const CUtensorMap& tq, const CUtensorMap& td, const CUtensorMap& tt,
+                                  const MaxSimParams& p, const LossParams& lp, int grid, cudaStream_t stream) {
+  auto kern = maxsim_kpipe_kernel<KP, kMode>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<KP>::kAlloc);
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[2];
+  fill_cfg(cfg, attr, grid, p.cluster, SmemLayout<KP>::kAlloc, stream, p.pdl);
+  return cudaLaunchKernelEx(&cfg, kern, tq, td, tt, p, lp);
+}
+
+template <int KP>
+static int max_clusters_variant(int cluster) {
+  auto kern = maxsim_kpipe_kernel<KP, kModeMax>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<KP>::kAlloc) != cudaSuccess) return 0;
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[2];
+  fill_cfg(cfg, attr, cluster, cluster, SmemLayout<KP>::kAlloc, nullptr, 0);
   int n = 0;
   if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) return 0;
   return n;
+}
+
+template <int KP>
+static cudaError_t launch_mode(const CUtensorMap& tq, const CUtensorMap& td, const CUtensorMap& tt, const MaxSimParams& p,
+                               const LossParams& lp, int mode, int grid, cudaStream_t stream) {
+  if (mode == kModeArgmax) return launch_variant<KP, kModeArgmax>(tq, td, tt, p, lp, grid, stream);
+  if (mode == kModeSmooth) return launch_variant<KP, kModeSmooth>(tq, td, tt, p, lp, grid, stream);
+  return launch_variant<KP, kModeMax>(tq, td, tt, p, lp, grid, stream);
 }
 
 }  // namespace kpipe
@@ -327,14 +320,14 @@ int maxsim_kpipe_max_clusters(int dim_panels, int cluster) {
   }
 }
 
-// dim_panels = padded embedding dim / 64 (3, 4 or 5; dims <= 128 use maxsim_sm100.cu)
+// dim_panels = padded embedding dim / 64 (3, 4 or 5; dims <= 128 use maxsim_sm100.cu); mode as in maxsim_launch
 cudaError_t maxsim_kpipe_launch(const CUtensorMap& tq, const CUtensorMap& td, const CUtensorMap& tt, const MaxSimParams& p,
-                                int dim_panels, bool argmax, int grid, cudaStream_t stream) {
+                                const LossParams& lp, int dim_panels, int mode, int grid, cudaStream_t stream) {
   using namespace kpipe;
   switch (dim_panels) {
-    case 3: return argmax ? launch_variant<3, true>(tq, td, tt, p, grid, stream) : launch_variant<3, false>(tq, td, tt, p, grid, stream);
-    case 4: return argmax ? launch_variant<4, true>(tq, td, tt, p, grid, stream) : launch_variant<4, false>(tq, td, tt, p, grid, stream);
-    case 5: return argmax ? launch_variant<5, true>(tq, td, tt, p, grid, stream) : launch_variant<5, false>(tq, td, tt, p, grid, stream);
+    case 3: return launch_mode<3>(tq, td, tt, p, lp, mode, grid, stream);
+    case 4: return launch_mode<4>(tq, td, tt, p, lp, mode, grid, stream);
+    case 5: return launch_mode<5>(tq, td, tt, p, lp, mode, grid, stream);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -38,16 +38,32 @@ struct MaxSimParams {
   int32_t* split_idx;  // same shape (argmax variant)
   uint32_t* split_flag;  // [q_groups_padded, doc_parts, R, 4]; a slot is valid when it holds `epoch`
   uint32_t epoch;
-  // fused all-gather: scores are stored straight into every peer GPU's slab [n_peers][n_queries][n_docs] over NVLink
+  // fused all-gather: scores are stored straight into every peer GPU's slab over NVLink -- through the NVSwitch
+  // multicast mapping of the symmetric buffer when there is one (one multimem.st reaches every rank), else through
+  // one peer mapping per rank.  All offsets are in 4-byte words from the base of the symmetric buffer.
   const uint64_t* peer_scores;  // device array of n_peers base pointers (symmetric memory), or nullptr
+  uint64_t mc_base;             // multicast address of the same buffer, or 0
   int n_peers;
-  int64_t peer_slab_offset;     // my_rank * n_queries * n_docs (floats)
-  // completion signal of the fused all-gather: the last CTA to finish stores `signal_value` into word
-  // peer_flag_offset + my_rank of every peer's buffer (consumers wait on their own copy)
-  uint32_t* done_counter;       // local device word, zero before the first launch (the last CTA resets it)
-  int64_t peer_flag_offset;     // in 4-byte words from the slab base
-  uint32_t signal_value;
-  int my_rank;
+  int64_t peer_slab_offset;     // first word of gathered[parity][my_rank] ([n_queries, n_docs] floats)
+  // completion: every CTA, once its scores are out, adds 1 (release, system scope) to word peer_flag_offset of every
+  // peer; a consumer waits until its copy of that word has grown by the grid size (cpb_wait_flags)
+  int64_t peer_flag_offset;
+  // write-after-read guard of the double-buffered slab: before its first score store the kernel waits until the LOCAL
+  // flag words wait_flags[0..n_wait) have reached wait_value, i.e. every peer has finished the previous launch (and
+  // therefore, by stream order on the peer, is done with the slab this launch overwrites)
+  const uint32_t* wait_flags;
+  int n_wait;
+  uint32_t wait_value;
+  uint32_t wait_timeout_ms;
+  // fused loss: the last CTA to finish (this counter, reset by it) turns the score matrix into the loss + gradient
+  uint32_t* done_counter;       // local device word, zero before the first launch
+  // smooth-max aggregation (late_interaction_losses.py:40-44): tau * logsumexp(raw / tau) instead of the max
+  float smooth_c;               // log2(e) / tau (0 = hard max)
+  float smooth_out;             // tau * ln 2
+  int nq_real;                  // rows of each query that count (the rest of nq_pad is layout padding)
+  float* lse;                   // [n_docs, q_rows] per-(document, query row) smooth maximum, or nullptr
+  int pdl;                      // programmatic dependent launch: 0 off, 1 wait before the first global access, 2 never wait
+  int boundary_mode;            // epilogue path for tiles holding one document boundary (0 re-read, 1 shifted chunks)
   int dbg_delay;   // profiling only: cycles the epilogue holds an unread accumulator in CPB_DBG_SKIP_EPILOGUE mode
   int mma_split;   // K-steps of a job issued before the next job's barrier waits (5..8)
 };

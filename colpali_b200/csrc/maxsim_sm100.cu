@@ -27,6 +27,7 @@
 //     walk the same document partition in lock-step and each fetches 1/C of every document tile with a
 //     TMA multicast, so a bank byte crosses the L2->SM fabric once per C*R query tiles.
 //   * warp 0: TMA producer.  warp 1: TMEM allocator + MMA issuer.  warps 2-5: epilogue.
+#include <atomic>
 #include <cfloat>
 #include <cstdint>
 #include <cuda.h>
@@ -65,10 +66,10 @@ struct SmemLayout {
   static constexpr int kAlloc = kBytes + 1024;  // slack for manual 1024-B alignment
 };
 
-template <int R, bool kArgmax>
+template <int R, int kMode>
 __global__ void __launch_bounds__(kThreads, 1)
 maxsim_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_d,
-                  const __grid_constant__ CUtensorMap tmap_tail, const MaxSimParams p) {
+                  const __grid_constant__ CUtensorMap tmap_tail, const MaxSimParams p, const LossParams lp) {
   using L = SmemLayout<R>;
   constexpr int S = L::kStages;
 
@@ -136,6 +137,7 @@ maxsim_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   if (C > 1) cluster_sync_all(); else __syncthreads();  // barriers initialised cluster-wide before any multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  maxsim_pdl_entry(p);
   const long long dbg_c0 = clock64();
   const uint64_t dbg_t0 = global_timer_ns();
 
@@ -321,31 +323,14 @@ maxsim_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   } else {
     // ================================ epilogue (maxsim_epilogue.cuh) ==========================
     const CtaSlice sl{g, part, r_cnt, d0, d1, bal_r0, bal_r1};
-    maxsim_epilogue<R, kArgmax>(p, sl, tmem_base, tmem_full, tmem_empty, warp, lane);
+    maxsim_epilogue<R, kMode>(p, sl, tmem_base, tmem_full, tmem_empty, warp, lane);
   }
 
   // ---- teardown ---------------------------------------------------------------------------
-  if (p.peer_scores != nullptr && p.done_counter != nullptr && warp >= 2)
-    __threadfence_system();  // my peer stores are ordered before the completion signal below
-  tc_fence_before();
-  // no CTA may exit while a peer can still multicast into its shared memory or signal its barriers
-  if (C > 1) cluster_sync_all(); else __syncthreads();
+  maxsim_finish(p, lp, C, warp);
   if ((p.flags & CPB_DBG_CLOCKS) && threadIdx.x == 0) {
     p.scores[2 * blockIdx.x] = static_cast<float>(clock64() - dbg_c0);
     p.scores[2 * blockIdx.x + 1] = static_cast<float>(global_timer_ns() - dbg_t0);
-  }
-  if (p.peer_scores != nullptr && p.done_counter != nullptr && threadIdx.x == 0) {
-    // fused all-gather completion: the last CTA of the grid tells every peer that this rank's slab is complete
-    __threadfence();
-    const unsigned prev = atomicAdd(p.done_counter, 1u);
-    if (prev + 1u == gridDim.x) {
-      *p.done_counter = 0u;  // ready for the next launch (stream ordered)
-      __threadfence_system();
-      for (int pr = 0; pr < p.n_peers; ++pr) {
-        volatile uint32_t* f = reinterpret_cast<volatile uint32_t*>(__ldg(p.peer_scores + pr)) + p.peer_flag_offset + p.my_rank;
-        *f = p.signal_value;
-      }
-    }
   }
   if (warp == 1) {
     tc_fence_after();
@@ -355,17 +340,29 @@ maxsim_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
 
 // Wait (on the stream) until flags[0..n) have all reached `value` (launch counters only grow; wrap-safe compare):
 // consumer side of the fused all-gather.
-__global__ void wait_flags_kernel(const uint32_t* flags, int n, uint32_t value) {
+// values[i] is what flags[i] must have reached (nullptr: `value` for all).  A peer that is late is not an error (first
+// call set-up, a straggler): the wait reports a time-out through *status instead of trapping, after timeout_ms.
+__global__ void wait_flags_kernel(const uint32_t* flags, const uint32_t* values, int n, uint32_t value,
+                                  uint32_t timeout_ms, uint32_t* status) {
   if (threadIdx.x >= n) return;
-  const volatile uint32_t* f = flags + threadIdx.x;
+  const uint32_t* f = flags + threadIdx.x;
+  const uint32_t want = values ? values[threadIdx.x] : value;
   const uint64_t t0 = global_timer_ns();
-  while (static_cast<int32_t>(*f - value) < 0) {
-    if (global_timer_ns() - t0 > 4000000000ull) __trap();
+  const uint64_t limit = static_cast<uint64_t>(timeout_ms) * 1000000ull;
+  while (true) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+    if (static_cast<int32_t>(v - want) >= 0) break;
+    if (global_timer_ns() - t0 > limit) {
+      if (status) atomicOr(status, 1u << (threadIdx.x & 31));
+      break;
+    }
+    __nanosleep(64);
   }
-  __threadfence_system();
 }
-cudaError_t wait_flags_launch(const uint32_t* flags, int n, uint32_t value, cudaStream_t stream) {
-  wait_flags_kernel<<<1, 64, 0, stream>>>(flags, n, value);
+cudaError_t wait_flags_launch(const uint32_t* flags, const uint32_t* values, int n, uint32_t value, uint32_t timeout_ms,
+                              uint32_t* status, cudaStream_t stream) {
+  wait_flags_kernel<<<1, 64, 0, stream>>>(flags, values, n, value, timeout_ms, status);
   return cudaGetLastError();
 }
 
@@ -381,7 +378,7 @@ __global__ void maxsim_reduce_segments_kernel(const float* __restrict__ partial,
 
 template <int R>
 static void fill_cluster_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int grid, int cluster,
-                             cudaStream_t stream) {
+                             cudaStream_t stream, int pdl = 0) {
   cfg.gridDim = dim3(static_cast<unsigned>(grid));
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = SmemLayout<R>::kAlloc;
@@ -392,44 +389,54 @@ static void fill_cluster_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr,
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (pdl != 0) {  // this launch may start while the previous kernel of the stream is still draining
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
 }
 
-template <int R, bool kArgmax>
+template <int R, int kMode>
 static cudaError_t launch_variant(const CUtensorMap& tq, const CUtensorMap& td, const CUtensorMap& tt,
-                                  const MaxSimParams& p, int grid, cudaStream_t stream) {
-  auto kern = maxsim_fwd_kernel<R, kArgmax>;
-  static bool attr_set[64] = {};  // per instantiation and per device: the attribute is sticky once set
+                                  const MaxSimParams& p, const LossParams& lp, int grid, cudaStream_t stream) {
+  auto kern = maxsim_fwd_kernel<R, kMode>;
+  // per instantiation and per device: the attribute is sticky once set (atomic: launches may come from several threads)
+  static std::atomic<bool> attr_set[64];
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
-  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+  if (dev < 0 || dev >= 64 || !attr_set[dev].load(std::memory_order_acquire)) {
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<R>::kAlloc);
     if (e != cudaSuccess) return e;
-    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    if (dev >= 0 && dev < 64) attr_set[dev].store(true, std::memory_order_release);
   }
   cudaLaunchConfig_t cfg{};
-  cudaLaunchAttribute attr[1];
-  fill_cluster_cfg<R>(cfg, attr, grid, p.cluster, stream);
-  return cudaLaunchKernelEx(&cfg, kern, tq, td, tt, p);
+  cudaLaunchAttribute attr[2];
+  fill_cluster_cfg<R>(cfg, attr, grid, p.cluster, stream, p.pdl);
+  return cudaLaunchKernelEx(&cfg, kern, tq, td, tt, p, lp);
 }
 
+// mode: kModeMax / kModeArgmax / kModeSmooth (maxsim_epilogue.cuh)
 cudaError_t maxsim_launch(const CUtensorMap& tq, const CUtensorMap& td, const CUtensorMap& tt, const MaxSimParams& p,
-                          int r, bool argmax, int grid, cudaStream_t stream) {
-  if (r == 1)
-    return argmax ? launch_variant<1, true>(tq, td, tt, p, grid, stream)
-                  : launch_variant<1, false>(tq, td, tt, p, grid, stream);
-  return argmax ? launch_variant<2, true>(tq, td, tt, p, grid, stream)
-                : launch_variant<2, false>(tq, td, tt, p, grid, stream);
+                          const LossParams& lp, int r, int mode, int grid, cudaStream_t stream) {
+  if (r == 1) {
+    if (mode == kModeArgmax) return launch_variant<1, kModeArgmax>(tq, td, tt, p, lp, grid, stream);
+    if (mode == kModeSmooth) return launch_variant<1, kModeSmooth>(tq, td, tt, p, lp, grid, stream);
+    return launch_variant<1, kModeMax>(tq, td, tt, p, lp, grid, stream);
+  }
+  if (mode == kModeArgmax) return launch_variant<2, kModeArgmax>(tq, td, tt, p, lp, grid, stream);
+  if (mode == kModeSmooth) return launch_variant<2, kModeSmooth>(tq, td, tt, p, lp, grid, stream);
+  return launch_variant<2, kModeMax>(tq, td, tt, p, lp, grid, stream);
 }
 
 // How many clusters of `cluster` CTAs can be co-resident (persistent-grid sizing).
 template <int R>
 static int max_clusters_variant(int cluster) {
-  auto kern = maxsim_fwd_kernel<R, false>;
+  auto kern = maxsim_fwd_kernel<R, kModeMax>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<R>::kAlloc) != cudaSuccess)
     return 0;
   cudaLaunchConfig_t cfg{};
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   fill_cluster_cfg<R>(cfg, attr, cluster, cluster, nullptr);
   int n = 0;
   if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) return 0;

@@ -25,7 +25,7 @@ import torch
 from . import _lib
 
 HEAD_DIM = 128      # the validated kernel (head_sm100.cu)
-MAX_HEAD_DIM = 320  # DRAFT: multiples of 32 above 128 go through head_wide_sm100.cu (ColQwen3: 320)
+MAX_HEAD_DIM = 320  # multiples of 32 above 128 go through head_wide_sm100.cu (ColQwen3: 320)
 
 
 def _supported_dim(dim: int) -> bool:

@@ -10,92 +10,166 @@ Mirrors ``colpali_engine/loss/late_interaction_losses.py`` (reference @ 9be8f19)
 * ``ColbertSigmoidLoss``      :401-465
 
 Same constructor keyword arguments, same ``forward(query_embeddings, doc_embeddings, offset=0)``.  The
-``einsum("bnd,csd->bcns")`` / ``amax`` / ``sum`` of :153-154 and everything after it run as
+``einsum("bnd,csd->bcns")`` / ``amax`` (or ``tau * logsumexp`` with ``use_smooth_max=True``, :40-44) / ``sum`` of
+:153-154 and everything after it run as
 
-1. the fused sm_100a MaxSim kernel (csrc/maxsim_sm100.cu), which also records, per (document, query token),
-   the index of the winning document token (int32 ``[C, B*N_q]`` instead of the reference's saved
-   ``[B, C, N_q, N_d]`` similarity tensor);
-2. one small kernel (csrc/loss_sm100.cu) that turns the ``[B, C]`` sums into the scalar loss *and* its gradient
-   with respect to the sums;
-3. in backward, a gather kernel for ``dQ`` and a scatter-add kernel for ``dD``.
+1. ONE launch of the fused sm_100a MaxSim kernel (csrc/maxsim_sm100.cu; csrc/maxsim_kpipe_sm100.cu for embedding dims
+   above 128) whose last CTA turns the ``[B, C]`` sums into the scalar loss *and* its gradient with respect to the
+   sums (csrc/loss_body.cuh).  For the backward it records, per (document, query token), either the index of the
+   winning document token (int32) or the smooth maximum (fp32) -- ``[C, B*N_q]`` instead of the reference's saved
+   ``[B, C, N_q, N_d]`` similarity tensor.  (Queries longer than 32 tokens and the explicit-negative losses, which need
+   two score matrices, run the loss as its own small kernel, csrc/loss_sm100.cu.)
+2. in backward, hard max: a gather kernel for ``dQ`` and a per-document counting-sort kernel that writes every row of
+   ``dD`` once (csrc/loss_sm100.cu); smooth max: two kernels that recompute the similarity tiles on the tensor cores
+   and apply the softmax weights (csrc/smooth_bwd_sm100.cu, embedding dim 128).
 
 Differences from the reference that a caller can observe, all documented in DESIGN.md:
 the loss is returned in fp32 whatever the embedding dtype (the reference returns the embedding dtype);
-embeddings are contracted in bf16 with fp32 accumulation; ``use_smooth_max=True`` is not implemented yet and
-raises; where several document tokens tie for the maximum the gradient goes to the first one (``amax`` splits
-it evenly) -- this only differs on all-zero (padding) rows, whose gradients the model masks anyway.
+embeddings are contracted in bf16 with fp32 accumulation; where several document tokens tie for the maximum the
+gradient goes to the first one (``amax`` splits it evenly) -- this only differs on all-zero (padding) rows, whose
+gradients the model masks anyway.
 """
 
 from __future__ import annotations
 
+import ctypes
+
 import torch
 
 from . import _lib
-from .scoring import DocBank, QueryBlock, maxsim
+from .scoring import DocBank, QueryBlock, launch_maxsim
+
+
+_DONE_COUNTERS: dict = {}
+
+
+def _done_counter(dev: torch.device) -> torch.Tensor:
+    """Device word the fused loss uses to find the last CTA, one per (device, stream) (the kernel resets it)."""
+    key = (str(dev), torch.cuda.current_stream(dev).cuda_stream)
+    t = _DONE_COUNTERS.get(key)
+    if t is None:
+        t = torch.zeros(1, dtype=torch.int32, device=dev)
+        _DONE_COUNTERS[key] = t
+    return t
+
+
+def _loss_desc(mode, temperature, normalize, filt, thr, factor, offset, loss, grad, bounds=None, neg_scores=None,
+               n_neg=0, weight=1.0, grad_neg=None) -> _lib.LossDesc:
+    d = _lib.LossDesc()
+    d.mode, d.normalize_scores, d.pos_aware_negative_filtering, d.offset = int(mode), int(normalize), int(filt), int(offset)
+    d.temperature, d.filter_threshold, d.filter_factor = float(temperature), float(thr), float(factor)
+    d.d_neg_scores = neg_scores.data_ptr() if neg_scores is not None else None
+    d.n_neg, d.in_batch_term_weight = int(n_neg), float(weight)
+    d.d_loss = loss.data_ptr()
+    d.d_grad_scores = grad.data_ptr() if grad is not None else None
+    d.d_grad_neg_scores = grad_neg.data_ptr() if grad_neg is not None else None
+    d.d_bounds = bounds.data_ptr() if bounds is not None else None
+    return d
+
+
+def _maxsim_for_loss(qb: QueryBlock, bank: DocBank, need_grad: bool, smooth_tau: float, nq_real: int,
+                     loss_desc=None):
+    """One fused MaxSim launch; returns (scores, aux) with aux = int32 argmax (hard max) or fp32 lse (smooth max), the
+    only per-(document, query row) state the backward needs.  With ``loss_desc`` the last CTA also emits the loss."""
+    dev = bank.device
+    scores = torch.empty(qb.n, bank.n_docs, dtype=torch.float32, device=dev)
+    aux = None
+    if need_grad:
+        aux = torch.empty(bank.n_docs, qb.n * qb.nq_pad, dtype=torch.float32 if smooth_tau > 0 else torch.int32, device=dev)
+    launch_maxsim(qb, bank, scores=scores, argmax=aux if smooth_tau == 0 else None, lse=aux if smooth_tau > 0 else None,
+                  smooth_tau=smooth_tau, nq_real=nq_real, loss=loss_desc,
+                  done_counter=_done_counter(dev) if loss_desc is not None else None)
+    return scores, aux
+
+
+def _maxsim_backward(g, go, aux, smooth_tau, nq_real, q_flat, b, nq_pad, bank_flat, bank_start, bank_len, n_docs,
+                     max_len, need_dq, need_dd):
+    """dq [b * nq_pad, dim], dd [rows, dim] (fp32, fully written by the kernels) for one score matrix."""
+    dev = q_flat.device
+    dim = q_flat.shape[1]
+    dq = torch.empty(b * nq_pad, dim, dtype=torch.float32, device=dev) if need_dq else None
+    dd = torch.empty(bank_flat.shape[0], dim, dtype=torch.float32, device=dev) if need_dd else None
+    if not (need_dq or need_dd):
+        return None, None
+    a = _lib.MaxSimBwdArgs()
+    a.flags = _lib.CPB_FLAG_CONTIGUOUS  # the banks of the losses are dense [C, L, D] tensors
+    a.d_grad_scores, a.d_grad_out = g.data_ptr(), go.data_ptr()
+    if smooth_tau > 0:
+        a.d_lse, a.smooth_tau = aux.data_ptr(), float(smooth_tau)
+    else:
+        a.d_argmax = aux.data_ptr()
+    a.d_q, a.n_queries, a.nq_pad, a.nq_real, a.dim = q_flat.data_ptr(), b, nq_pad, int(nq_real), dim
+    a.d_docs, a.doc_rows = bank_flat.data_ptr(), bank_flat.shape[0]
+    a.d_doc_start, a.d_doc_len, a.n_docs, a.max_doc_len = bank_start.data_ptr(), bank_len.data_ptr(), n_docs, int(max_len)
+    a.d_dq = dq.data_ptr() if need_dq else None
+    a.d_dd = dd.data_ptr() if need_dd else None
+    with torch.cuda.device(dev):
+        a.stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = _lib.load().cpb_maxsim_bwd_launch(ctypes.byref(a))
+    _lib.check(rc, "cpb_maxsim_bwd_launch")
+    _lib.count_launches(int(need_dq) + int(need_dd))
+    return dq, dd
+
+
+def _check_inputs(q, d, neg=None):
+    if q.dim() != 3 or d.dim() != 3 or (neg is not None and neg.dim() != 4):
+        raise ValueError("expected [B, N_q, D], [C, N_d, D] (and [B, n_neg, N_neg, D]) embeddings, got "
+                         f"{tuple(q.shape)} / {tuple(d.shape)}" + (f" / {tuple(neg.shape)}" if neg is not None else ""))
+    dev = q.device
+    if dev.type != "cuda" or d.device != dev or (neg is not None and neg.device != dev):
+        raise _lib.ColpaliB200Error("colpali_b200 losses need all embeddings on the same CUDA device")
+    return dev
 
 
 class _InBatchLossFn(torch.autograd.Function):
+    """ColbertLoss / ColbertPairwiseCELoss / ColbertSigmoidLoss: ONE kernel launch forward -- the fused MaxSim kernel
+    whose last CTA turns the [B, C] score matrix into the loss and d loss / d scores (queries of up to 32 tokens; longer
+    queries add the segment-sum and loss kernels)."""
+
     @staticmethod
-    def forward(ctx, q, d, offset, mode, temperature, normalize, filt, thr, factor, bounds_out):
-        if q.dim() != 3 or d.dim() != 3:
-            raise ValueError(f"expected [B, N_q, D] and [C, N_d, D] embeddings, got {tuple(q.shape)} / {tuple(d.shape)}")
-        dev = q.device
-        if dev.type != "cuda" or d.device != dev:
-            raise _lib.ColpaliB200Error("colpali_b200 losses need query and document embeddings on the same CUDA device")
-        lib = _lib.load()
+    def forward(ctx, q, d, offset, mode, temperature, normalize, filt, thr, factor, bounds_out, smooth_tau):
+        dev = _check_inputs(q, d)
         qb = QueryBlock(q.detach(), dev)
         bank = DocBank.from_passages(d.detach(), dev)  # dense [C, L, D]: zero (padding) rows are ordinary tokens,
-        # they score exactly 0 and take part in the max, as in the reference
+        # they score exactly 0 and take part in the max / log-sum-exp, as in the reference
         need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
-        if need_grad:
-            scores, argmax = maxsim(qb, bank, want_argmax=True)
-        else:
-            scores, argmax = maxsim(qb, bank), None
         b, c = qb.n, bank.n_docs
         loss = torch.empty(1, dtype=torch.float32, device=dev)
         g = torch.empty(b, c, dtype=torch.float32, device=dev) if need_grad else None
-        with torch.cuda.device(dev):
-            rc = lib.cpb_colbert_loss_fwd_dim(
-                scores.data_ptr(), qb.flat.data_ptr(), b, qb.nq_pad, c, mode,
-                float(temperature), int(normalize), int(filt), float(thr), float(factor), int(offset),
-                loss.data_ptr(), g.data_ptr() if g is not None else None,
-                bounds_out.data_ptr() if bounds_out is not None else None,
-                qb.flat.shape[1], torch.cuda.current_stream(dev).cuda_stream,
-            )
-        _lib.check(rc, "cpb_colbert_loss_fwd_dim")
-        _lib.count_launches(1)
+        nq_real = int(q.shape[1])
+        if qb.nq_pad == 32:
+            desc = _loss_desc(mode, temperature, normalize, filt, thr, factor, offset, loss, g, bounds_out)
+            _, aux = _maxsim_for_loss(qb, bank, need_grad, smooth_tau, nq_real, loss_desc=desc)
+        else:
+            scores, aux = _maxsim_for_loss(qb, bank, need_grad, smooth_tau, nq_real)
+            desc = _loss_desc(mode, temperature, normalize, filt, thr, factor, offset, loss, g, bounds_out)
+            with torch.cuda.device(dev):
+                rc = _lib.load().cpb_colbert_loss_launch(ctypes.byref(desc), scores.data_ptr(), qb.flat.data_ptr(), b,
+                                                         qb.nq_pad, c, qb.flat.shape[1],
+                                                         torch.cuda.current_stream(dev).cuda_stream)
+            _lib.check(rc, "cpb_colbert_loss_launch")
+            _lib.count_launches(1)
         if need_grad:
-            ctx.save_for_backward(qb.flat, bank.flat, bank.start, argmax, g)
-            ctx.meta = (qb.n, qb.nq_pad, c, tuple(q.shape), tuple(d.shape), q.dtype, d.dtype)
+            ctx.save_for_backward(qb.flat, bank.flat, bank.start, bank.length, aux, g)
+            ctx.meta = (b, qb.nq_pad, nq_real, c, bank.max_len, float(smooth_tau), tuple(q.shape), tuple(d.shape),
+                        q.dtype, d.dtype)
         return loss[0]
 
     @staticmethod
     def backward(ctx, grad_out):
-        q_flat, d_flat, d_start, argmax, g = ctx.saved_tensors
-        b, nq_pad, c, q_shape, d_shape, q_dtype, d_dtype = ctx.meta
-        dev = q_flat.device
-        lib = _lib.load()
+        q_flat, d_flat, d_start, d_len, aux, g = ctx.saved_tensors
+        b, nq_pad, nq_real, c, max_len, smooth_tau, q_shape, d_shape, q_dtype, d_dtype = ctx.meta
         want_q, want_d = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         dim = q_flat.shape[1]  # padded embedding dim (128, or 192 / 256 / 320 for wide models)
-        dq = torch.empty(b * nq_pad, dim, dtype=torch.float32, device=dev) if want_q else None
-        dd = torch.zeros(d_flat.shape[0], dim, dtype=torch.float32, device=dev) if want_d else None
         go = grad_out.detach().to(torch.float32).reshape(1).contiguous()
-        with torch.cuda.device(dev):
-            rc = lib.cpb_maxsim_bwd_dim(
-                g.data_ptr(), go.data_ptr(), argmax.data_ptr(),
-                q_flat.data_ptr(), b, nq_pad,
-                d_flat.data_ptr(), d_flat.shape[0], d_start.data_ptr(), c,
-                dq.data_ptr() if dq is not None else None, dd.data_ptr() if dd is not None else None,
-                dim, torch.cuda.current_stream(dev).cuda_stream,
-            )
-        _lib.check(rc, "cpb_maxsim_bwd_dim")
-        _lib.count_launches(int(want_q) + int(want_d))
+        dq, dd = _maxsim_backward(g, go, aux, smooth_tau, nq_real, q_flat, b, nq_pad, d_flat, d_start, d_len, c, max_len,
+                                  want_q, want_d)
         grad_q = grad_d = None
         if want_q:
             grad_q = dq.view(b, nq_pad, dim)[:, : q_shape[1], : q_shape[2]].to(q_dtype)
         if want_d:
             grad_d = dd.view(d_shape[0], d_shape[1], dim)[:, :, : d_shape[2]].to(d_dtype)
-        return grad_q, grad_d, None, None, None, None, None, None, None, None
+        return (grad_q, grad_d) + (None,) * 9
 
 
 class _NegLossFn(torch.autograd.Function):
@@ -103,70 +177,48 @@ class _NegLossFn(torch.autograd.Function):
     negatives of all queries (only the block diagonal is used), one loss kernel for both score matrices."""
 
     @staticmethod
-    def forward(ctx, q, d, neg, offset, inner_mode, temperature, normalize, filt, thr, factor, weight):
-        if q.dim() != 3 or d.dim() != 3 or neg.dim() != 4:
-            raise ValueError("expected [B, N_q, D], [C, N_d, D] and [B, n_neg, N_neg, D] embeddings, got "
-                             f"{tuple(q.shape)} / {tuple(d.shape)} / {tuple(neg.shape)}")
+    def forward(ctx, q, d, neg, offset, inner_mode, temperature, normalize, filt, thr, factor, weight, smooth_tau):
+        dev = _check_inputs(q, d, neg)
         if neg.shape[0] != q.shape[0]:
             raise ValueError(f"{neg.shape[0]} negative groups for {q.shape[0]} queries")
-        dev = q.device
-        if dev.type != "cuda" or d.device != dev or neg.device != dev:
-            raise _lib.ColpaliB200Error("colpali_b200 losses need all embeddings on the same CUDA device")
-        lib = _lib.load()
         qb = QueryBlock(q.detach(), dev)
         bank = DocBank.from_passages(d.detach(), dev)
         b, n_neg = neg.shape[0], neg.shape[1]
         nbank = DocBank.from_passages(neg.detach().reshape(b * n_neg, neg.shape[2], neg.shape[3]), dev)
         need_grad = any(ctx.needs_input_grad[:3])
-        if need_grad:
-            s_pos, am_pos = maxsim(qb, bank, want_argmax=True)
-            s_neg, am_neg = maxsim(qb, nbank, want_argmax=True)
-        else:
-            s_pos, s_neg, am_pos, am_neg = maxsim(qb, bank), maxsim(qb, nbank), None, None
+        nq_real = int(q.shape[1])
+        s_pos, aux_pos = _maxsim_for_loss(qb, bank, need_grad, smooth_tau, nq_real)
+        s_neg, aux_neg = _maxsim_for_loss(qb, nbank, need_grad, smooth_tau, nq_real)
         c = bank.n_docs
         loss = torch.empty(1, dtype=torch.float32, device=dev)
         g_pos = torch.empty(b, c, dtype=torch.float32, device=dev) if need_grad else None
         g_neg = torch.empty(b, b * n_neg, dtype=torch.float32, device=dev) if need_grad else None
+        desc = _loss_desc(inner_mode, temperature, normalize, filt, thr, factor, offset, loss, g_pos, None, s_neg, n_neg,
+                          weight, g_neg)
         with torch.cuda.device(dev):
-            rc = lib.cpb_colbert_neg_loss_fwd_dim(
-                s_pos.data_ptr(), s_neg.data_ptr(), qb.flat.data_ptr(), b, qb.nq_pad, c, n_neg, inner_mode,
-                float(temperature), int(normalize), int(filt), float(thr), float(factor), float(weight), int(offset),
-                loss.data_ptr(), g_pos.data_ptr() if need_grad else None, g_neg.data_ptr() if need_grad else None,
-                qb.flat.shape[1], torch.cuda.current_stream(dev).cuda_stream,
-            )
-        _lib.check(rc, "cpb_colbert_neg_loss_fwd_dim")
+            rc = _lib.load().cpb_colbert_loss_launch(ctypes.byref(desc), s_pos.data_ptr(), qb.flat.data_ptr(), b, qb.nq_pad,
+                                                     c, qb.flat.shape[1], torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(rc, "cpb_colbert_loss_launch")
         _lib.count_launches(1)
         if need_grad:
-            ctx.save_for_backward(qb.flat, bank.flat, bank.start, am_pos, g_pos, nbank.flat, nbank.start, am_neg, g_neg)
-            ctx.meta = (b, qb.nq_pad, c, b * n_neg, tuple(q.shape), tuple(d.shape), tuple(neg.shape), q.dtype, d.dtype, neg.dtype)
+            ctx.save_for_backward(qb.flat, bank.flat, bank.start, bank.length, aux_pos, g_pos, nbank.flat, nbank.start,
+                                  nbank.length, aux_neg, g_neg)
+            ctx.meta = (b, qb.nq_pad, nq_real, c, b * n_neg, bank.max_len, nbank.max_len, float(smooth_tau), tuple(q.shape),
+                        tuple(d.shape), tuple(neg.shape), q.dtype, d.dtype, neg.dtype)
         return loss[0]
 
     @staticmethod
     def backward(ctx, grad_out):
-        q_flat, d_flat, d_start, am_pos, g_pos, n_flat, n_start, am_neg, g_neg = ctx.saved_tensors
-        b, nq_pad, c, cn, q_shape, d_shape, n_shape, q_dtype, d_dtype, n_dtype = ctx.meta
-        dev = q_flat.device
-        lib = _lib.load()
+        (q_flat, d_flat, d_start, d_len, aux_pos, g_pos, n_flat, n_start, n_len, aux_neg, g_neg) = ctx.saved_tensors
+        (b, nq_pad, nq_real, c, cn, max_len, nmax_len, smooth_tau, q_shape, d_shape, n_shape, q_dtype, d_dtype,
+         n_dtype) = ctx.meta
         want_q, want_d, want_n = ctx.needs_input_grad[:3]
         go = grad_out.detach().to(torch.float32).reshape(1).contiguous()
-        stream = torch.cuda.current_stream(dev).cuda_stream
         dim = q_flat.shape[1]
-
-        def bwd(g, am, flat, start, n_docs, need_dq, need_dd):
-            dq = torch.empty(b * nq_pad, dim, dtype=torch.float32, device=dev) if need_dq else None
-            dd = torch.zeros(flat.shape[0], dim, dtype=torch.float32, device=dev) if need_dd else None
-            if need_dq or need_dd:
-                with torch.cuda.device(dev):
-                    rc = lib.cpb_maxsim_bwd_dim(g.data_ptr(), go.data_ptr(), am.data_ptr(), q_flat.data_ptr(), b, nq_pad,
-                                                flat.data_ptr(), flat.shape[0], start.data_ptr(), n_docs,
-                                                dq.data_ptr() if need_dq else None, dd.data_ptr() if need_dd else None,
-                                                dim, stream)
-                _lib.check(rc, "cpb_maxsim_bwd_dim")
-                _lib.count_launches(int(need_dq) + int(need_dd))
-            return dq, dd
-
-        dq1, dd = bwd(g_pos, am_pos, d_flat, d_start, c, want_q, want_d)
-        dq2, dn = bwd(g_neg, am_neg, n_flat, n_start, cn, want_q, want_n)
+        dq1, dd = _maxsim_backward(g_pos, go, aux_pos, smooth_tau, nq_real, q_flat, b, nq_pad, d_flat, d_start, d_len, c,
+                                   max_len, want_q, want_d)
+        dq2, dn = _maxsim_backward(g_neg, go, aux_neg, smooth_tau, nq_real, q_flat, b, nq_pad, n_flat, n_start, n_len, cn,
+                                   nmax_len, want_q, want_n)
         grad_q = grad_d = grad_n = None
         if want_q:
             grad_q = (dq1 + dq2).view(b, nq_pad, dim)[:, : q_shape[1], : q_shape[2]].to(q_dtype)
@@ -174,7 +226,7 @@ class _NegLossFn(torch.autograd.Function):
             grad_d = dd.view(d_shape[0], d_shape[1], dim)[:, :, : d_shape[2]].to(d_dtype)
         if want_n:
             grad_n = dn.view(n_shape[0], n_shape[1], n_shape[2], dim)[..., : n_shape[3]].to(n_dtype)
-        return (grad_q, grad_d, grad_n) + (None,) * 8
+        return (grad_q, grad_d, grad_n) + (None,) * 9
 
 
 class ColbertModule(torch.nn.Module):
@@ -194,14 +246,10 @@ class ColbertModule(torch.nn.Module):
 
     # -- shared fused path ------------------------------------------------------------------------------
     def _fused_in_batch_loss(self, mode: int, q: torch.Tensor, d: torch.Tensor, offset: int) -> torch.Tensor:
-        if self.use_smooth_max:
-            raise NotImplementedError(
-                "use_smooth_max=True (tau * logsumexp instead of amax, late_interaction_losses.py:40-44) is not "
-                "implemented in the fused sm_100a path yet; use the reference module for it."
-            )
         bounds = torch.empty(2, dtype=torch.float32, device=q.device) if (self.check_bounds and self.normalize_scores) else None
         loss = _InBatchLossFn.apply(q, d, int(offset), mode, self.temperature, self.normalize_scores,
-                                    self.pos_aware_negative_filtering, self.filter_threshold, self.filter_factor, bounds)
+                                    self.pos_aware_negative_filtering, self.filter_threshold, self.filter_factor, bounds,
+                                    float(self.tau) if self.use_smooth_max else 0.0)
         if bounds is not None:
             mn, mx = bounds.tolist()
             if mn < -self.norm_tol or mx > 1 + self.norm_tol:
@@ -277,11 +325,10 @@ class _NegativeLossBase(ColbertModule):
 
     def forward(self, query_embeddings: torch.Tensor, doc_embeddings: torch.Tensor, neg_doc_embeddings: torch.Tensor,
                 offset: int = 0) -> torch.Tensor:
-        if self.use_smooth_max:
-            raise NotImplementedError("use_smooth_max=True is not implemented in the fused sm_100a path yet")
         return _NegLossFn.apply(query_embeddings, doc_embeddings, neg_doc_embeddings, int(offset), self._inner_mode,
                                 self.temperature, self.normalize_scores, self.pos_aware_negative_filtering,
-                                self.filter_threshold, self.filter_factor, self.in_batch_term_weight)
+                                self.filter_threshold, self.filter_factor, self.in_batch_term_weight,
+                                float(self.tau) if self.use_smooth_max else 0.0)
 
 
 class ColbertNegativeCELoss(_NegativeLossBase):

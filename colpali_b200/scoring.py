@@ -14,6 +14,7 @@ per-token maximum is ``max(real, 0)``).  ``DocBank`` records that as a per-docum
 
 from __future__ import annotations
 
+import ctypes
 from typing import List, Optional, Union
 
 import torch
@@ -44,7 +45,7 @@ def _resolve_device(device: Optional[Union[str, torch.device]]) -> torch.device:
     return device
 
 
-MAX_EMBED_DIM = 320  # ColQwen3 (DRAFT: dims above 128 go through the K-pipelined kernel, cpb_maxsim_fwd_dim)
+MAX_EMBED_DIM = 320  # ColQwen3; dims above 128 go through the K-pipelined kernel (csrc/maxsim_kpipe_sm100.cu)
 
 
 def _padded_dim(d: int) -> int:
@@ -180,51 +181,79 @@ _SPLIT_WS: dict = {}
 _EPOCH = [0]
 
 
-def _split_workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
-    """Per-device exchange buffer for documents cut by a partition boundary (zeroed once, reused: slots are tagged
-    with a per-call epoch).  Calls that share it must be stream-ordered, which they are on one PyTorch stream."""
-    ws = _SPLIT_WS.get(str(dev))
+def _split_workspace(dev: torch.device, stream_id: int, nbytes: int) -> torch.Tensor:
+    """Exchange buffer for documents cut by a partition boundary, one per (device, stream): launches that share it
+    are stream-ordered (zeroed once, reused: slots are tagged with a per-launch epoch)."""
+    key = (str(dev), stream_id)
+    ws = _SPLIT_WS.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
-        _SPLIT_WS[str(dev)] = ws
+        _SPLIT_WS[key] = ws
     return ws
 
 
-def maxsim(q: QueryBlock, bank: DocBank, *, round_bf16: bool = False, want_argmax: bool = False):
-    """Run the fused kernel.  Returns device fp32 ``[n_queries, n_docs]`` (and int32 argmax
-    ``[n_docs, n_queries * nq_pad]`` when asked)."""
+def next_epoch() -> int:
+    _EPOCH[0] = _EPOCH[0] % 0xFFFFFFF0 + 1
+    return _EPOCH[0]
+
+
+def launch_maxsim(q: "QueryBlock", bank: "DocBank", *, scores: Optional[torch.Tensor], argmax: Optional[torch.Tensor] = None,
+                  lse: Optional[torch.Tensor] = None, round_bf16: bool = False, independent: bool = False,
+                  smooth_tau: float = 0.0, nq_real: int = 0, loss: Optional[_lib.LossDesc] = None,
+                  done_counter: Optional[torch.Tensor] = None, gather: Optional[dict] = None) -> int:
+    """Fill a ``cpb_maxsim_args`` and enqueue the fused kernel on the current stream of ``bank.device``.
+    Returns the number of CTAs launched (the fused all-gather's consumers count completions in CTAs)."""
     lib = _lib.load()
     dev = bank.device
     dim = int(bank.flat.shape[1])
     if q.flat.shape[1] != dim:
         raise ValueError(f"queries have (padded) dim {q.flat.shape[1]}, documents {dim}")
-    scores = torch.empty(q.n, bank.n_docs, dtype=torch.float32, device=dev)
-    argmax = torch.empty(bank.n_docs, q.n * q.nq_pad, dtype=torch.int32, device=dev) if want_argmax else None
     ws_bytes = lib.cpb_maxsim_workspace_bytes(q.n, q.nq_pad, bank.n_docs)
     ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev) if ws_bytes else None
-    flags = (_lib.CPB_FLAG_ROUND_BF16 if round_bf16 else 0) | (_lib.CPB_FLAG_CONTIGUOUS if bank.contiguous else 0)
+    a = _lib.MaxSimArgs()
+    a.flags = ((_lib.CPB_FLAG_ROUND_BF16 if round_bf16 else 0) | (_lib.CPB_FLAG_CONTIGUOUS if bank.contiguous else 0)
+               | (_lib.CPB_FLAG_INDEPENDENT if independent else 0))
+    a.d_q, a.n_queries, a.nq_pad, a.nq_real, a.dim = q.flat.data_ptr(), q.n, q.nq_pad, int(nq_real), dim
+    a.d_docs, a.doc_rows = bank.flat.data_ptr(), bank.flat.shape[0]
+    a.d_doc_start, a.d_doc_len = bank.start.data_ptr(), bank.length.data_ptr()
+    a.d_doc_floor = bank.floor.data_ptr() if bank.floor is not None else None
+    a.n_docs, a.uniform_len, a.max_doc_len = bank.n_docs, bank.uniform_len, bank.max_len
+    a.d_scores = scores.data_ptr() if scores is not None else None
+    a.d_argmax = argmax.data_ptr() if argmax is not None else None
+    a.d_lse = lse.data_ptr() if lse is not None else None
+    a.d_workspace = ws.data_ptr() if ws is not None else None
+    a.smooth_tau = float(smooth_tau)
     with torch.cuda.device(dev):
-        stream = torch.cuda.current_stream(dev).cuda_stream
-        common = (
-            q.flat.data_ptr(), q.n, q.nq_pad,
-            bank.flat.data_ptr(), bank.flat.shape[0],
-            bank.start.data_ptr(), bank.length.data_ptr(),
-            bank.floor.data_ptr() if bank.floor is not None else None, bank.n_docs,
-            scores.data_ptr(), argmax.data_ptr() if argmax is not None else None,
-            ws.data_ptr() if ws is not None else None,
-            flags,
-        )
-        if dim > EMBED_DIM:  # DRAFT: K-pipelined kernel, whole-document partitions only
-            rc = lib.cpb_maxsim_fwd_dim(*common, dim, stream)
-        elif bank.contiguous and bank.max_len > 0 and torch.cuda.current_stream(dev) == torch.cuda.default_stream(dev):
-            split = _split_workspace(dev, lib.cpb_maxsim_split_workspace_bytes(q.n, q.nq_pad))
-            _EPOCH[0] = _EPOCH[0] % 0xFFFFFFF0 + 1
-            rc = lib.cpb_maxsim_fwd_balanced(*common, bank.uniform_len, bank.max_len, split.data_ptr(), split.numel(),
-                                             _EPOCH[0], stream)
-        else:
-            rc = lib.cpb_maxsim_fwd(*common, stream)
-    _lib.check(rc, "cpb_maxsim_fwd")
+        stream = torch.cuda.current_stream(dev)
+        a.stream = stream.cuda_stream
+        if dim == EMBED_DIM and bank.contiguous and bank.max_len > 0 and smooth_tau == 0.0:
+            nbytes = lib.cpb_maxsim_split_workspace_bytes(q.n, q.nq_pad) * (4 if independent else 1)
+            split = _split_workspace(dev, stream.cuda_stream, nbytes)
+            a.d_split_ws, a.split_ws_bytes, a.epoch = split.data_ptr(), split.numel(), next_epoch()
+        if gather is not None:
+            a.d_peer_bases, a.mc_base, a.n_peers = gather["peer_bases"], gather["mc_base"], gather["n_peers"]
+            a.slab_word_offset, a.flag_word_offset = gather["slab_word_offset"], gather["flag_word_offset"]
+            if gather.get("wait_flags"):
+                a.d_wait_flags, a.n_wait, a.wait_value = gather["wait_flags"], gather["n_peers"], gather["wait_value"]
+        if loss is not None:
+            a.loss = ctypes.pointer(loss)
+            a.d_done_counter = done_counter.data_ptr()
+        rc = lib.cpb_maxsim_launch(ctypes.byref(a))
+    _lib.check(rc, "cpb_maxsim_launch")
     _lib.count_launches(2 if ws is not None else 1)
+    return int(a.grid_out)
+
+
+def maxsim(q: QueryBlock, bank: DocBank, *, round_bf16: bool = False, want_argmax: bool = False,
+           independent: bool = False):
+    """Run the fused kernel.  Returns device fp32 ``[n_queries, n_docs]`` (and int32 argmax
+    ``[n_docs, n_queries * nq_pad]`` when asked).  ``independent=True`` tells the kernel that it reads nothing the
+    previous kernel on the stream wrote (next query batch against a resident bank): it may then overlap that
+    kernel's tail (CPB_FLAG_INDEPENDENT)."""
+    dev = bank.device
+    scores = torch.empty(q.n, bank.n_docs, dtype=torch.float32, device=dev)
+    argmax = torch.empty(bank.n_docs, q.n * q.nq_pad, dtype=torch.int32, device=dev) if want_argmax else None
+    launch_maxsim(q, bank, scores=scores, argmax=argmax, round_bf16=round_bf16, independent=independent)
     return (scores, argmax) if want_argmax else scores
 
 

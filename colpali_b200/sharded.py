@@ -110,84 +110,122 @@ def score_sharded(
 class FusedGatherScorer:
     """Corpus-sharded scoring whose all-gather is fused into the MaxSim kernel (no collective kernel at all).
 
-    Every rank owns ``n_local`` documents; the kernel epilogue stores each score into all ranks' copies of
-    ``gathered[my_rank]`` through NVLink peer mappings of a symmetric-memory buffer
-    (``torch.distributed._symmetric_memory``), and the last CTA of each rank's grid then stores a per-launch completion
-    word into every peer; after ``wait()`` (or ``barrier()``) every rank holds ``[world, n_queries, n_local]``.
+    Every rank owns ``n_local`` documents; the kernel epilogue stores each score into ALL ranks' copies of
+    ``gathered[slab][my_rank]`` in a symmetric-memory buffer (``torch.distributed._symmetric_memory``) -- one
+    ``multimem.st`` through the NVSwitch multicast mapping when the fabric offers one, else one store per NVLink peer
+    mapping -- and every CTA, once its scores are out, adds 1 (release, system scope) to a per-(slab, rank) counter on
+    every rank.  ``wait()`` enqueues a kernel that spins until the local counters have grown by every rank's grid size.
+
+    The slab is triple-buffered: launch ``k + 3`` of a rank overwrites the slab of launch ``k``.  Before its first score
+    store the kernel itself waits (on LOCAL counters) until every rank has completed launch ``k + 1`` -- hence started
+    it, which by stream order on that rank is after it finished with the results of launch ``k`` (rule: enqueue the
+    consumers of a result on the same stream before the next ``score``).  So back-to-back launches need no host round
+    trip and no extra kernel, and launch ``k + 3`` never has to wait for launch ``k + 2``: with ``independent=True`` it
+    may start while the previous launch is still draining its remote stores.
+
     Needs queries of at most 32 tokens and equally sized shards.  ``available()`` tells whether symmetric memory can be
-    set up in this process group; callers fall back to ``score_sharded`` (NCCL all-gather) otherwise.
+    set up in this process group (agreed across ranks); callers fall back to ``score_sharded`` (NCCL all-gather) otherwise.
     """
 
-    def __init__(self, n_queries: int, n_local: int, device: torch.device, group=None):
+    _SLABS = 3
+    _FLAG_WORDS = 3 * 64  # [3 slabs][64 ranks]
+
+    def __init__(self, n_queries: int, n_local: int, device: torch.device, group=None, use_multicast: bool = True):
         import torch.distributed._symmetric_memory as symm_mem
 
         self.group = group if group is not None else dist.group.WORLD
         self.rank = dist.get_rank(self.group)
         self.world = dist.get_world_size(self.group)
+        if self.world > 64:
+            raise ValueError("FusedGatherScorer supports at most 64 ranks")
         self.n_queries, self.n_local, self.device = n_queries, n_local, device
-        self.n_slab = self.world * n_queries * n_local
-        # gathered slabs followed by one completion word per rank (64 words reserved)
-        self.buf = symm_mem.empty(self.n_slab + 64, dtype=torch.float32, device=device)
+        self.n_slab = self.world * n_queries * n_local          # words of one slab: gathered[world, n_q, n_local]
+        self.buf = symm_mem.empty(self._SLABS * self.n_slab + self._FLAG_WORDS, dtype=torch.float32, device=device)
         self.hdl = symm_mem.rendezvous(self.buf, self.group)
         self.peer_ptrs = torch.tensor(list(self.hdl.buffer_ptrs), dtype=torch.int64, device=device)
-        self.counter = torch.zeros(1, dtype=torch.int32, device=device)
-        self.step = 0
+        mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0) if use_multicast else 0
+        # all ranks must agree on the store path (a rank without the mapping would miss the others' multicast stores)
+        agree = torch.tensor([1 if mc else 0], dtype=torch.int32, device=device)
+        dist.all_reduce(agree, op=dist.ReduceOp.MIN, group=self.group)
+        self.mc_base = mc if int(agree) else 0
+        self.step = 0            # launches issued
+        self.count = [0] * self._SLABS  # CTAs that have signalled per slab (every rank launches the same grid)
+        self.status = torch.zeros(1, dtype=torch.int32, device=device)
         self.buf.zero_()
         torch.cuda.synchronize(device)
         self.hdl.barrier()
 
     @staticmethod
     def available(device: torch.device, group=None) -> bool:
+        """True on every rank or on none (the outcome of the local set-up is all-reduced)."""
+        ok = 1
         try:
-            FusedGatherScorer(1, 1, device, group)
-            return True
-        except Exception:  # noqa: BLE001 - any failure means "use the NCCL path"
-            return False
+            import torch.distributed._symmetric_memory as symm_mem
 
-    def score(self, q, bank) -> torch.Tensor:
-        """Enqueue the fused kernel; returns the local gathered view ``[world, n_queries, n_local]`` (the other ranks'
-        slabs are complete after ``barrier()``)."""
-        from . import _lib
-        from .scoring import _EPOCH, _split_workspace
+            t = symm_mem.empty(64, dtype=torch.float32, device=device)
+        except Exception:  # noqa: BLE001 - any failure means "use the NCCL path"
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if not int(flag):
+            return False
+        try:  # collective: entered by every rank, since every rank got here
+            symm_mem.rendezvous(t, group if group is not None else dist.group.WORLD)
+        except Exception:  # noqa: BLE001
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        return bool(int(flag))
+
+    def _slab(self, k: int) -> torch.Tensor:
+        return self.buf[k * self.n_slab: (k + 1) * self.n_slab].view(self.world, self.n_queries, self.n_local)
+
+    def _flags(self, k: int) -> torch.Tensor:
+        return self.buf[self._SLABS * self.n_slab + k * 64:]
+
+    def score(self, q, bank, independent: bool = False) -> torch.Tensor:
+        """Enqueue the fused kernel; returns the local gathered view ``[world, n_queries, n_local]`` of this launch's
+        slab (complete after ``wait()``).  ``independent``: see ``scoring.maxsim``."""
+        from .scoring import launch_maxsim
 
         if q.n != self.n_queries or bank.n_docs != self.n_local or q.nq_pad != 32:
             raise ValueError("FusedGatherScorer was built for a different shape (or queries longer than 32 tokens)")
-        lib = _lib.load()
-        dev = self.device
-        flags = _lib.CPB_FLAG_CONTIGUOUS if bank.contiguous else 0
-        split = None
-        if bank.contiguous and bank.max_len > 0:
-            split = _split_workspace(dev, lib.cpb_maxsim_split_workspace_bytes(q.n, q.nq_pad))
-        _EPOCH[0] = _EPOCH[0] % 0xFFFFFFF0 + 1
-        with torch.cuda.device(dev):
-            rc = lib.cpb_maxsim_fwd_allgather(
-                q.flat.data_ptr(), q.n, q.nq_pad, bank.flat.data_ptr(), bank.flat.shape[0],
-                bank.start.data_ptr(), bank.length.data_ptr(),
-                bank.floor.data_ptr() if bank.floor is not None else None, bank.n_docs,
-                self.peer_ptrs.data_ptr(), self.world, self.rank, flags,
-                bank.uniform_len, bank.max_len, split.data_ptr() if split is not None else None,
-                split.numel() if split is not None else 0, _EPOCH[0],
-                self.counter.data_ptr(), self.n_slab, self.step + 1, torch.cuda.current_stream(dev).cuda_stream,
-            )
-        _lib.check(rc, "cpb_maxsim_fwd_allgather")
-        _lib.count_launches(1)
+        k = self.step % self._SLABS
+        gather = {
+            "peer_bases": self.peer_ptrs.data_ptr(), "mc_base": self.mc_base, "n_peers": self.world,
+            "slab_word_offset": k * self.n_slab + self.rank * self.n_queries * self.n_local,
+            "flag_word_offset": self._SLABS * self.n_slab + k * 64 + self.rank,
+        }
+        if self.step >= 2:  # write-after-read guard: launch step - 2 (slab k + 1) is complete on every rank
+            g = (k + 1) % self._SLABS
+            gather["wait_flags"] = self._flags(g).data_ptr()
+            gather["wait_value"] = self.count[g] & 0xFFFFFFFF
+        grid = launch_maxsim(q, bank, scores=None, gather=gather, independent=independent)
+        self.count[k] += grid  # every rank launches the same shape, hence the same grid
         self.step += 1
-        return self.buf[: self.n_slab].view(self.world, self.n_queries, self.n_local)
+        return self._slab(k)
 
     def wait(self) -> None:
         """Enqueue a wait until every rank has signalled completion of its most recent ``score`` launch (all ranks must
-        have issued the same number of launches): afterwards the gathered view is complete."""
+        have issued the same number of launches): afterwards the gathered view of that launch is complete."""
         from . import _lib
 
+        if self.step == 0:
+            return
+        k = (self.step - 1) % self._SLABS
         lib = _lib.load()
-        flags = self.buf[self.n_slab :]
         with torch.cuda.device(self.device):
-            rc = lib.cpb_wait_flags(flags.data_ptr(), self.world, self.step,
-                                    torch.cuda.current_stream(self.device).cuda_stream)
+            rc = lib.cpb_wait_flags(self._flags(k).data_ptr(), self.world, self.count[k] & 0xFFFFFFFF,
+                                    self.status.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream)
         _lib.check(rc, "cpb_wait_flags")
         _lib.count_launches(1)
 
+    def check_status(self) -> None:
+        """Synchronising: raise if a wait timed out (a peer never signalled)."""
+        late = int(self.status.item())
+        if late:
+            raise RuntimeError(f"fused all-gather: ranks with bit mask {late:#x} did not signal within the time-out")
+
     def barrier(self) -> None:
-        """Device-side cross-rank barrier on the current stream (symmetric-memory signal pads): after it, every rank's
-        kernel has finished and all slabs are visible."""
+        """Device-side cross-rank barrier on the current stream (symmetric-memory signal pads)."""
         self.hdl.barrier()

@@ -13,8 +13,15 @@
  *   - bf16 tensors are raw uint16 storage, row-major, rows of `dim` elements;
  *   - return value: 0 on success, negative CPB_E_* on error; cpb_last_error() returns a
  *     thread-local human-readable message for the most recent failure on the calling thread;
- *   - functions are re-entrant and keep no global mutable state besides a cached driver
- *     entry point.
+ *   - argument blocks are plain structs whose first member is `struct_size` = sizeof(the struct)
+ *     as the caller compiled it: members added by later versions are read only when present, so a
+ *     zero-initialised struct with the fields you need is always a valid call;
+ *   - launches may be issued concurrently from several host threads (different streams).  The
+ *     only process-wide state is (a) caches of device properties / occupancy, which are
+ *     idempotent and guarded, and (b) the tuning knobs of cpb_set_option, which are atomics read
+ *     once per launch -- change them only for experiments.  Device scratch that a caller shares
+ *     between launches (d_split_ws, d_done_counter) must not be shared by launches that can run
+ *     at the same time: give every stream its own.
  */
 #ifndef COLPALI_B200_H_
 #define COLPALI_B200_H_
@@ -25,7 +32,7 @@
 extern "C" {
 #endif
 
-#define CPB_ABI_VERSION 1
+#define CPB_ABI_VERSION 2
 
 /* error codes */
 #define CPB_OK 0
@@ -34,15 +41,18 @@ extern "C" {
 #define CPB_E_CUDA (-3)      /* a CUDA runtime / driver call failed                 */
 #define CPB_E_DEVICE (-4)    /* device is not sm_100 (tcgen05 / TMEM required)      */
 
-/* flags for cpb_maxsim_fwd */
+/* flags of cpb_maxsim_args.flags / cpb_maxsim_fwd */
 #define CPB_FLAG_ROUND_BF16 1u /* emulate the reference's bf16 result rounding: each per-token
                                   maximum and the final score are rounded to bf16 (what
                                   torch.einsum(...).max().sum() yields for bf16 inputs,
                                   processing_utils.py:179) instead of staying fp32. */
-
 #define CPB_FLAG_CONTIGUOUS 2u /* the caller guarantees d_doc_start[j+1] == d_doc_start[j] + d_doc_len[j]
                                   for every j (documents stored back to back): tiles then run across
                                   document boundaries and no short per-document tail tiles are issued. */
+#define CPB_FLAG_INDEPENDENT 4u /* this launch reads nothing that the previous kernel on the stream wrote
+                                   (e.g. the next query batch against a resident bank): it may start
+                                   while that kernel is still draining (programmatic dependent launch
+                                   without the dependency wait). */
 
 int cpb_abi_version(void);
 const char* cpb_last_error(void);
@@ -51,176 +61,171 @@ const char* cpb_last_error(void);
 int cpb_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
 
 /*
- * Tuning knobs for experiments (process-wide, not thread-safe against concurrent launches):
+ * Tuning knobs for experiments (process-wide atomics, read once per launch):
  *   "cluster"         0 = auto, 1 / 2 / 4 = CTAs per cluster sharing document tiles by TMA multicast
  *   "qtiles_per_cta"  0 = auto, 1 / 2     = resident 128-row query tiles per CTA
- *   "mma_split"       5..8 (default 6): K-steps of a job issued before the next job's barrier waits
- *   "balanced"        1 (default) / 0: allow tile-balanced partitions in cpb_maxsim_fwd_balanced
- *   "debug_delay"     profiling only
- *   "debug_flags"     profiling-only bits (upper 16), 0 in production
+ *   "balanced"        1 (default) / 0: allow tile-balanced partitions
+ *   "pdl"             1 (default) / 0: programmatic dependent launch of the MaxSim kernels
+ *   "boundary_mode"   1 (default) / 0: shifted-chunk epilogue for tiles that hold a document boundary
+ *   "head_cluster"    0 = auto, 1 / 2: CTAs sharing the projection weight block (wide head)
+ *   "wait_timeout_ms" time-out of cpb_wait_flags (default 120000)
+ *   "debug_delay", "debug_flags"  profiling only
  */
 int cpb_set_option(const char* name, int value);
 
-/*
+/* ------------------------------------------------------------------------------------------------------------------
+ * In-batch loss on a [n_queries, n_docs] matrix of raw MaxSim sums, with its gradient.
+ *   replaces: ColbertLoss.forward            colpali_engine/loss/late_interaction_losses.py:152,155-164
+ *             ColbertPairwiseCELoss.forward  :296,299-313      ColbertSigmoidLoss.forward :446-465
+ *             ColbertModule._apply_normalization :46-71, ._filter_high_negatives :93-107
+ *             explicit negatives: ColbertNegativeCELoss.forward :215-252, ColbertPairwiseNegativeCELoss.forward :361-398
+ *               loss = (1 - w) * mean_{b,l} softplus((neg[b,l] - pos[b]) / T) + w * in_batch_loss(mode)
+ *               pos[b] = scores[b, b + offset];  neg[b, l] = neg_scores[b, b * n_neg + l]  (both length-normalised)
+ *   lengths (:152) are counted from column 0 of the query rows.  The positive of query b is document b + offset (:33-38).
+ * ------------------------------------------------------------------------------------------------------------------ */
+#define CPB_LOSS_CE 0       /* ColbertLoss: cross entropy over in-batch documents          */
+#define CPB_LOSS_PAIRWISE 1 /* ColbertPairwiseCELoss: softplus(hardest negative - positive) */
+#define CPB_LOSS_SIGMOID 2  /* ColbertSigmoidLoss: n_docs == n_queries, offset 0            */
+
+typedef struct cpb_loss_desc {
+  uint32_t struct_size;
+  int32_t mode;                         /* CPB_LOSS_* */
+  int32_t normalize_scores;             /* divide every row by its query length (:155-156) */
+  int32_t pos_aware_negative_filtering; /* :161-162 */
+  int32_t offset;                       /* positive of query b = document b + offset */
+  float temperature;
+  float filter_threshold, filter_factor;
+  const float* d_neg_scores;            /* fp32 [n_queries, n_queries * n_neg] or NULL: every query against every query's
+                                           negatives (only the block diagonal is used) */
+  int32_t n_neg;
+  float in_batch_term_weight;           /* w above; ignored without negatives */
+  float* d_loss;                        /* fp32 [1] out: mean over queries */
+  float* d_grad_scores;                 /* fp32 [n_queries, n_docs] out or NULL: d loss / d raw score */
+  float* d_grad_neg_scores;             /* fp32 [n_queries, n_queries * n_neg] out or NULL */
+  float* d_bounds;                      /* fp32 [2] out or NULL: min / max of the normalised scores (:64-70) */
+} cpb_loss_desc;
+
+/* Stand-alone launch of the loss kernel on an existing score matrix.  d_q: bf16 [n_queries * nq_pad, dim]. */
+int cpb_colbert_loss_launch(const cpb_loss_desc* loss, const float* d_scores, const void* d_q, int n_queries, int nq_pad,
+                            int n_docs, int dim, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Fused MaxSim forward.
  *   replaces: torch.einsum("bnd,csd->bcns", q, d).max(dim=3)[0].sum(dim=2)
  *             colpali_engine/utils/processing_utils.py:179  (score_multi_vector inner loop)
  *             colpali_engine/loss/late_interaction_losses.py:153-154 (ColbertLoss scores),
- *             :297-298 (ColbertPairwiseCELoss), :444-445 (ColbertSigmoidLoss)
- *
- *   d_q          bf16 [n_queries * nq_pad, 128]; every query occupies nq_pad rows (nq_pad a
- *                multiple of 32), zero rows after its real tokens (a zero row adds 0, exactly
- *                like the reference's zero padding of queries, processing_utils.py:172).
- *   d_docs       bf16 [doc_rows, 128]: flat token bank.
- *   d_doc_start  int32 [n_docs]: first bank row of each document.
- *   d_doc_len    int32 [n_docs]: number of rows of each document (0 allowed).
- *   d_doc_floor  fp32 [n_docs] or NULL: initial value of every per-token maximum of that
- *                document; -inf = plain max, 0 = the document had zero-padding rows in the
- *                reference batch (processing_utils.py:176-178: pad rows score exactly 0 and take
- *                part in the max).  NULL means -inf everywhere.
- *   d_scores     fp32 [n_queries, n_docs] out.
- *   d_argmax     int32 [n_docs, n_queries * nq_pad] out, or NULL.  Row index (relative to the
- *                document start) of the first maximal token for every (document, query row);
- *                -1 when the maximum is the floor.  Needed by cpb_maxsim_bwd.
- *   d_workspace  fp32 [(nq_pad/32) * n_queries * n_docs] scratch, only read when nq_pad > 32
- *                (may be NULL otherwise).
- */
+ *             :297-298 (ColbertPairwiseCELoss), :444-445 (ColbertSigmoidLoss), and with smooth_tau > 0 the
+ *             tau * logsumexp(raw / tau) aggregation of :40-44 / :88-90.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct cpb_maxsim_args {
+  uint32_t struct_size;
+  uint32_t flags;               /* CPB_FLAG_* */
+  void* stream;
+  /* queries: bf16 [n_queries * nq_pad, dim]; every query occupies nq_pad rows (a multiple of 32), zero rows after its
+     real tokens (a zero row adds 0 to a hard-max score, exactly like the reference's zero padding, processing_utils.py:172) */
+  const void* d_q;
+  int32_t n_queries, nq_pad;
+  int32_t nq_real;              /* smooth max only: rows of each query that belong to the caller's tensor (<= nq_pad) */
+  int32_t dim;                  /* 128 (smaller dims zero-padded by the caller), 192, 256 or 320 */
+  /* document bank: bf16 [doc_rows, dim] flat tokens + per-document (start row, rows) */
+  const void* d_docs;
+  int64_t doc_rows;
+  const int32_t* d_doc_start;   /* [n_docs] */
+  const int32_t* d_doc_len;     /* [n_docs], 0 allowed */
+  const float* d_doc_floor;     /* [n_docs] or NULL: initial value of every per-token maximum of that document; 0 = the
+                                   document had zero-padding rows in the reference batch (processing_utils.py:176-178:
+                                   pad rows score 0 and take part in the max), -inf = plain max.  NULL = -inf everywhere */
+  int32_t n_docs;
+  int32_t uniform_len;          /* > 0 if every document has exactly this many rows, else 0 */
+  int32_t max_doc_len;          /* longest document, 0 = unknown (no tile-balanced partitions) */
+  /* outputs */
+  float* d_scores;              /* fp32 [n_queries, n_docs] (may be NULL with the fused all-gather) */
+  int32_t* d_argmax;            /* int32 [n_docs, n_queries * nq_pad] or NULL: document-relative row of the first maximal
+                                   token per (document, query row), -1 when the floor won.  For cpb_maxsim_bwd_launch */
+  float* d_lse;                 /* smooth max: fp32 [n_docs, n_queries * nq_pad] or NULL: tau * logsumexp per (document,
+                                   query row).  For cpb_maxsim_bwd_launch */
+  float* d_workspace;           /* fp32 [(nq_pad/32) * n_queries * n_docs] scratch, needed when nq_pad > 32 */
+  /* tile-balanced partitions of a CPB_FLAG_CONTIGUOUS bank: every persistent CTA gets the same number of 256-row tiles
+     even if that cuts a document; the two partial per-token maxima of a cut document are exchanged through d_split_ws */
+  void* d_split_ws;             /* cpb_maxsim_split_workspace_bytes() bytes, ZERO-INITIALISED ONCE by the caller, reused by
+                                   stream-ordered launches; NULL disables balancing */
+  int64_t split_ws_bytes;
+  uint32_t epoch;               /* non-zero, different for every launch that shares d_split_ws */
+  /* aggregation */
+  float smooth_tau;             /* 0 = maximum; > 0 = tau * logsumexp(raw / tau) (ColbertModule.tau) */
+  /* Corpus-sharded scoring with the all-gather of the score slabs FUSED into the epilogue (BASELINE configs[3]; the
+     reference scores on one device).  Every rank owns n_docs documents and the same queries; each score goes straight
+     into all ranks' copies of a symmetric buffer over NVLink: word slab_word_offset + q * n_docs + doc.  Every CTA then
+     adds 1 (release, system scope) to word flag_word_offset of every rank; a consumer waits until that word has grown by
+     the grid size of the launch (grid_out, cpb_wait_flags).  nq_pad must be 32. */
+  const uint64_t* d_peer_bases; /* device array of n_peers base addresses of the peers' symmetric buffers, or NULL */
+  uint64_t mc_base;             /* NVSwitch multicast address of the same buffer (one multimem.st / multimem.red reaches
+                                   every rank), or 0 to store through the n_peers peer mappings */
+  int32_t n_peers;
+  int64_t slab_word_offset;
+  int64_t flag_word_offset;
+  const uint32_t* d_wait_flags; /* or NULL: before its first score store the kernel waits until these n_wait LOCAL words
+                                   have reached wait_value (wrap-safe) -- the completion counters of the previous launch on
+                                   a double-buffered slab: write-after-read safety without a host round trip */
+  int32_t n_wait;
+  uint32_t wait_value;
+  /* the in-batch loss "emitted directly": the last CTA of the grid turns d_scores into the loss (+ gradient) */
+  const cpb_loss_desc* loss;    /* NULL = scores only */
+  uint32_t* d_done_counter;     /* device uint32, zero before the first launch (the kernel resets it), needed with `loss` */
+  /* written by the call */
+  int32_t grid_out;             /* CTAs launched */
+} cpb_maxsim_args;
+
+int cpb_maxsim_launch(cpb_maxsim_args* args);
+
+/* Positional form of the plain case (dim 128, hard max, whole-document partitions). */
 int cpb_maxsim_fwd(const void* d_q, int n_queries, int nq_pad,
                    const void* d_docs, int64_t doc_rows,
                    const int32_t* d_doc_start, const int32_t* d_doc_len, const float* d_doc_floor, int n_docs,
                    float* d_scores, int32_t* d_argmax, float* d_workspace,
                    uint32_t flags, void* stream);
 
-/*
- * Same as cpb_maxsim_fwd, with tile-balanced partitioning for CPB_FLAG_CONTIGUOUS banks: every persistent CTA gets
- * the same number of 256-row tiles even if that cuts a document in two; the two partial per-token maxima of a cut
- * document are exchanged through d_split_ws (right neighbour publishes, left neighbour combines and emits the score).
- *   uniform_len     > 0 if every document has exactly this many rows (skips a binary search), else 0
- *   max_doc_len     length of the longest document (partitions shorter than this fall back to whole documents)
- *   d_split_ws      device scratch of cpb_maxsim_split_workspace_bytes() bytes, ZERO-INITIALISED ONCE by the caller and
- *                   then reused across calls on the same stream order; NULL disables balancing
- *   epoch           non-zero, different for every call that shares d_split_ws (a slot is valid when it holds `epoch`)
- */
-int cpb_maxsim_fwd_balanced(const void* d_q, int n_queries, int nq_pad,
-                            const void* d_docs, int64_t doc_rows,
-                            const int32_t* d_doc_start, const int32_t* d_doc_len, const float* d_doc_floor, int n_docs,
-                            float* d_scores, int32_t* d_argmax, float* d_workspace, uint32_t flags,
-                            int uniform_len, int max_doc_len, void* d_split_ws, int64_t split_ws_bytes, uint32_t epoch,
-                            void* stream);
+/* Bytes of d_workspace for this shape (0 when nq_pad == 32) / of d_split_ws. */
+int64_t cpb_maxsim_workspace_bytes(int n_queries, int nq_pad, int n_docs);
 int64_t cpb_maxsim_split_workspace_bytes(int n_queries, int nq_pad);
 
-/*
- * Corpus-sharded scoring with the all-gather of the score slabs FUSED into the kernel epilogue (BASELINE configs[3];
- * the reference scores on one device only).  Every rank owns n_docs documents and the same n_queries queries; each
- * score is stored straight into all ranks' gathered buffers through NVLink peer mappings:
- *     peer_slabs[r][my_rank][q][doc] = score      for r in 0..n_peers-1      (fp32, [n_peers, n_queries, n_docs] each)
- * No collective kernel follows.  Completion: if d_done_counter is given, the last CTA of the grid stores `signal_value`
- * into 32-bit word (flag_word_offset + my_rank) of every peer's buffer once all of this rank's scores are written
- * (__threadfence_system ordered); a consumer waits until its own words [flag_word_offset, +n_peers) hold the value
- * (cpb_wait_flags).  Without d_done_counter the caller needs a cross-rank barrier instead.  nq_pad must be 32.
- *   d_done_counter   local device uint32, zero before the first launch (reset by the kernel), or NULL
- *   d_peer_slabs   device array of n_peers uint64 base addresses of the peers' gathered buffers (this rank's included),
- *                  e.g. torch.distributed._symmetric_memory handle.buffer_ptrs_dev
- * Other arguments as cpb_maxsim_fwd_balanced (d_split_ws may be NULL).
- */
-int cpb_maxsim_fwd_allgather(const void* d_q, int n_queries, int nq_pad,
-                             const void* d_docs, int64_t doc_rows,
-                             const int32_t* d_doc_start, const int32_t* d_doc_len, const float* d_doc_floor, int n_docs,
-                             const uint64_t* d_peer_slabs, int n_peers, int my_rank, uint32_t flags,
-                             int uniform_len, int max_doc_len, void* d_split_ws, int64_t split_ws_bytes, uint32_t epoch,
-                             uint32_t* d_done_counter, int64_t flag_word_offset, uint32_t signal_value, void* stream);
+/* Enqueue a wait on `stream` until d_flags[i] has reached `value` for every i < n (wrap-safe: counters only grow) --
+ * the consumer side of the fused all-gather.  A peer that is late is waited for up to "wait_timeout_ms"; on time-out bit
+ * i of *d_status (may be NULL) is set and the stream continues -- check it after synchronising. */
+int cpb_wait_flags(const uint32_t* d_flags, int n, uint32_t value, uint32_t* d_status, void* stream);
 
-/* Enqueue a wait on `stream` until d_flags[0..n) all equal `value` (consumer side of cpb_maxsim_fwd_allgather). */
-int cpb_wait_flags(const uint32_t* d_flags, int n, uint32_t value, void* stream);
+/* ------------------------------------------------------------------------------------------------------------------
+ * Backward of the MaxSim forward: given g = d loss / d scores,
+ *   hard max (d_argmax):  dq[row] = sum_c g[b(row), c] * docs[start_c + argmax[c, row]]
+ *                         dd[start_c + s] = sum_{rows with argmax[c, row] == s} g[b(row), c] * q[row]
+ *   smooth max (d_lse):   P[c, row, s] = exp((<q_row, d_s> - lse[c, row]) / tau) recomputed tile by tile,
+ *                         dq[row] = sum_c g[b, c] sum_s P * d_s,   dd[start_c + s] = sum_row g[b, c] P * q_row
+ *   replaces: autograd through torch.einsum / amax | logsumexp / sum (late_interaction_losses.py:153-154, :40-44); the
+ *   reference keeps the [B, C, N_q, N_d] similarity tensor alive for it, this path keeps [C, rows] int32 or fp32.
+ * Both outputs are WRITTEN (no pre-zeroing, no atomics): every bank row of every document is produced exactly once.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct cpb_maxsim_bwd_args {
+  uint32_t struct_size;
+  uint32_t flags;               /* CPB_FLAG_CONTIGUOUS: the documents cover the bank (else rows outside are zeroed first) */
+  void* stream;
+  const float* d_grad_scores;   /* fp32 [n_queries, n_docs] */
+  const float* d_grad_out;      /* fp32 [1] upstream gradient of the loss, or NULL for 1 */
+  const int32_t* d_argmax;      /* hard max: [n_docs, n_queries * nq_pad] from the forward, else NULL */
+  const float* d_lse;           /* smooth max: [n_docs, n_queries * nq_pad] from the forward, else NULL */
+  float smooth_tau;             /* > 0 with d_lse */
+  const void* d_q;
+  int32_t n_queries, nq_pad, nq_real, dim;
+  const void* d_docs;
+  int64_t doc_rows;
+  const int32_t* d_doc_start;   /* [n_docs] */
+  const int32_t* d_doc_len;     /* [n_docs] (rows of the bank outside every document are zero-filled in dd) */
+  int32_t n_docs;
+  int32_t max_doc_len;          /* longest document */
+  float* d_dq;                  /* fp32 [n_queries * nq_pad, dim] out, or NULL to skip */
+  float* d_dd;                  /* fp32 [doc_rows, dim] out, or NULL to skip */
+} cpb_maxsim_bwd_args;
 
-/*
- * DRAFT: cpb_maxsim_fwd for embedding dims 192 / 256 / 320 (ColQwen3: models/qwen3/colqwen3/modeling_colqwen3.py:48).
- * d_q and d_docs are [rows, dim] bf16; every other argument as cpb_maxsim_fwd.  Whole-document partitions only.
- */
-int cpb_maxsim_fwd_dim(const void* d_q, int n_queries, int nq_pad,
-                       const void* d_docs, int64_t doc_rows,
-                       const int32_t* d_doc_start, const int32_t* d_doc_len, const float* d_doc_floor, int n_docs,
-                       float* d_scores, int32_t* d_argmax, float* d_workspace,
-                       uint32_t flags, int dim, void* stream);
-
-/* Bytes of d_workspace cpb_maxsim_fwd needs for this shape (0 when nq_pad == 32). */
-int64_t cpb_maxsim_workspace_bytes(int n_queries, int nq_pad, int n_docs);
-
-/* loss modes of cpb_colbert_loss_fwd */
-#define CPB_LOSS_CE 0       /* ColbertLoss: cross entropy over in-batch documents          */
-#define CPB_LOSS_PAIRWISE 1 /* ColbertPairwiseCELoss: softplus(hardest negative - positive) */
-#define CPB_LOSS_SIGMOID 2  /* ColbertSigmoidLoss (late_interaction_losses.py:431-465): n_docs == n_queries, offset 0 */
-
-/*
- * In-batch-negative loss on a [n_queries, n_docs] matrix of raw MaxSim sums, with its gradient.
- *   replaces: ColbertLoss.forward            colpali_engine/loss/late_interaction_losses.py:152,155-164
- *             ColbertPairwiseCELoss.forward  colpali_engine/loss/late_interaction_losses.py:296,299-313
- *             ColbertModule._apply_normalization :46-71, ._filter_high_negatives :93-107
- *   lengths (late_interaction_losses.py:152) are counted here from column 0 of d_q (same padded
- *   layout as cpb_maxsim_fwd).  The positive of query b is document b + offset (:33-38).
- *
- *   d_loss         fp32 [1] out: mean over queries.
- *   d_grad_scores  fp32 [n_queries, n_docs] out or NULL: d loss / d raw score.
- *   d_bounds       fp32 [2] out or NULL: min / max of the length-normalised scores (the reference
- *                  prints a warning when they leave [-norm_tol, 1 + norm_tol], :64-70).
- */
-int cpb_colbert_loss_fwd(const float* d_scores, const void* d_q, int n_queries, int nq_pad, int n_docs, int mode,
-                         float temperature, int normalize_scores, int pos_aware_negative_filtering,
-                         float filter_threshold, float filter_factor, int offset,
-                         float* d_loss, float* d_grad_scores, float* d_bounds, void* stream);
-
-/*
- * Losses with explicit negative documents.
- *   replaces: ColbertNegativeCELoss.forward          colpali_engine/loss/late_interaction_losses.py:215-252
- *             ColbertPairwiseNegativeCELoss.forward  colpali_engine/loss/late_interaction_losses.py:361-398
- *   loss = (1 - w) * mean_{b,l} softplus((neg[b,l] - pos[b]) / T)  +  w * in_batch_loss(inner_mode)
- *   pos[b] = scores[b, b + offset];  neg[b, l] = neg_scores[b, b * n_neg + l]  (both length-normalised).
- *
- *   d_scores           fp32 [n_queries, n_docs]           raw MaxSim sums against the (gathered) positives
- *   d_neg_scores       fp32 [n_queries, n_queries * n_neg] raw MaxSim sums of every query against every query's
- *                      negatives (only the block diagonal is used; one dense MaxSim launch produces it)
- *   inner_mode         CPB_LOSS_CE (ColbertNegativeCELoss) or CPB_LOSS_PAIRWISE (ColbertPairwiseNegativeCELoss)
- *   d_grad_scores / d_grad_neg_scores   gradients of the loss w.r.t. both score matrices (zeros off the block diagonal)
- */
-int cpb_colbert_neg_loss_fwd(const float* d_scores, const float* d_neg_scores, const void* d_q, int n_queries,
-                             int nq_pad, int n_docs, int n_neg, int inner_mode, float temperature,
-                             int normalize_scores, int pos_aware_negative_filtering, float filter_threshold,
-                             float filter_factor, float in_batch_term_weight, int offset,
-                             float* d_loss, float* d_grad_scores, float* d_grad_neg_scores, void* stream);
-
-/*
- * Backward of cpb_maxsim_fwd: given g = d loss / d scores and the argmax saved by the forward,
- *   dq[row]                       = sum_c g[query(row), c] * docs[doc_start[c] + argmax[c, row]]
- *   dd[doc_start[c] + argmax[..]] += g[query(row), c] * q[row]            (fp32 vector atomics)
- *   replaces: autograd through torch.einsum / amax / sum (late_interaction_losses.py:153-154); the
- *   reference keeps the [B, C, N_q, N_d] similarity tensor alive for it, this path keeps [C, rows] int32.
- *
- *   d_grad_out  fp32 [1] upstream gradient of the loss, or NULL for 1.
- *   d_dq        fp32 [n_queries * nq_pad, 128] out, or NULL to skip.
- *   d_dd        fp32 [doc_rows, 128] in/out, MUST be zero-initialised by the caller, or NULL to skip.
- *   Rows whose argmax is -1 (the floor won) receive no gradient.
- */
-int cpb_maxsim_bwd(const float* d_grad_scores, const float* d_grad_out, const int32_t* d_argmax,
-                   const void* d_q, int n_queries, int nq_pad,
-                   const void* d_docs, int64_t doc_rows, const int32_t* d_doc_start, int n_docs,
-                   float* d_dq, float* d_dd, void* stream);
-
-/* DRAFT: the two loss entry points for d_q of shape [n_queries * nq_pad, dim], dim in {128, 192, 256, 320}. */
-int cpb_colbert_loss_fwd_dim(const float* d_scores, const void* d_q, int n_queries, int nq_pad, int n_docs, int mode,
-                             float temperature, int normalize_scores, int pos_aware_negative_filtering,
-                             float filter_threshold, float filter_factor, int offset,
-                             float* d_loss, float* d_grad_scores, float* d_bounds, int dim, void* stream);
-int cpb_colbert_neg_loss_fwd_dim(const float* d_scores, const float* d_neg_scores, const void* d_q, int n_queries,
-                                 int nq_pad, int n_docs, int n_neg, int inner_mode, float temperature,
-                                 int normalize_scores, int pos_aware_negative_filtering, float filter_threshold,
-                                 float filter_factor, float in_batch_term_weight, int offset,
-                                 float* d_loss, float* d_grad_scores, float* d_grad_neg_scores, int dim, void* stream);
-
-/* DRAFT: cpb_maxsim_bwd for [rows, dim] operands and gradients, dim in {128, 192, 256, 320} (see cpb_maxsim_fwd_dim). */
-int cpb_maxsim_bwd_dim(const float* d_grad_scores, const float* d_grad_out, const int32_t* d_argmax,
-                       const void* d_q, int n_queries, int nq_pad,
-                       const void* d_docs, int64_t doc_rows, const int32_t* d_doc_start, int n_docs,
-                       float* d_dq, float* d_dd, int dim, void* stream);
+int cpb_maxsim_bwd_launch(const cpb_maxsim_bwd_args* args);
 
 /* flags for cpb_head_fwd */
 #define CPB_HEAD_CLAMP_NORM 1u      /* norm = max(norm, 1e-12): ColModernVBert variant (modeling_colmodernvbert.py:59) */
@@ -232,8 +237,9 @@ int cpb_maxsim_bwd_dim(const float* d_grad_scores, const float* d_grad_out, cons
  *   replaces: proj = self.custom_text_proj(h); proj = proj / proj.norm(dim=-1, keepdim=True);
  *             proj = proj * attention_mask.unsqueeze(-1) [; proj = proj * image_mask]
  *             colpali_engine/models/qwen2/colqwen2/modeling_colqwen2.py:65-74 (ctor :34-35) and the identical
- *             tails of ColPali :67-77, ColQwen2.5 :67-76, ColQwen3.5 :67-76, ColQwen2.5-Omni :64-73,
- *             ColGemma3 :84-93, ColIdefics3 :38-46, ColModernVBert :57-65 (CPB_HEAD_CLAMP_NORM).
+ *             tails of ColPali :67-77, ColQwen2.5 :67-76, ColQwen3 (dim 320, modeling_colqwen3.py:87-96), ColQwen3.5
+ *             :67-76, ColQwen2.5-Omni :64-73, ColGemma3 :84-93, ColIdefics3 :38-46, ColModernVBert :57-65
+ *             (CPB_HEAD_CLAMP_NORM).
  *
  *   d_hidden          bf16 [n_tokens, hidden]   last_hidden_state, flattened over (batch, sequence)
  *   d_weight          bf16 [dim, hidden]        custom_text_proj.weight (nn.Linear layout)
@@ -241,7 +247,7 @@ int cpb_maxsim_bwd_dim(const float* d_grad_scores, const float* d_grad_out, cons
  *   d_attention_mask  int64 [n_tokens] or NULL  multiplied in as a value (0/1 in practice)
  *   d_extra_mask      uint8 [n_tokens] or NULL  non-zero keeps the row (input_ids == image_token_id)
  *   d_out             bf16 [n_tokens, dim]
- *   dim must be 128 and hidden a multiple of 64 in this build (CPB_E_UNSUPPORTED otherwise).
+ *   dim: 128, or a multiple of 32 in (128, 320]; hidden a multiple of 64 (CPB_E_UNSUPPORTED otherwise).
  */
 int cpb_head_fwd(const void* d_hidden, int64_t n_tokens, int hidden,
                  const void* d_weight, const void* d_bias, int dim,

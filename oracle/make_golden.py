@@ -215,6 +215,56 @@ def loss_cfg3():
     print("loss_cfg3 ok")
 
 
+def loss_smooth():
+    """use_smooth_max=True (tau * logsumexp, late_interaction_losses.py:40-44): small cases with all gradients for
+    every loss class, and cfg3 (ColbertLoss / ColbertPairwiseCELoss) with fp32 inputs."""
+    g = torch.Generator().manual_seed(15)
+    rnd = lambda *sh: torch.nn.functional.normalize(torch.randn(*sh, generator=g), dim=-1).bfloat16().float()  # noqa: E731
+    q, d, neg = rnd(4, 5, 16), rnd(6, 9, 16), rnd(4, 3, 7, 16)
+    q[1, 3:] = 0   # all-zero query rows still add tau * log(N_d) each (but do not count in `lengths`)
+    d[0, :2] = 0   # zero document rows take part in the log-sum-exp (exp(0) = 1)
+    neg[0, 1, :2] = 0
+    out = {"q": q.numpy().copy(), "d": d.numpy().copy(), "neg": neg.numpy().copy()}
+    for name, mod, port, kw in (
+        ("colbert", ColbertLoss(use_smooth_max=True), O.colbert_loss_port, {}),
+        ("colbert_tau05_nonorm", ColbertLoss(use_smooth_max=True, tau=0.05, normalize_scores=False, temperature=0.5),
+         O.colbert_loss_port, dict(tau=0.05, normalize_scores=False, temperature=0.5)),
+        ("pairwise", ColbertPairwiseCELoss(use_smooth_max=True), O.colbert_pairwise_ce_loss_port, {}),
+        ("pairwise_filter", ColbertPairwiseCELoss(use_smooth_max=True, pos_aware_negative_filtering=True),
+         O.colbert_pairwise_ce_loss_port, dict(pos_aware_negative_filtering=True)),
+    ):
+        qq, dd = q.clone().requires_grad_(True), d.clone().requires_grad_(True)
+        loss = mod(qq, dd, offset=1)
+        loss.backward()
+        out[f"{name}_loss"], out[f"{name}_dq"], out[f"{name}_dd"] = loss.detach().numpy(), qq.grad.numpy(), dd.grad.numpy()
+        assert torch.allclose(port(q, d, offset=1, use_smooth_max=True, **kw), loss.detach(), atol=1e-6), name
+    qq, dd = q.clone().requires_grad_(True), d[:4].clone().requires_grad_(True)
+    loss = ColbertSigmoidLoss(use_smooth_max=True)(qq, dd)
+    loss.backward()
+    out["sigmoid_loss"], out["sigmoid_dq"], out["sigmoid_dd"] = loss.detach().numpy(), qq.grad.numpy(), dd.grad.numpy()
+    for name, mod in (("negce", ColbertNegativeCELoss(use_smooth_max=True)),
+                      ("pairneg", ColbertPairwiseNegativeCELoss(use_smooth_max=True, in_batch_term_weight=0.3))):
+        qq, dd, nn = q.clone().requires_grad_(True), d.clone().requires_grad_(True), neg.clone().requires_grad_(True)
+        loss = mod(qq, dd, nn, offset=1)
+        loss.backward()
+        out[f"{name}_loss"], out[f"{name}_dq"], out[f"{name}_dd"], out[f"{name}_dn"] = (
+            loss.detach().numpy(), qq.grad.numpy(), dd.grad.numpy(), nn.grad.numpy())
+    # cfg3 (BASELINE configs[2]) with the smooth maximum, fp32 inputs = the numerical oracle
+    q3, d3, lens = O.cfg3_inputs()
+    out["cfg3_q_checksum"], out["cfg3_d_checksum"] = checksum(q3), checksum(d3)
+    for name, cls in (("colbert", ColbertLoss), ("pairwise", ColbertPairwiseCELoss)):
+        qq, dd = q3.float().requires_grad_(True), d3.float().requires_grad_(True)
+        loss = cls(use_smooth_max=True)(qq, dd)
+        loss.backward()
+        out[f"cfg3_{name}_fp32"] = loss.detach().numpy()
+        out[f"cfg3_{name}_dq"] = qq.grad.numpy()
+        out[f"cfg3_{name}_dd_first2"] = dd.grad[:2].numpy()
+        out[f"cfg3_{name}_dd_rownorm"] = dd.grad.norm(dim=-1).numpy().astype(np.float32)
+        print(f"  cfg3 smooth {name}: {float(loss):.5f}")
+    np.savez_compressed(os.path.join(GOLD, "loss_smooth.npz"), **out)
+    print("loss_smooth ok")
+
+
 def head_small():
     """Run the reference ColQwen2 (tiny random-init config) and capture the head's input/output."""
     from transformers.models.qwen2_vl import Qwen2VLConfig
@@ -251,7 +301,7 @@ def head_small():
 
 
 def wide_dims():
-    """DRAFT (r2): ColQwen3's embedding dim 320 -- scorer (ragged, bf16 and fp32 inputs), ColbertLoss with gradients,
+    """ColQwen3's embedding dim 320 -- scorer (ragged, bf16 and fp32 inputs), ColbertLoss with gradients,
     and the head of a tiny random-init reference ColQwen3 (models/qwen3/colqwen3/modeling_colqwen3.py)."""
     from transformers.models.qwen3_vl import Qwen3VLConfig
 
@@ -307,7 +357,8 @@ def wide_dims():
 
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
-    which = set(sys.argv[1:]) or {"scorer_small", "cfg1", "cfg2", "loss_small", "loss_neg_small", "loss_cfg3", "head_small"}
+    which = set(sys.argv[1:]) or {"scorer_small", "cfg1", "cfg2", "loss_small", "loss_neg_small", "loss_cfg3", "loss_smooth",
+                                  "head_small", "wide"}
     if "scorer_small" in which:
         scorer_small()
     if "cfg1" in which:
@@ -320,7 +371,9 @@ if __name__ == "__main__":
         loss_neg_small()
     if "loss_cfg3" in which:
         loss_cfg3()
+    if "loss_smooth" in which:
+        loss_smooth()
     if "head_small" in which:
         head_small()
-    if "wide" in which:  # DRAFT fixture, not in the default set
+    if "wide" in which:
         wide_dims()

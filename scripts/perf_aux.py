@@ -1,4 +1,4 @@
-"""GPU timings of the other hot-path rows (loss fwd/bwd at cfg3, projection head) and of the informal comparator
+"""(python scripts/perf_aux.py [--only loss|head|ref])  GPU timings of the other hot-path rows (loss fwd/bwd at cfg3, projection head) and of the informal comparator
 (the reference's own einsum/max/sum chain executed by PyTorch on the same B200).  Prints one JSON line each."""
 import json, sys, time
 import torch

@@ -1,5 +1,5 @@
-"""Round-2 timings of the drafts: K-pipelined scorer at dims 192/256/320 (cfg2 shape), wide head at dim 320 with and
-without the 2-CTA W multicast.  One JSON line each."""
+"""Timings of the wide-embedding kernels: K-pipelined scorer at dims 192/256/320 (cfg2 shape), wide head at dims 256/320 with
+and without the 2-CTA W multicast.  One JSON line each."""
 import json, sys
 import torch
 sys.path.insert(0, ".")

@@ -32,7 +32,7 @@ def test_exports_match_header(lib):
 
 
 def test_abi_version(lib):
-    assert lib.cpb_abi_version() == 1
+    assert lib.cpb_abi_version() == 2
 
 
 def test_argument_validation_needs_no_gpu(lib):
@@ -61,37 +61,66 @@ def test_product_path_fails_loudly_on_cpu():
 
 def test_every_entry_point_validates_before_touching_cuda(lib):
     """Bad arguments are rejected with CPB_E_INVALID / CPB_E_UNSUPPORTED and a message, without a GPU."""
+    import ctypes
+
+    from colpali_b200._lib import LossDesc, MaxSimArgs, MaxSimBwdArgs
+
     INVALID, UNSUPPORTED = -1, -2
-    # losses
-    rc = lib.cpb_colbert_loss_fwd(None, None, 4, 32, 3, 0, 0.02, 1, 0, 0.95, 0.5, 0, None, None, None, None)
-    assert rc == INVALID and b"positive index out of range" in lib.cpb_last_error()          # offset + B > C
-    rc = lib.cpb_colbert_loss_fwd(None, None, 4, 32, 4, 7, 0.02, 1, 0, 0.95, 0.5, 0, None, None, None, None)
-    assert rc == INVALID and b"unknown loss mode" in lib.cpb_last_error()
-    rc = lib.cpb_colbert_loss_fwd(None, None, 4, 32, 6, 2, 0.02, 1, 0, 0.95, 0.5, 0, None, None, None, None)
-    assert rc == INVALID and b"sigmoid" in lib.cpb_last_error()                               # needs a square matrix
-    rc = lib.cpb_colbert_loss_fwd(None, None, 4, 32, 4, 0, -1.0, 1, 0, 0.95, 0.5, 0, None, None, None, None)
-    assert rc == INVALID and b"temperature" in lib.cpb_last_error()
-    rc = lib.cpb_colbert_neg_loss_fwd(None, None, None, 4, 32, 4, 2, 0, 0.02, 1, 0, 0.95, 0.5, 0.5, 0, None, None, None, None)
-    assert rc == INVALID
+    err = lib.cpb_last_error
+    # losses (struct argument blocks: struct_size is checked first)
+    d = LossDesc(mode=0, temperature=0.02, normalize_scores=1, filter_threshold=0.95, filter_factor=0.5)
+
+    def loss(n_q, n_docs, dim=128):
+        return lib.cpb_colbert_loss_launch(ctypes.byref(d), None, None, n_q, 32, n_docs, dim, None)
+
+    assert loss(4, 3) == INVALID and b"positive index out of range" in err()                    # offset + B > C
+    d.mode = 7
+    assert loss(4, 4) == INVALID and b"unknown loss mode" in err()
+    d.mode = 2
+    assert loss(4, 6) == INVALID and b"sigmoid" in err()                                        # needs a square matrix
+    d.mode, d.temperature = 0, -1.0
+    assert loss(4, 4) == INVALID and b"temperature" in err()
+    d.temperature = 0.02
+    assert loss(4, 4, dim=200) == UNSUPPORTED and b"200" in err()
+    d.struct_size = 8
+    assert loss(4, 4) == INVALID and b"struct_size" in err()
+    # forward
+    a = MaxSimArgs(n_queries=1, nq_pad=32, n_docs=1, dim=128)
+    assert lib.cpb_maxsim_launch(ctypes.byref(a)) == INVALID and b"null device pointer" in err()
+    a.dim = 100
+    assert lib.cpb_maxsim_launch(ctypes.byref(a)) == UNSUPPORTED and b"100" in err()
+    a.dim, a.smooth_tau = 128, -1.0
+    a.d_q = a.d_docs = a.d_doc_start = a.d_doc_len = a.d_scores = 16  # non-null, never dereferenced on the host
+    a.doc_rows = 10
+    assert lib.cpb_maxsim_launch(ctypes.byref(a)) == INVALID and b"smooth_tau" in err()
+    a.smooth_tau, a.nq_real = 0.1, 0
+    assert lib.cpb_maxsim_launch(ctypes.byref(a)) == INVALID and b"nq_real" in err()
+    a.struct_size = 16
+    assert lib.cpb_maxsim_launch(ctypes.byref(a)) == INVALID and b"struct_size" in err()
+    assert lib.cpb_maxsim_launch(None) == INVALID
     # backward
-    rc = lib.cpb_maxsim_bwd(None, None, None, None, 4, 32, None, 10, None, 3, None, None, None)
-    assert rc == INVALID and b"null device pointer" in lib.cpb_last_error()
+    b = MaxSimBwdArgs(n_queries=4, nq_pad=32, n_docs=3, dim=128, doc_rows=10, max_doc_len=5)
+    assert lib.cpb_maxsim_bwd_launch(ctypes.byref(b)) == INVALID and b"exactly one of" in err()
+    b.d_argmax = 16
+    assert lib.cpb_maxsim_bwd_launch(ctypes.byref(b)) == INVALID and b"null device pointer" in err()
+    b.d_argmax, b.d_lse, b.dim = None, 16, 320
+    b.d_grad_scores = b.d_q = b.d_docs = b.d_doc_start = b.d_doc_len = 16
+    assert lib.cpb_maxsim_bwd_launch(ctypes.byref(b)) == INVALID and b"smooth_tau" in err()
+    b.smooth_tau = 0.1
+    assert lib.cpb_maxsim_bwd_launch(ctypes.byref(b)) == UNSUPPORTED and b"dim 128 only" in err()
     # head
     rc = lib.cpb_head_fwd(None, 0, 1536, None, None, 128, None, None, None, 0, None)
     assert rc == INVALID
     rc = lib.cpb_head_fwd(None, 10, 1536, None, None, 352, None, None, None, 0, None)
-    assert rc == UNSUPPORTED and b"352" in lib.cpb_last_error()                               # above ColQwen3's 320
+    assert rc == UNSUPPORTED and b"352" in err()                               # above ColQwen3's 320
     rc = lib.cpb_head_fwd(None, 10, 1536, None, None, 200, None, None, None, 0, None)
-    assert rc == UNSUPPORTED and b"200" in lib.cpb_last_error()                               # not a multiple of 32
+    assert rc == UNSUPPORTED and b"200" in err()                               # not a multiple of 32
     rc = lib.cpb_head_fwd(None, 10, 1000, None, None, 128, None, None, None, 0, None)
-    assert rc == UNSUPPORTED and b"multiple of 64" in lib.cpb_last_error()
-    # balanced / all-gather variants and their helpers
-    rc = lib.cpb_maxsim_fwd_balanced(None, 1, 32, None, 0, None, None, None, 1, None, None, None, 0, 0, 0, None, 0, 0, None)
-    assert rc == INVALID and b"epoch" in lib.cpb_last_error()
-    rc = lib.cpb_maxsim_fwd_allgather(None, 1, 32, None, 0, None, None, None, 1, None, 2, 0, 0, 0, 0, None, 0, 1, None, 0, 1, None)
-    assert rc == INVALID and b"peer" in lib.cpb_last_error()
-    assert lib.cpb_wait_flags(None, 2, 1, None) == INVALID
+    assert rc == UNSUPPORTED and b"multiple of 64" in err()
+    # helpers of the balanced / all-gather paths
+    assert lib.cpb_wait_flags(None, 2, 1, None, None) == INVALID
     assert lib.cpb_maxsim_split_workspace_bytes(32, 32) > 0
     # tuning knobs
     assert lib.cpb_set_option(b"cluster", 3) == INVALID and lib.cpb_set_option(b"no_such_option", 1) == INVALID
     assert lib.cpb_set_option(b"cluster", 0) == 0 and lib.cpb_set_option(b"balanced", 1) == 0
+    assert lib.cpb_set_option(b"pdl", 2) == INVALID and lib.cpb_set_option(b"pdl", 1) == 0

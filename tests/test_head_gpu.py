@@ -93,7 +93,7 @@ def test_unsupported_shapes_fail_loudly():
 @pytest.mark.parametrize("tokens,hidden,dim", [(5000, 2560, 320), (777, 2048, 320), (130, 64, 320), (1000, 1536, 192),
                                                (1000, 1536, 256), (127, 128, 160)])
 def test_wide_projection_dims_against_oracle(tokens, hidden, dim, head_cluster):
-    """DRAFT (r2): head_wide_sm100.cu -- ColQwen3's dim = 320 (models/qwen3/colqwen3/modeling_colqwen3.py:48) and
+    """head_wide_sm100.cu -- ColQwen3's dim = 320 (models/qwen3/colqwen3/modeling_colqwen3.py:48) and
     the other multiples of 32 above 128, with and without the 2-CTA W multicast."""
     from colpali_b200 import _lib
     gen = torch.Generator().manual_seed(hidden + dim)
@@ -121,7 +121,7 @@ def test_wide_projection_dims_against_oracle(tokens, hidden, dim, head_cluster):
 
 
 def test_wide_dim320_reference_model_forward_golden():
-    """DRAFT (r2): head of a random-init reference ColQwen3 (dim 320), captured by oracle/make_golden.py wide."""
+    """head of a random-init reference ColQwen3 (dim 320), captured by oracle/make_golden.py wide."""
     g = load_golden("wide_dim320.npz")
     mask = torch.from_numpy(g["h_mask"])
     h = from_bits(g["h_h"]).reshape(3, 24, -1)

@@ -284,7 +284,7 @@ def test_randomised_shapes_against_fp32_torch(seed):
 
 @pytest.mark.parametrize("dim", [192, 256, 300, 320])
 def test_wide_embeddings_k_pipelined_kernel(dim):
-    """DRAFT (r2-drafts): embedding dims above 128 (ColQwen3: 320) through cpb_maxsim_fwd_dim."""
+    """embedding dims above 128 (ColQwen3: 320) through the K-pipelined kernel."""
     dev = torch.device(DEV)
     g = torch.Generator().manual_seed(dim)
     lens = [int(x) for x in torch.randint(1, 700, (60,), generator=g)]
@@ -308,7 +308,7 @@ def test_wide_embeddings_k_pipelined_kernel(dim):
 
 
 def test_wide_dim320_against_reference_golden():
-    """DRAFT (r2): K-pipelined scorer at ColQwen3's dim against the reference's own outputs (ragged, N_q up to 32)."""
+    """K-pipelined scorer at ColQwen3's dim against the reference's own outputs (ragged, N_q up to 32)."""
     g = load_golden("wide_dim320.npz")
     qs = split_rows(from_bits(g["s_q"], (-1, 320)), g["s_qlen"])
     ps = split_rows(from_bits(g["s_p"], (-1, 320)), g["s_plen"])

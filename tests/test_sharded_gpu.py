@@ -69,31 +69,40 @@ def _fused_worker(rank, world, port, out_dir):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     from colpali_b200.sharded import FusedGatherScorer
 
-    qs = O.unit_rows((8, 32, 128), 5)
+    n_launch = 50
     docs = O.unit_rows((60, 200, 128), 50 + rank)          # every rank owns a different dense shard
     bank = cb.DocBank.from_passages(docs.to(dev), dev)
-    qb = cb.QueryBlock(qs.to(dev), dev)
+    qbs = [cb.QueryBlock(O.unit_rows((8, 32, 128), 500 + i).to(dev), dev) for i in range(n_launch)]  # same on all ranks
     ok = FusedGatherScorer.available(dev)
     res = {"available": np.array(ok)}
     if ok:
-        sc = FusedGatherScorer(8, 60, dev)
-        for _ in range(3):
-            gathered = sc.score(qb, bank)
-            sc.wait()  # per-launch completion words written by the last CTA of every rank's grid
+        # what every launch must produce: an NCCL all-gather of the local score slabs
+        want = torch.empty(n_launch, world, 8, 60, device=dev)
+        for i, qb in enumerate(qbs):
+            dist.all_gather_into_tensor(want[i].view(world * 8, 60), cb.maxsim(qb, bank))
+        for mc in (True, False):
+            sc = FusedGatherScorer(8, 60, dev, use_multicast=mc)
+            got = torch.empty_like(want)
+            # 50 back-to-back launches with different queries, NO host synchronisation or barrier in between: the double
+            # buffer + the per-launch completion counters are the only protection against overwriting unread slabs
+            for i, qb in enumerate(qbs):
+                view = sc.score(qb, bank)
+                sc.wait()
+                got[i].copy_(view)  # the consumer of launch i, stream-ordered before launch i + 2
             torch.cuda.synchronize()
-            dist.barrier()  # nobody starts the next launch (which overwrites the slabs) before everyone has read
-        snap = gathered.clone()
-        gathered = snap
-        res["gathered"] = gathered.cpu().numpy()
-        res["local"] = cb.maxsim(qb, bank).cpu().numpy()
+            sc.check_status()
+            res[f"equal_mc{int(mc)}"] = np.array([bool(torch.equal(got[i], want[i])) for i in range(n_launch)])
+            res[f"used_mc{int(mc)}"] = np.array(sc.mc_base != 0)
+            dist.barrier()
     np.savez(os.path.join(out_dir, f"f{rank}.npz"), **res)
     dist.barrier()
     dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_fused_allgather_two_ranks(tmp_path):
-    """The kernel stores its scores straight into both ranks' gathered buffers (NVLink peer stores)."""
+def test_fused_allgather_two_ranks_back_to_back(tmp_path):
+    """The kernel stores its scores straight into both ranks' gathered buffers (NVSwitch multicast or NVLink peer
+    stores); 50 launches back to back, every one compared with an NCCL all-gather."""
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
@@ -102,5 +111,6 @@ def test_fused_allgather_two_ranks(tmp_path):
     if not bool(r[0]["available"]):
         pytest.skip("symmetric memory is not available in this environment")
     for k in range(2):
-        for src in range(2):
-            assert np.array_equal(r[k]["gathered"][src], r[src]["local"]), (k, src)
+        for mc in (0, 1):
+            assert r[k][f"equal_mc{mc}"].all(), (k, mc, np.nonzero(~r[k][f"equal_mc{mc}"])[0][:10])
+        assert not bool(r[k]["used_mc0"])
