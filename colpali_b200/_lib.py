@@ -27,6 +27,8 @@ EXPORTED_SYMBOLS = (
     "cpb_maxsim_split_workspace_bytes",
     "cpb_wait_flags",
     "cpb_maxsim_bwd_launch",
+    "cpb_exchange_push",
+    "cpb_signal_peers",
     "cpb_head_fwd",
 )
 
@@ -91,12 +93,27 @@ class MaxSimBwdArgs(ctypes.Structure):
         ("d_q", c_vp), ("n_queries", c_i), ("nq_pad", c_i), ("nq_real", c_i), ("dim", c_i),
         ("d_docs", c_vp), ("doc_rows", c_i64), ("d_doc_start", c_vp), ("d_doc_len", c_vp), ("n_docs", c_i),
         ("max_doc_len", c_i),
-        ("d_dq", c_vp), ("d_dd", c_vp),
+        ("d_dq", c_vp), ("d_dd", c_vp), ("d_dd_doc_base", c_vp),
     ]
 
     def __init__(self, **kw):
         super().__init__(**kw)
         self.struct_size = ctypes.sizeof(MaxSimBwdArgs)
+
+
+class ExchangePushArgs(ctypes.Structure):
+    """``cpb_exchange_push_args`` (include/colpali_b200.h)."""
+
+    _fields_ = [
+        ("struct_size", c_u32), ("pad_first", c_u32), ("stream", c_vp),
+        ("d_src", c_vp), ("n_docs", c_i), ("len", c_i), ("slot_len", c_i), ("dim", c_i),
+        ("d_peer_bases", c_vp), ("mc_base", c_u64), ("n_peers", c_i),
+        ("bank_word_offset", c_i64), ("flag_word_offset", c_i64), ("grid_out", c_i),
+    ]
+
+    def __init__(self, **kw):
+        super().__init__(**kw)
+        self.struct_size = ctypes.sizeof(ExchangePushArgs)
 
 
 _lib: Optional[ctypes.CDLL] = None
@@ -150,6 +167,10 @@ def load() -> ctypes.CDLL:
     lib.cpb_wait_flags.argtypes = [c_vp, ci, c_u32, c_vp, c_vp]
     lib.cpb_maxsim_bwd_launch.restype = ci
     lib.cpb_maxsim_bwd_launch.argtypes = [ctypes.POINTER(MaxSimBwdArgs)]
+    lib.cpb_exchange_push.restype = ci
+    lib.cpb_exchange_push.argtypes = [ctypes.POINTER(ExchangePushArgs)]
+    lib.cpb_signal_peers.restype = ci
+    lib.cpb_signal_peers.argtypes = [c_vp, c_u64, ci, c_i64, c_vp]
     lib.cpb_head_fwd.restype = ci
     lib.cpb_head_fwd.argtypes = [
         c_vp, c_i64, ci,  # d_hidden, n_tokens, hidden

@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/colpali_b200.h"
+#include "exchange_params.h"
 #include "head_params.h"
 #include "loss_params.h"
 #include "maxsim_params.h"
@@ -317,13 +318,13 @@ int cpb_maxsim_launch(cpb_maxsim_args* a) {
     p.n_peers = n_peers;
     p.peer_slab_offset = slab_word_offset;
     p.peer_flag_offset = flag_word_offset;
-    if (d_wait_flags) {
-      if (n_wait < 1 || n_wait > 64) return fail(CPB_E_INVALID, "bad n_wait %d", n_wait);
-      p.wait_flags = d_wait_flags;
-      p.n_wait = n_wait;
-      p.wait_value = wait_value;
-      p.wait_timeout_ms = static_cast<uint32_t>(g_opt_wait_timeout_ms.load());
-    }
+  }
+  if (d_wait_flags) {  // fused all-gather: write-after-read guard; training exchange: the gathered bank is complete
+    if (n_wait < 1 || n_wait > 64) return fail(CPB_E_INVALID, "bad n_wait %d", n_wait);
+    p.wait_flags = d_wait_flags;
+    p.n_wait = n_wait;
+    p.wait_value = wait_value;
+    p.wait_timeout_ms = static_cast<uint32_t>(g_opt_wait_timeout_ms.load());
   }
   cpb::LossParams lp{};
   if (loss) {
@@ -465,8 +466,41 @@ int cpb_wait_flags(const uint32_t* d_flags, int n, uint32_t value, uint32_t* d_s
   return CPB_OK;
 }
 
+int cpb_exchange_push(cpb_exchange_push_args* a) {
+  if (!a || a->struct_size < offsetof(cpb_exchange_push_args, flag_word_offset) + sizeof(int64_t))
+    return fail(CPB_E_INVALID, "cpb_exchange_push_args is null or its struct_size is too small");
+  if (a->n_docs <= 0 || a->len < 0 || a->slot_len < a->len || a->slot_len <= 0) return fail(CPB_E_INVALID, "bad document block shape (%d docs, len %d, slot %d)", a->n_docs, a->len, a->slot_len);
+  if (a->dim <= 0 || (a->dim % 8) != 0) return fail(CPB_E_INVALID, "dim=%d must be a positive multiple of 8", a->dim);
+  if (!a->d_peer_bases || (a->len > 0 && !a->d_src)) return fail(CPB_E_INVALID, "null device pointer");
+  if (a->n_peers < 1 || a->n_peers > 64) return fail(CPB_E_INVALID, "bad peer count %d", a->n_peers);
+  if (a->bank_word_offset < 0 || (a->bank_word_offset & 3) || a->flag_word_offset < 0) return fail(CPB_E_INVALID, "bad symmetric-buffer offsets");
+  if (reinterpret_cast<uintptr_t>(a->d_src) & 15u) return fail(CPB_E_INVALID, "d_src is not 16-byte aligned");
+  cpb::ExchangePushParams p{};
+  p.src = static_cast<const __nv_bfloat16*>(a->d_src);
+  p.n_docs = a->n_docs;
+  p.len = a->len;
+  p.slot_len = a->slot_len;
+  p.dim = a->dim;
+  p.pad_first = a->pad_first ? 1 : 0;
+  p.peer_bases = a->d_peer_bases;
+  p.mc_base = a->mc_base;
+  p.n_peers = a->n_peers;
+  p.bank_word_offset = a->bank_word_offset;
+  p.flag_word_offset = a->flag_word_offset;
+  int grid = 0;
+  CPB_CUDA(cpb::exchange_push_launch(p, &grid, static_cast<cudaStream_t>(a->stream)));
+  if (CPB_HAS(a, cpb_exchange_push_args, grid_out)) a->grid_out = grid;
+  return CPB_OK;
+}
+
+int cpb_signal_peers(const uint64_t* d_peer_bases, uint64_t mc_base, int n_peers, int64_t flag_word_offset, void* stream_) {
+  if (!d_peer_bases || n_peers < 1 || n_peers > 64 || flag_word_offset < 0) return fail(CPB_E_INVALID, "bad peer arguments");
+  CPB_CUDA(cpb::signal_peers_launch(d_peer_bases, mc_base, n_peers, flag_word_offset, static_cast<cudaStream_t>(stream_)));
+  return CPB_OK;
+}
+
 int cpb_maxsim_bwd_launch(const cpb_maxsim_bwd_args* a) {
-  if (!a || a->struct_size < sizeof(cpb_maxsim_bwd_args)) return fail(CPB_E_INVALID, "cpb_maxsim_bwd_args is null or its struct_size is too small");
+  if (!a || a->struct_size < offsetof(cpb_maxsim_bwd_args, d_dd) + sizeof(float*)) return fail(CPB_E_INVALID, "cpb_maxsim_bwd_args is null or its struct_size is too small");
   const int dim = a->dim;
   if (dim != 128 && dim != 192 && dim != 256 && dim != 320)
     return fail(CPB_E_UNSUPPORTED, "embedding dim %d is not supported by this build (128, 192, 256, 320)", dim);
@@ -483,6 +517,8 @@ int cpb_maxsim_bwd_launch(const cpb_maxsim_bwd_args* a) {
   if (smooth && dim != 128) return fail(CPB_E_UNSUPPORTED, "the smooth-max backward serves dim 128 only (got %d)", dim);
   if (smooth && (a->nq_real <= 0 || a->nq_real > a->nq_pad)) return fail(CPB_E_INVALID, "smooth max needs 0 < nq_real <= nq_pad");
   if (a->max_doc_len <= 0) return fail(CPB_E_INVALID, "max_doc_len must be positive");
+  const uint64_t* dd_doc_base = CPB_HAS(a, cpb_maxsim_bwd_args, d_dd_doc_base) ? a->d_dd_doc_base : nullptr;
+  if (dd_doc_base && smooth) return fail(CPB_E_UNSUPPORTED, "the peer-scatter dD serves the hard max only");
   cpb::BwdParams p{};
   p.g = a->d_grad_scores;
   p.grad_out = a->d_grad_out;
@@ -495,6 +531,7 @@ int cpb_maxsim_bwd_launch(const cpb_maxsim_bwd_args* a) {
   p.doc_len = a->d_doc_len;
   p.dq = a->d_dq;
   p.dd = a->d_dd;
+  p.dd_doc_base = dd_doc_base;
   p.B = a->n_queries;
   p.C = a->n_docs;
   p.nq_pad = a->nq_pad;

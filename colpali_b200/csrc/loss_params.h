@@ -37,6 +37,9 @@ struct BwdParams {
   const int32_t* doc_len;     // [C]
   float* dq;                  // [q_rows, dim] written
   float* dd;                  // [doc_rows, dim] written (every row of every document)
+  const uint64_t* dd_doc_base; // or nullptr.  Multi-GPU training exchange: address of document c's [len_c, dim] fp32
+                              // gradient block in its OWNER rank's (pre-zeroed) accumulator, reached through the NVLink
+                              // peer mapping; rows are then ADDED there (red.global.add) instead of written to dd
   int B, C, nq_pad, nq_real, q_rows;
   int dim;                    // padded embedding dim: 128, 192, 256 or 320
   int max_doc_len;            // longest document

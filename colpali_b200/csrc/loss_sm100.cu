@@ -151,9 +151,17 @@ __global__ void __launch_bounds__(kDdThreads) maxsim_bwd_dd_kernel(const BwdPara
     } else {
       for (int k = 0; k < n; ++k) add_row(s_list[lo + k]);
     }
-    float2* dst = reinterpret_cast<float2*>(p.dd + (doc_row0 + t) * kDim);
+    if (p.dd_doc_base != nullptr) {
+      // exchange mode: this document belongs to another rank's batch; several ranks add into the same rows
+      if (n == 0) continue;
+      float2* dst = reinterpret_cast<float2*>(__ldg(p.dd_doc_base + c)) + static_cast<int64_t>(t0 + t) * (kDim / 2);
 #pragma unroll
-    for (int j = 0; j < P; ++j) dst[j * 32 + lane] = acc[j];
+      for (int j = 0; j < P; ++j) atomicAdd(dst + j * 32 + lane, acc[j]);  // red.global.add.v2.f32 over NVLink
+    } else {
+      float2* dst = reinterpret_cast<float2*>(p.dd + (doc_row0 + t) * kDim);
+#pragma unroll
+      for (int j = 0; j < P; ++j) dst[j * 32 + lane] = acc[j];
+    }
   }
 }
 
@@ -165,14 +173,14 @@ static cudaError_t maxsim_bwd_launch_p(const BwdParams& p, cudaStream_t stream) 
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
-  if (p.dd != nullptr) {
+  if (p.dd != nullptr || p.dd_doc_base != nullptr) {
     const size_t smem = static_cast<size_t>(p.q_rows) * sizeof(int);
     auto kern = maxsim_bwd_dd_kernel<P>;
     if (smem > 48 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
       if (e != cudaSuccess) return e;
     }
-    if (!p.contiguous) {  // rows between documents belong to nobody: zero them
+    if (!p.contiguous && p.dd_doc_base == nullptr) {  // rows between documents belong to nobody: zero them
       cudaError_t e = cudaMemsetAsync(p.dd, 0, static_cast<size_t>(p.doc_rows) * 64 * P * sizeof(float), stream);
       if (e != cudaSuccess) return e;
     }

@@ -68,7 +68,7 @@ def _loss_desc(mode, temperature, normalize, filt, thr, factor, offset, loss, gr
 
 
 def _maxsim_for_loss(qb: QueryBlock, bank: DocBank, need_grad: bool, smooth_tau: float, nq_real: int,
-                     loss_desc=None):
+                     loss_desc=None, wait=None):
     """One fused MaxSim launch; returns (scores, aux) with aux = int32 argmax (hard max) or fp32 lse (smooth max), the
     only per-(document, query row) state the backward needs.  With ``loss_desc`` the last CTA also emits the loss."""
     dev = bank.device
@@ -78,17 +78,19 @@ def _maxsim_for_loss(qb: QueryBlock, bank: DocBank, need_grad: bool, smooth_tau:
         aux = torch.empty(bank.n_docs, qb.n * qb.nq_pad, dtype=torch.float32 if smooth_tau > 0 else torch.int32, device=dev)
     launch_maxsim(qb, bank, scores=scores, argmax=aux if smooth_tau == 0 else None, lse=aux if smooth_tau > 0 else None,
                   smooth_tau=smooth_tau, nq_real=nq_real, loss=loss_desc,
-                  done_counter=_done_counter(dev) if loss_desc is not None else None)
+                  done_counter=_done_counter(dev) if loss_desc is not None else None, wait=wait)
     return scores, aux
 
 
 def _maxsim_backward(g, go, aux, smooth_tau, nq_real, q_flat, b, nq_pad, bank_flat, bank_start, bank_len, n_docs,
-                     max_len, need_dq, need_dd):
-    """dq [b * nq_pad, dim], dd [rows, dim] (fp32, fully written by the kernels) for one score matrix."""
+                     max_len, need_dq, need_dd, dd_doc_base=None):
+    """dq [b * nq_pad, dim], dd [rows, dim] (fp32, fully written by the kernels) for one score matrix.  With
+    ``dd_doc_base`` (int64 device tensor of per-document peer addresses) the document gradients are added straight into
+    their owner ranks' accumulators instead (multi-GPU exchange) and ``dd`` is None."""
     dev = q_flat.device
     dim = q_flat.shape[1]
     dq = torch.empty(b * nq_pad, dim, dtype=torch.float32, device=dev) if need_dq else None
-    dd = torch.empty(bank_flat.shape[0], dim, dtype=torch.float32, device=dev) if need_dd else None
+    dd = torch.empty(bank_flat.shape[0], dim, dtype=torch.float32, device=dev) if (need_dd and dd_doc_base is None) else None
     if not (need_dq or need_dd):
         return None, None
     a = _lib.MaxSimBwdArgs()
@@ -102,7 +104,8 @@ def _maxsim_backward(g, go, aux, smooth_tau, nq_real, q_flat, b, nq_pad, bank_fl
     a.d_docs, a.doc_rows = bank_flat.data_ptr(), bank_flat.shape[0]
     a.d_doc_start, a.d_doc_len, a.n_docs, a.max_doc_len = bank_start.data_ptr(), bank_len.data_ptr(), n_docs, int(max_len)
     a.d_dq = dq.data_ptr() if need_dq else None
-    a.d_dd = dd.data_ptr() if need_dd else None
+    a.d_dd = dd.data_ptr() if dd is not None else None
+    a.d_dd_doc_base = dd_doc_base.data_ptr() if (need_dd and dd_doc_base is not None) else None
     with torch.cuda.device(dev):
         a.stream = torch.cuda.current_stream(dev).cuda_stream
         rc = _lib.load().cpb_maxsim_bwd_launch(ctypes.byref(a))

@@ -200,7 +200,8 @@ def next_epoch() -> int:
 def launch_maxsim(q: "QueryBlock", bank: "DocBank", *, scores: Optional[torch.Tensor], argmax: Optional[torch.Tensor] = None,
                   lse: Optional[torch.Tensor] = None, round_bf16: bool = False, independent: bool = False,
                   smooth_tau: float = 0.0, nq_real: int = 0, loss: Optional[_lib.LossDesc] = None,
-                  done_counter: Optional[torch.Tensor] = None, gather: Optional[dict] = None) -> int:
+                  done_counter: Optional[torch.Tensor] = None, gather: Optional[dict] = None,
+                  wait: Optional[tuple] = None) -> int:
     """Fill a ``cpb_maxsim_args`` and enqueue the fused kernel on the current stream of ``bank.device``.
     Returns the number of CTAs launched (the fused all-gather's consumers count completions in CTAs)."""
     lib = _lib.load()
@@ -235,6 +236,8 @@ def launch_maxsim(q: "QueryBlock", bank: "DocBank", *, scores: Optional[torch.Te
             a.slab_word_offset, a.flag_word_offset = gather["slab_word_offset"], gather["flag_word_offset"]
             if gather.get("wait_flags"):
                 a.d_wait_flags, a.n_wait, a.wait_value = gather["wait_flags"], gather["n_peers"], gather["wait_value"]
+        if wait is not None:  # (device pointer to n local counter words, n, value they must have reached)
+            a.d_wait_flags, a.n_wait, a.wait_value = wait
         if loss is not None:
             a.loss = ctypes.pointer(loss)
             a.d_done_counter = done_counter.data_ptr()

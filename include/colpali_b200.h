@@ -223,9 +223,41 @@ typedef struct cpb_maxsim_bwd_args {
   int32_t max_doc_len;          /* longest document */
   float* d_dq;                  /* fp32 [n_queries * nq_pad, dim] out, or NULL to skip */
   float* d_dd;                  /* fp32 [doc_rows, dim] out, or NULL to skip */
+  const uint64_t* d_dd_doc_base; /* or NULL.  Hard max only, multi-GPU exchange: device array [n_docs] of addresses of each
+                                   document's [len, dim] fp32 gradient block in its OWNER rank's pre-zeroed accumulator
+                                   (NVLink peer mapping); gradient rows are then ADDED there (red.global.add) instead of
+                                   being written to d_dd -- the reduce-scatter of the reference's gather backward */
 } cpb_maxsim_bwd_args;
 
 int cpb_maxsim_bwd_launch(const cpb_maxsim_bwd_args* args);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Multi-GPU training exchange without a collective kernel (replaces accelerator.pad_across_processes + concat_all_gather,
+ * colpali_engine/trainer/contrastive_trainer.py:143-150, and pad_to_max_len_right + gather_with_grad,
+ * trainer/colmodel_torch_training.py:155-175): every rank writes its zero-padded [n_docs, slot_len, dim] document block
+ * into ALL ranks' copies of a symmetric buffer (multimem.st through the NVSwitch multicast mapping, or st.global through
+ * the NVLink peer mappings), then every CTA adds 1 (release, system scope) to word flag_word_offset on every rank.
+ * Consumers wait until that word has grown by grid_out (cpb_wait_flags, or cpb_maxsim_args.d_wait_flags in-kernel).
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct cpb_exchange_push_args {
+  uint32_t struct_size;
+  uint32_t pad_first;           /* 1: zero rows in front of the data (HF trainer), 0: behind it (torch-loop trainer) */
+  void* stream;
+  const void* d_src;            /* bf16 [n_docs, len, dim] contiguous */
+  int32_t n_docs, len, slot_len, dim;   /* slot_len >= len: rows per document in the gathered bank; dim % 8 == 0 */
+  const uint64_t* d_peer_bases; /* device array of n_peers symmetric-buffer base addresses */
+  uint64_t mc_base;             /* multicast address of the same buffer, or 0 */
+  int32_t n_peers;
+  int64_t bank_word_offset;     /* 4-byte words from the buffer base to this rank's block (multiple of 4) */
+  int64_t flag_word_offset;
+  int32_t grid_out;             /* written: CTAs launched = what the flag word grows by */
+} cpb_exchange_push_args;
+
+int cpb_exchange_push(cpb_exchange_push_args* args);
+
+/* Enqueue a one-thread kernel that adds 1 (release, system scope) to word flag_word_offset of every rank's buffer:
+ * publishes everything the stream did before (e.g. the peer adds of cpb_maxsim_bwd_launch with d_dd_doc_base). */
+int cpb_signal_peers(const uint64_t* d_peer_bases, uint64_t mc_base, int n_peers, int64_t flag_word_offset, void* stream);
 
 /* flags for cpb_head_fwd */
 #define CPB_HEAD_CLAMP_NORM 1u      /* norm = max(norm, 1e-12): ColModernVBert variant (modeling_colmodernvbert.py:59) */
