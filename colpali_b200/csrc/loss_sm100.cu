@@ -35,7 +35,9 @@ cudaError_t colbert_loss_launch(const LossParams& p, cudaStream_t stream) {
 // ------------------------------------------------------------------------------------------------
 // Embedding dim = 64 * P (P = 2..5): a lane owns the bf16 pairs {lane, lane + 32, ...} of a row.
 
-// dQ: one warp per query row, a gather over the C winning document tokens
+// dQ: one warp per query row, a gather over the C winning document tokens.  The (index, weight, start) triples of 32
+// documents are fetched by the 32 lanes at once and broadcast by shuffles, and four row gathers are in flight before the
+// first is consumed: the loop is a chain of dependent 256-byte loads otherwise (C = 64..512 iterations).
 template <int P>
 __global__ void __launch_bounds__(256) maxsim_bwd_dq_kernel(const BwdParams p) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -48,19 +50,55 @@ __global__ void __launch_bounds__(256) maxsim_bwd_dq_kernel(const BwdParams p) {
 #pragma unroll
   for (int j = 0; j < P; ++j) acc[j] = make_float2(0.f, 0.f);
   const float* g = p.g + static_cast<int64_t>(b) * p.C;
-#pragma unroll 2
-  for (int c = 0; c < p.C; ++c) {
-    const int idx = __ldg(p.argmax + static_cast<int64_t>(c) * p.q_rows + row);
-    if (idx < 0) continue;
-    const float w = __ldg(g + c) * scale;
-    if (w == 0.f) continue;  // block-diagonal gradients of the explicit-negative losses are mostly zero
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(p.docs + (static_cast<int64_t>(__ldg(p.doc_start + c)) + idx) * kDim);
+  auto src_of = [&](int64_t start, int idx) {
+    return reinterpret_cast<const uint32_t*>(p.docs + (start + idx) * kDim);
+  };
+  auto fma_row = [&](const uint32_t (&raw)[P], float w) {
 #pragma unroll
     for (int j = 0; j < P; ++j) {
-      const uint32_t raw = __ldg(src + j * 32 + lane);
-      const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(&raw);
+      const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(&raw[j]);
       acc[j].x = fmaf(w, __low2float(v), acc[j].x);
       acc[j].y = fmaf(w, __high2float(v), acc[j].y);
+    }
+  };
+  for (int c0 = 0; c0 < p.C; c0 += 32) {
+    const int c = c0 + lane;
+    int idx = -1;
+    float w = 0.f;
+    int start = 0;
+    if (c < p.C) {
+      idx = __ldg(p.argmax + static_cast<int64_t>(c) * p.q_rows + row);
+      w = __ldg(g + c) * scale;  // block-diagonal gradients of the explicit-negative losses are mostly zero
+      start = __ldg(p.doc_start + c);
+    }
+    unsigned act = __ballot_sync(0xffffffffu, idx >= 0 && w != 0.f);  // ascending document order: deterministic sums
+    while (act != 0u) {
+      int k[4];
+      float wk[4];
+      uint32_t raw[4][P];
+      int n = 0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        k[u] = act ? __ffs(act) - 1 : -1;
+        if (act) { act &= act - 1; ++n; }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int kk = k[u] < 0 ? 0 : k[u];
+        const int idx_k = __shfl_sync(0xffffffffu, idx, kk);
+        const int start_k = __shfl_sync(0xffffffffu, start, kk);
+        wk[u] = (u < n) ? __shfl_sync(0xffffffffu, w, kk) : 0.f;
+        if (u < n) {
+          const uint32_t* src = src_of(start_k, idx_k);
+#pragma unroll
+          for (int j = 0; j < P; ++j) raw[u][j] = __ldg(src + j * 32 + lane);
+        } else {
+#pragma unroll
+          for (int j = 0; j < P; ++j) raw[u][j] = 0u;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) fma_row(raw[u], wk[u]);
     }
   }
   float2* dst = reinterpret_cast<float2*>(p.dq + static_cast<int64_t>(row) * kDim);
