@@ -273,6 +273,12 @@ def score_multi_vector(
     ``batch_size`` no longer bounds memory (no score tensor is materialised); it is kept because it
     defines the reference's zero-padding groups, hence the result for ragged list inputs.
     Extra keyword ``round_bf16`` reproduces the reference's bf16-rounded scores for bf16 inputs.
+    ``ps`` may be a device-resident ``DocBank`` (build once, score many query batches).
+
+    Numerics: embeddings are contracted in bf16 with fp32 accumulation whatever the input dtype -- fp32 / fp16 inputs
+    are ROUNDED TO bf16 on entry (the reference scores them in their own dtype).  For bf16 inputs (what the Col* models
+    produce) the fp32 scores here are more accurate than the reference's bf16-rounded ones; for fp32 inputs expect
+    ~1e-2 relative difference from the reference, inside north_star's bf16 tolerance.
     """
     if len(qs) == 0:
         raise ValueError("No queries provided")
