@@ -324,8 +324,8 @@ int cpb_maxsim_launch(cpb_maxsim_args* a) {
     p.wait_flags = d_wait_flags;
     p.n_wait = n_wait;
     p.wait_value = wait_value;
-    p.wait_timeout_ms = static_cast<uint32_t>(g_opt_wait_timeout_ms.load());
   }
+  p.wait_timeout_ms = static_cast<uint32_t>(g_opt_wait_timeout_ms.load());
   cpb::LossParams lp{};
   if (loss) {
     if (nseg != 1 || d_peer_bases || !d_done_counter || !a->d_scores || (flags & CPB_FLAG_INDEPENDENT))

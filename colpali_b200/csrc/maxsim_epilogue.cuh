@@ -270,9 +270,13 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
     const int slot = split_slot(part, r);
     if (lane == 0) {
       const volatile uint32_t* f = reinterpret_cast<volatile uint32_t*>(p.split_flag + slot * 4 + quad);
+      // the neighbour CTA may not be resident yet (PDL overlap, an SM busy with another stream): wait for it as long
+      // as for a remote rank before calling it a protocol failure
       const uint64_t t0 = global_timer_ns();
+      const uint64_t limit = static_cast<uint64_t>(p.wait_timeout_ms) * 1000000ull;
       while (*f != p.epoch) {
-        if (global_timer_ns() - t0 > 4000000000ull) __trap();
+        if (global_timer_ns() - t0 > limit) __trap();
+        __nanosleep(32);
       }
     }
     __syncwarp();
