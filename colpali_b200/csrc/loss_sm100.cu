@@ -111,15 +111,16 @@ __global__ void __launch_bounds__(256) maxsim_bwd_dq_kernel(const BwdParams p) {
 // the query rows of its tokens and WRITES the gradient row once -- rows nobody points at are written as zeros, so the
 // caller does not pre-zero the [doc_rows, dim] fp32 buffer (34 MB at cfg3) and nothing is read-modify-written.
 // Buckets of at most 32 rows are summed in query-row order (deterministic); larger ones in arrival order.
-constexpr int kDdTokens = 256;
+// The kernel is a chain of dependent small loads (index -> weight -> query row), so it is sized for latency: 64 tokens
+// per CTA (8 per warp, ~1 100 CTAs at cfg3 = every SM full), index loads and row gathers issued in pairs.
+constexpr int kDdTokens = 64;
 constexpr int kDdThreads = 256;
 
 template <int P>
 __global__ void __launch_bounds__(kDdThreads) maxsim_bwd_dd_kernel(const BwdParams p) {
   extern __shared__ int s_list[];  // [q_rows] query rows grouped by token
-  __shared__ int s_cnt[kDdTokens + 1];
+  __shared__ int s_cnt[kDdTokens];
   __shared__ int s_off[kDdTokens + 1];
-  __shared__ int s_warp_tot[kDdThreads / 32];
   constexpr int kDim = 64 * P;
   const int c = blockIdx.x;
   const int t0 = blockIdx.y * kDdTokens;
@@ -129,36 +130,41 @@ __global__ void __launch_bounds__(kDdThreads) maxsim_bwd_dd_kernel(const BwdPara
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float scale = p.grad_out ? *p.grad_out : 1.f;
   const int32_t* am = p.argmax + static_cast<int64_t>(c) * p.q_rows;
-  for (int i = tid; i <= kDdTokens; i += kDdThreads) s_cnt[i] = 0;
+  if (tid < kDdTokens) s_cnt[tid] = 0;
   __syncthreads();
-  // histogram of winning tokens (rows whose gradient weight is zero are dropped here)
-  for (int row = tid; row < p.q_rows; row += kDdThreads) {
+  // bucket of a query row: its winning token if that lies in my range and the row's gradient weight is non-zero
+  auto bucket_of = [&](int row) {
     const int idx = __ldg(am + row) - t0;
-    if (idx >= 0 && idx < nt && __ldg(p.g + static_cast<int64_t>(row / p.nq_pad) * p.C + c) != 0.f) atomicAdd(&s_cnt[idx], 1);
+    return (idx >= 0 && idx < nt && __ldg(p.g + static_cast<int64_t>(row / p.nq_pad) * p.C + c) != 0.f) ? idx : -1;
+  };
+  // histogram (two rows per thread and iteration: independent load chains)
+  for (int row = tid; row < p.q_rows; row += 2 * kDdThreads) {
+    const int b0 = bucket_of(row);
+    const int b1 = (row + kDdThreads < p.q_rows) ? bucket_of(row + kDdThreads) : -1;
+    if (b0 >= 0) atomicAdd(&s_cnt[b0], 1);
+    if (b1 >= 0) atomicAdd(&s_cnt[b1], 1);
   }
   __syncthreads();
-  // exclusive scan of kDdTokens counters (one per thread)
-  {
-    const int v = s_cnt[tid];
-    int x = v;
+  if (warp == 0) {  // exclusive scan of the 64 counters by one warp (two per lane)
+    const int v0 = s_cnt[2 * lane], v1 = s_cnt[2 * lane + 1];
+    int x = v0 + v1;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int y = __shfl_up_sync(0xffffffffu, x, o);
       if (lane >= o) x += y;
     }
-    if (lane == 31) s_warp_tot[warp] = x;
-    __syncthreads();
-    int base = 0;
-    for (int w = 0; w < warp; ++w) base += s_warp_tot[w];
-    s_off[tid] = base + x - v;
-    if (tid == kDdThreads - 1) s_off[kDdTokens] = base + x;
-    s_cnt[tid] = 0;  // reused as the fill cursor
+    s_off[2 * lane] = x - v0 - v1;
+    s_off[2 * lane + 1] = x - v1;
+    if (lane == 31) s_off[kDdTokens] = x;
+    s_cnt[2 * lane] = 0;  // reused as the fill cursors
+    s_cnt[2 * lane + 1] = 0;
   }
   __syncthreads();
-  for (int row = tid; row < p.q_rows; row += kDdThreads) {
-    const int idx = __ldg(am + row) - t0;
-    if (idx >= 0 && idx < nt && __ldg(p.g + static_cast<int64_t>(row / p.nq_pad) * p.C + c) != 0.f)
-      s_list[s_off[idx] + atomicAdd(&s_cnt[idx], 1)] = row;
+  for (int row = tid; row < p.q_rows; row += 2 * kDdThreads) {
+    const int b0 = bucket_of(row);
+    const int b1 = (row + kDdThreads < p.q_rows) ? bucket_of(row + kDdThreads) : -1;
+    if (b0 >= 0) s_list[s_off[b0] + atomicAdd(&s_cnt[b0], 1)] = row;
+    if (b1 >= 0) s_list[s_off[b1] + atomicAdd(&s_cnt[b1], 1)] = row + kDdThreads;
   }
   __syncthreads();
   const int64_t doc_row0 = static_cast<int64_t>(__ldg(p.doc_start + c)) + t0;
@@ -167,13 +173,16 @@ __global__ void __launch_bounds__(kDdThreads) maxsim_bwd_dd_kernel(const BwdPara
     float2 acc[P];
 #pragma unroll
     for (int j = 0; j < P; ++j) acc[j] = make_float2(0.f, 0.f);
-    auto add_row = [&](int row) {
-      const float w = __ldg(p.g + static_cast<int64_t>(row / p.nq_pad) * p.C + c) * scale;
+    auto load_row = [&](int row, float& w, uint32_t (&raw)[P]) {
+      w = __ldg(p.g + static_cast<int64_t>(row / p.nq_pad) * p.C + c) * scale;
       const uint32_t* src = reinterpret_cast<const uint32_t*>(p.q + static_cast<int64_t>(row) * kDim);
 #pragma unroll
+      for (int j = 0; j < P; ++j) raw[j] = __ldg(src + j * 32 + lane);
+    };
+    auto fma_row = [&](float w, const uint32_t (&raw)[P]) {
+#pragma unroll
       for (int j = 0; j < P; ++j) {
-        const uint32_t raw = __ldg(src + j * 32 + lane);
-        const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(&raw);
+        const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(&raw[j]);
         acc[j].x = fmaf(w, __low2float(v), acc[j].x);
         acc[j].y = fmaf(w, __high2float(v), acc[j].y);
       }
@@ -182,12 +191,30 @@ __global__ void __launch_bounds__(kDdThreads) maxsim_bwd_dd_kernel(const BwdPara
       const int mine = (lane < n) ? s_list[lo + lane] : 0x7fffffff;
       int rank = 0;
       for (int k = 0; k < n; ++k) rank += (__shfl_sync(0xffffffffu, mine, k) < mine) ? 1 : 0;
+      // sorted[k] = the row of rank k, gathered into lane k
+      int sorted = 0x7fffffff;
       for (int k = 0; k < n; ++k) {
         const unsigned m = __ballot_sync(0xffffffffu, lane < n && rank == k);
-        add_row(__shfl_sync(0xffffffffu, mine, __ffs(m) - 1));
+        const int r = __shfl_sync(0xffffffffu, mine, __ffs(m) - 1);
+        if (lane == k) sorted = r;
+      }
+      for (int k = 0; k < n; k += 2) {  // two row gathers in flight
+        float w0, w1 = 0.f;
+        uint32_t r0[P], r1[P];
+        load_row(__shfl_sync(0xffffffffu, sorted, k), w0, r0);
+        const bool two = k + 1 < n;
+        const int row1 = __shfl_sync(0xffffffffu, sorted, two ? k + 1 : k);
+        if (two) load_row(row1, w1, r1);
+        fma_row(w0, r0);
+        if (two) fma_row(w1, r1);
       }
     } else {
-      for (int k = 0; k < n; ++k) add_row(s_list[lo + k]);
+      for (int k = 0; k < n; ++k) {
+        float w;
+        uint32_t r[P];
+        load_row(s_list[lo + k], w, r);
+        fma_row(w, r);
+      }
     }
     if (p.dd_doc_base != nullptr) {
       // exchange mode: this document belongs to another rank's batch; several ranks add into the same rows

@@ -76,25 +76,38 @@ __device__ __forceinline__ float tree32(const uint32_t (&v)[32]) {
   return fmax3(fmax3(w0, w1, u2), u3, u3);
 }
 
-// max over columns lo <= i < hi of a 32-column chunk
+// max over columns lo <= i < hi of a 32-column chunk (mask, then the FMNMX3 tree: no 32-deep dependency chain)
 __device__ __forceinline__ float max32_range(const uint32_t (&v)[32], float m, int lo, int hi) {
+  if (lo == 0 && hi == 32) return max32(v, m);
+  uint32_t x[32];
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    float x = (i >= lo && i < hi) ? __uint_as_float(v[i]) : -INFINITY;
-    m = fmaxf(m, x);
-  }
-  return m;
+  for (int i = 0; i < 32; ++i) x[i] = (i >= lo && i < hi) ? v[i] : 0xff800000u;  // -inf
+  return max32(x, m);
 }
 
 // running (value, first index) argmax over columns lo <= i < hi; strict '>' keeps the earliest maximum,
 // which is what torch.max(dim) returns on ties.  idx0 = document-relative index of column 0 of the chunk.
+// The chunk maximum comes from the FMNMX3 tree; only if it beats some lane's running maximum is the position of its
+// first occurrence looked up (compare + select per column, then a min tree) -- everything data-parallel: the obvious
+// running (m, idx) update is a 32-deep chain of dependent compare/select pairs and ran at ~45 cycles per column.
 __device__ __forceinline__ void argmax32_range(const uint32_t (&v)[32], float& m, int& idx, int idx0, int lo, int hi) {
+  uint32_t x[32];
+  const bool full = (lo == 0 && hi == 32);
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    float x = __uint_as_float(v[i]);
-    bool take = (i >= lo) && (i < hi) && (x > m);
-    m = take ? x : m;
-    idx = take ? (idx0 + i) : idx;
+  for (int i = 0; i < 32; ++i) x[i] = (full || (i >= lo && i < hi)) ? v[i] : 0xff800000u;  // -inf outside the range
+  const float t = tree32(x);
+  const bool take = t > m;
+  if (__any_sync(0xffffffffu, take)) {
+    int c[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) c[i] = (__uint_as_float(x[i]) == t) ? i : 64;
+#pragma unroll
+    for (int w = 16; w > 0; w >>= 1) {
+#pragma unroll
+      for (int i = 0; i < w; ++i) c[i] = min(c[i], c[i + w]);
+    }
+    m = take ? t : m;
+    idx = take ? (idx0 + c[0]) : idx;
   }
 }
 
@@ -529,12 +542,8 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
             mm = mb;
             while (doc_end <= tile_end) finish_doc();
           } else {
-#pragma unroll 1
-            for (int cb = 0; cb < n_valid; cb += 32) {
-              uint32_t v[32];
-              tmem_ld_x32(taddr + cb, v);
-              tmem_ld_wait();
-              reg_fence32(v);
+            // generic walk, software-pipelined over two register buffers: chunk c + 1 is in flight while chunk c folds
+            auto fold_chunk = [&](const uint32_t (&v)[32], int cb) {
               const int abs0 = row + cb;
               const int abs1 = min(abs0 + 32, tile_end);
               int pos = abs0;
@@ -553,6 +562,22 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
                 pos = seg_end;
                 if (doc_end > abs1) break;  // the current document continues past this chunk
                 finish_doc();
+              }
+            };
+            uint32_t va[32], vb[32];
+            tmem_ld_x32(taddr, va);
+#pragma unroll 1
+            for (int cb = 0; cb < n_valid; cb += 64) {
+              tmem_ld_wait();
+              reg_fence32(va);
+              const bool has_b = cb + 32 < n_valid;
+              if (has_b) tmem_ld_x32(taddr + cb + 32, vb);
+              fold_chunk(va, cb);
+              if (has_b) {
+                tmem_ld_wait();
+                reg_fence32(vb);
+                if (cb + 64 < n_valid) tmem_ld_x32(taddr + cb + 64, va);
+                fold_chunk(vb, cb + 32);
               }
             }
             release_acc();
