@@ -76,25 +76,28 @@ __device__ __forceinline__ float tree32(const uint32_t (&v)[32]) {
   return fmax3(fmax3(w0, w1, u2), u3, u3);
 }
 
+// Column masks are written as ONE unsigned compare per column, (unsigned)(i - lo) < (unsigned)(hi - lo), feeding a
+// select: the obvious `(i >= lo && i < hi) ? .. : ..` made nvcc emit a BSSY / BRA / BSYNC diamond per column (32 per
+// chunk), which is what made the generic epilogue walk ~10x slower than the tree paths.
+__device__ __forceinline__ void mask32(const uint32_t (&v)[32], uint32_t (&x)[32], int lo, int hi) {
+  const unsigned span = static_cast<unsigned>(hi - lo);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) x[i] = (static_cast<unsigned>(i - lo) < span) ? v[i] : 0xff800000u;  // -inf outside
+}
+
 // max over columns lo <= i < hi of a 32-column chunk (mask, then the FMNMX3 tree: no 32-deep dependency chain)
 __device__ __forceinline__ float max32_range(const uint32_t (&v)[32], float m, int lo, int hi) {
   if (lo == 0 && hi == 32) return max32(v, m);
   uint32_t x[32];
-#pragma unroll
-  for (int i = 0; i < 32; ++i) x[i] = (i >= lo && i < hi) ? v[i] : 0xff800000u;  // -inf
+  mask32(v, x, lo, hi);
   return max32(x, m);
 }
 
-// running (value, first index) argmax over columns lo <= i < hi; strict '>' keeps the earliest maximum,
-// which is what torch.max(dim) returns on ties.  idx0 = document-relative index of column 0 of the chunk.
-// The chunk maximum comes from the FMNMX3 tree; only if it beats some lane's running maximum is the position of its
-// first occurrence looked up (compare + select per column, then a min tree) -- everything data-parallel: the obvious
-// running (m, idx) update is a 32-deep chain of dependent compare/select pairs and ran at ~45 cycles per column.
-__device__ __forceinline__ void argmax32_range(const uint32_t (&v)[32], float& m, int& idx, int idx0, int lo, int hi) {
-  uint32_t x[32];
-  const bool full = (lo == 0 && hi == 32);
-#pragma unroll
-  for (int i = 0; i < 32; ++i) x[i] = (full || (i >= lo && i < hi)) ? v[i] : 0xff800000u;  // -inf outside the range
+// (value, first index) of the maximum of a chunk folded into the running pair; strict '>' keeps the earliest maximum,
+// which is what torch.max(dim) returns on ties.  The chunk maximum comes from the FMNMX3 tree; only if it beats some
+// lane's running maximum is the position of its first occurrence looked up (compare + select per column, then a min
+// tree) -- everything data-parallel instead of a 32-deep chain of dependent compare / select pairs.
+__device__ __forceinline__ void argmax32_core(const uint32_t (&x)[32], float& m, int& idx, int idx0) {
   const float t = tree32(x);
   const bool take = t > m;
   if (__any_sync(0xffffffffu, take)) {
@@ -108,6 +111,16 @@ __device__ __forceinline__ void argmax32_range(const uint32_t (&v)[32], float& m
     }
     m = take ? t : m;
     idx = take ? (idx0 + c[0]) : idx;
+  }
+}
+// the same over columns lo <= i < hi; idx0 = document-relative index of column 0 of the chunk
+__device__ __forceinline__ void argmax32_range(const uint32_t (&v)[32], float& m, int& idx, int idx0, int lo, int hi) {
+  if (lo == 0 && hi == 32) {
+    argmax32_core(v, m, idx, idx0);
+  } else {
+    uint32_t x[32];
+    mask32(v, x, lo, hi);
+    argmax32_core(x, m, idx, idx0);
   }
 }
 
@@ -149,9 +162,10 @@ __device__ __forceinline__ float lg2_approx(float x) {
 __device__ __forceinline__ void lse32_range(const uint32_t (&v)[32], float& m, float& l, float c, int lo, int hi) {
   float y[32];
   float cm = -INFINITY;
+  const unsigned span = static_cast<unsigned>(hi - lo);
 #pragma unroll
   for (int i = 0; i < 32; ++i) {
-    y[i] = (i >= lo && i < hi) ? __uint_as_float(v[i]) * c : -INFINITY;
+    y[i] = (static_cast<unsigned>(i - lo) < span) ? __uint_as_float(v[i]) * c : -INFINITY;
     cm = fmaxf(cm, y[i]);
   }
   const float mn = fmaxf(m, cm);
@@ -201,6 +215,7 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
   const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
   const bool round_ref = (p.flags & CPB_FLAG_ROUND_BF16) != 0;
   const bool skip = (p.flags & CPB_DBG_SKIP_EPILOGUE) != 0;
+  const bool shifted_boundary = p.boundary_mode == 1;  // read once: a constant-bank load inside the hold window costs ~60 cycles
 
   // document `doc` is complete for resident query tile r: fold this query segment's 32 token maxima
   // (smooth mode: mm / ll are the online log-sum-exp pair in base-2 units, late_interaction_losses.py:40-44)
@@ -334,7 +349,10 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
       const int tile_end = row + n_valid;
       int nxt = cur, nxt_row0 = cur_row0, nxt_end = cur_end, nxt_nlen = cur_nlen;
       float nxt_ninit = cur_ninit;
-#pragma unroll
+      // One copy of the job body for the argmax / smooth modes: with the loop over the resident query tiles unrolled
+      // the generic walk exists twice and the kernel outgrows the instruction cache (measured: the cfg3 argmax forward
+      // ran at ~12 k cycles per job).  The max mode keeps the unrolled form its per-job budget was tuned with.
+#pragma unroll(kMode == kModeMax ? R : 1)
       for (int r = 0; r < R; ++r) {
         if (r < r_cnt) {
           const uint32_t a = job & 1u;
@@ -345,8 +363,9 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
           long long t2 = 0;
           tc_fence_after();
           const uint32_t taddr = tmem_base + lane_base + a * kTileN;
-          float mm = m[r], ll = ls[r];
-          int ai = am[r];
+          // per-tile state by select, not by index: r is a run-time value when the loop is not unrolled
+          float mm = (r == 0) ? m[0] : m[R - 1], ll = (r == 0) ? ls[0] : ls[R - 1];
+          int ai = (r == 0) ? am[0] : am[R - 1];
           int doc = cur, doc_row0 = cur_row0, doc_end = cur_end, doc_nlen = cur_nlen;
           float doc_ninit = cur_ninit;
 
@@ -433,7 +452,7 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
             mm = max32(vc, mm);
             mm = max32(vd, mm);
             while (doc_end <= tile_end) finish_doc();  // document (and empty followers) ending at the tile end
-          } else if (path == 2 && p.boundary_mode == 1 && doc_end - row >= 32 && doc_end - row <= kTileN - 32) {
+          } else if (path == 2 && shifted_boundary && doc_end - row >= 32 && doc_end - row <= kTileN - 32) {
             // one boundary at column b, at least 32 columns from either edge: read the tile as 32-column chunks
             // ALIGNED TO THE BOUNDARY -- the old document's columns [0, b) as chunks at min(32 i, b - 32), the new
             // one's [b, 256) at min(b + 32 j, 224).  Chunks of one document may overlap (a maximum is idempotent), so
@@ -530,20 +549,26 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
             tmem_ld_wait();
             reg_fence32(va);
             release_acc();
-            {
+            {  // split the boundary chunk: columns < bl belong to the old document (two masked trees, branch-free)
               const int bl = b & 31;
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                const float x = __uint_as_float(va[i]);
-                if (i < bl) mm = fmaxf(mm, x); else mb = fmaxf(mb, x);
-              }
+              mm = max32_range(va, mm, 0, bl);
+              mb = max32_range(va, mb, bl, 32);
             }
             finish_doc();  // old document (running max mm); the cursor moves to the new one, whose max is mb
             mm = mb;
             while (doc_end <= tile_end) finish_doc();
           } else {
-            // generic walk, software-pipelined over two register buffers: chunk c + 1 is in flight while chunk c folds
-            auto fold_chunk = [&](const uint32_t (&v)[32], int cb) {
+            // generic walk, software-pipelined: chunk c + 1 is in flight (into `w`) while chunk c folds (from `v`); one
+            // copy of the fold code, 32 register moves per chunk
+            uint32_t v[32], w[32];
+            tmem_ld_x32(taddr, w);
+#pragma unroll 1
+            for (int cb = 0; cb < n_valid; cb += 32) {
+              tmem_ld_wait();
+              reg_fence32(w);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = w[i];
+              if (cb + 32 < n_valid) tmem_ld_x32(taddr + cb + 32, w);
               const int abs0 = row + cb;
               const int abs1 = min(abs0 + 32, tile_end);
               int pos = abs0;
@@ -563,22 +588,6 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
                 if (doc_end > abs1) break;  // the current document continues past this chunk
                 finish_doc();
               }
-            };
-            uint32_t va[32], vb[32];
-            tmem_ld_x32(taddr, va);
-#pragma unroll 1
-            for (int cb = 0; cb < n_valid; cb += 64) {
-              tmem_ld_wait();
-              reg_fence32(va);
-              const bool has_b = cb + 32 < n_valid;
-              if (has_b) tmem_ld_x32(taddr + cb + 32, vb);
-              fold_chunk(va, cb);
-              if (has_b) {
-                tmem_ld_wait();
-                reg_fence32(vb);
-                if (cb + 64 < n_valid) tmem_ld_x32(taddr + cb + 64, va);
-                fold_chunk(vb, cb + 32);
-              }
             }
             release_acc();
           }
@@ -588,9 +597,15 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
             e_post += t3 - t2;
             if (path == 2) { e_hold2 += t2 - t1; ++n_path2; } else { e_hold += t2 - t1; }
           }
-          m[r] = mm;
-          am[r] = ai;
-          ls[r] = ll;
+          if (r == 0) {
+            m[0] = mm;
+            am[0] = ai;
+            ls[0] = ll;
+          } else {
+            m[R - 1] = mm;
+            am[R - 1] = ai;
+            ls[R - 1] = ll;
+          }
           nxt = doc;
           nxt_row0 = doc_row0;
           nxt_end = doc_end;
@@ -608,8 +623,8 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
     if (p.balanced && !skip && cur < p.n_docs && cur_end != 0x7fffffff && cur_row0 < bal_r1 && cur_end > bal_r1) {
       // my last document continues in the next partition: combine with the neighbour's partial and emit it
       for (int r = 0; r < r_cnt; ++r) {
-        float mm = m[r];
-        int ai = am[r];
+        float mm = (r == 0) ? m[0] : m[R - 1];
+        int ai = (r == 0) ? am[0] : am[R - 1];
         if (head_frag && cur == first_doc) {
           // (a document longer than a whole partition is excluded by the host: it would need a chain)
           __trap();

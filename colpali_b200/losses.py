@@ -37,7 +37,7 @@ import ctypes
 import torch
 
 from . import _lib
-from .scoring import DocBank, QueryBlock, launch_maxsim
+from .scoring import DocBank, QueryBlock, _on_device, launch_maxsim
 
 
 _DONE_COUNTERS: dict = {}
@@ -106,7 +106,7 @@ def _maxsim_backward(g, go, aux, smooth_tau, nq_real, q_flat, b, nq_pad, bank_fl
     a.d_dq = dq.data_ptr() if need_dq else None
     a.d_dd = dd.data_ptr() if dd is not None else None
     a.d_dd_doc_base = dd_doc_base.data_ptr() if (need_dd and dd_doc_base is not None) else None
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         a.stream = torch.cuda.current_stream(dev).cuda_stream
         rc = _lib.load().cpb_maxsim_bwd_launch(ctypes.byref(a))
     _lib.check(rc, "cpb_maxsim_bwd_launch")
@@ -146,7 +146,7 @@ class _InBatchLossFn(torch.autograd.Function):
         else:
             scores, aux = _maxsim_for_loss(qb, bank, need_grad, smooth_tau, nq_real)
             desc = _loss_desc(mode, temperature, normalize, filt, thr, factor, offset, loss, g, bounds_out)
-            with torch.cuda.device(dev):
+            with _on_device(dev):
                 rc = _lib.load().cpb_colbert_loss_launch(ctypes.byref(desc), scores.data_ptr(), qb.flat.data_ptr(), b,
                                                          qb.nq_pad, c, qb.flat.shape[1],
                                                          torch.cuda.current_stream(dev).cuda_stream)
@@ -198,7 +198,7 @@ class _NegLossFn(torch.autograd.Function):
         g_neg = torch.empty(b, b * n_neg, dtype=torch.float32, device=dev) if need_grad else None
         desc = _loss_desc(inner_mode, temperature, normalize, filt, thr, factor, offset, loss, g_pos, None, s_neg, n_neg,
                           weight, g_neg)
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             rc = _lib.load().cpb_colbert_loss_launch(ctypes.byref(desc), s_pos.data_ptr(), qb.flat.data_ptr(), b, qb.nq_pad,
                                                      c, qb.flat.shape[1], torch.cuda.current_stream(dev).cuda_stream)
         _lib.check(rc, "cpb_colbert_loss_launch")

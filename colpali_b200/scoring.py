@@ -192,6 +192,23 @@ def _split_workspace(dev: torch.device, stream_id: int, nbytes: int) -> torch.Te
     return ws
 
 
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+_NULL_CTX = _NullCtx()
+
+
+def _on_device(dev: torch.device):
+    """``torch.cuda.device(dev)`` only when it is not already the current device (the context manager costs ~8 us of
+    host time per launch, comparable to the small kernels of the loss path)."""
+    return _NULL_CTX if torch.cuda.current_device() == dev.index else torch.cuda.device(dev)
+
+
 def next_epoch() -> int:
     _EPOCH[0] = _EPOCH[0] % 0xFFFFFFF0 + 1
     return _EPOCH[0]
@@ -209,8 +226,9 @@ def launch_maxsim(q: "QueryBlock", bank: "DocBank", *, scores: Optional[torch.Te
     dim = int(bank.flat.shape[1])
     if q.flat.shape[1] != dim:
         raise ValueError(f"queries have (padded) dim {q.flat.shape[1]}, documents {dim}")
-    ws_bytes = lib.cpb_maxsim_workspace_bytes(q.n, q.nq_pad, bank.n_docs)
-    ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev) if ws_bytes else None
+    ws = None
+    if q.nq_pad > 32:  # per-segment partial scores, summed by a second tiny kernel
+        ws = torch.empty(lib.cpb_maxsim_workspace_bytes(q.n, q.nq_pad, bank.n_docs) // 4, dtype=torch.float32, device=dev)
     a = _lib.MaxSimArgs()
     a.flags = ((_lib.CPB_FLAG_ROUND_BF16 if round_bf16 else 0) | (_lib.CPB_FLAG_CONTIGUOUS if bank.contiguous else 0)
                | (_lib.CPB_FLAG_INDEPENDENT if independent else 0))
@@ -224,7 +242,7 @@ def launch_maxsim(q: "QueryBlock", bank: "DocBank", *, scores: Optional[torch.Te
     a.d_lse = lse.data_ptr() if lse is not None else None
     a.d_workspace = ws.data_ptr() if ws is not None else None
     a.smooth_tau = float(smooth_tau)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         stream = torch.cuda.current_stream(dev)
         a.stream = stream.cuda_stream
         if dim == EMBED_DIM and bank.contiguous and bank.max_len > 0 and smooth_tau == 0.0:
