@@ -316,6 +316,12 @@ def run_b200(args):
         e1.record()
         torch.cuda.synchronize()
         ms_kernel = e0.elapsed_time(e1) / k_steps
+    # the exchange makes all ranks run at the pace of the slowest GPU (power-limited clocks differ by a few per cent):
+    # report that GPU's kernel-alone time next to rank 0's, so the cost of the exchange itself can be read off
+    ms_kernel_all = torch.tensor([ms_kernel], device=dev)
+    if world > 1:
+        dist.all_reduce(ms_kernel_all, op=dist.ReduceOp.MAX)
+    ms_kernel_slowest = float(ms_kernel_all)
 
     # ---- end to end through the public API: host buffers in, host scores out ----------------------------------------
     # N = 1: colpali_b200.score_multi_vector (the reference's scorer signature).  N > 1: the sharded API -- every rank
@@ -404,7 +410,8 @@ def run_b200(args):
                 "bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": achieved / pk["bf16_tflops"], "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": pk["source"] + " burst",
-                "kernel_ms": ms_kernel, "algorithmic_flops_per_launch": FLOPS_PER_STEP,
+                "kernel_ms": ms_kernel, "kernel_ms_slowest_rank": ms_kernel_slowest,
+                "algorithmic_flops_per_launch": FLOPS_PER_STEP,
                 "algorithmic_bytes_per_launch": MIN_BYTES_PER_STEP,
                 "hbm_gbs_achieved": MIN_BYTES_PER_STEP / (ms_kernel * 1e-3) / 1e9,
             },

@@ -178,24 +178,46 @@ head_wide_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_consta
       tc_fence_after();
       const int64_t row = tile * kWBM + quad * 32 + lane;
       const uint32_t taddr = tmem_base + lane_base + a * 256;
+      // Both passes read the accumulator in 32-column chunks through two register buffers: chunk c + 1 is in flight
+      // while chunk c is consumed (the epilogue is ~7 k instructions per token row at dim 320 and, with a single
+      // accumulator, serial with the MMAs of the next tile -- every cycle here is tensor idle time).
       // pass 1: squared norm of the (bf16-rounded) projection row
       float ss = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < n_chunks; ++c) {
-        uint32_t v[32];
-        tmem_ld_x32(taddr + c * 32, v);
-        tmem_ld_wait();
-        reg_fence32(v);
+      auto sq_chunk = [&](const uint32_t (&v)[32], int c) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           float x = __uint_as_float(v[j]) + s_bias[c * 32 + j];
           if (!single) x = rbf_w(x);      // nn.Linear output is bf16                     (modeling_colqwen3.py:87)
           ss = fmaf(x, x, ss);
         }
+      };
+      {
+        uint32_t va[32], vb[32];
+        tmem_ld_x32(taddr, va);
+#pragma unroll 1
+        for (int c = 0; c < n_chunks; c += 2) {
+          tmem_ld_wait();
+          reg_fence32(va);
+          if (c + 1 < n_chunks) tmem_ld_x32(taddr + (c + 1) * 32, vb);
+          sq_chunk(va, c);
+          if (c + 1 < n_chunks) {
+            tmem_ld_wait();
+            reg_fence32(vb);
+            if (c + 2 < n_chunks) tmem_ld_x32(taddr + (c + 2) * 32, va);
+            sq_chunk(vb, c + 1);
+          }
+        }
       }
       float nrm = sqrtf(ss);
       if (!single) nrm = rbf_w(nrm);      // proj.norm(...) is a bf16 tensor               (:90)
       if (clamp) nrm = fmaxf(nrm, 1e-12f);
+      // x / nrm as reciprocal + one Newton step on the residual: the correctly rounded quotient for all but a
+      // vanishing fraction of operands at a third of the instructions of an IEEE division (320 of them per row)
+      const float inv = 1.0f / nrm;
+      auto div_nrm = [&](float x) {
+        const float y = x * inv;
+        return fmaf(fmaf(-y, nrm, x), inv, y);
+      };
       float mk = 1.f;
       const bool live = row < p.n_tokens;
       if (live) {
@@ -203,39 +225,50 @@ head_wide_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_consta
         if (p.extra_mask) mk *= (p.extra_mask[row] != 0) ? 1.f : 0.f;                      // (:93-96)
       }
       // pass 2: normalise, mask, store
-#pragma unroll 1
-      for (int c = 0; c < n_chunks; ++c) {
-        uint32_t v[32];
-        tmem_ld_x32(taddr + c * 32, v);
-        tmem_ld_wait();
-        reg_fence32(v);
-        if (c == n_chunks - 1) {  // the whole accumulator has been read twice: hand it back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[a]);
-        }
-        if (live) {
-          uint4* dst = reinterpret_cast<uint4*>(p.out + row * dim + c * 32);
+      auto out_chunk = [&](const uint32_t (&v)[32], int c) {
+        if (!live) return;
+        uint4* dst = reinterpret_cast<uint4*>(p.out + row * dim + c * 32);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint32_t w[4];
+        for (int j = 0; j < 4; ++j) {
+          uint32_t w[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              float x0 = __uint_as_float(v[8 * j + 2 * u]) + s_bias[c * 32 + 8 * j + 2 * u];
-              float x1 = __uint_as_float(v[8 * j + 2 * u + 1]) + s_bias[c * 32 + 8 * j + 2 * u + 1];
-              if (!single) {
-                x0 = rbf_w(x0);
-                x1 = rbf_w(x1);
-              }
-              float y0 = x0 / nrm, y1 = x1 / nrm;
-              if (!single) {
-                y0 = rbf_w(y0);           // the quotient is a bf16 tensor                 (:90)
-                y1 = rbf_w(y1);
-              }
-              const __nv_bfloat162 pk = __floats2bfloat162_rn(y0 * mk, y1 * mk);
-              w[u] = *reinterpret_cast<const uint32_t*>(&pk);
+          for (int u = 0; u < 4; ++u) {
+            float x0 = __uint_as_float(v[8 * j + 2 * u]) + s_bias[c * 32 + 8 * j + 2 * u];
+            float x1 = __uint_as_float(v[8 * j + 2 * u + 1]) + s_bias[c * 32 + 8 * j + 2 * u + 1];
+            if (!single) {
+              x0 = rbf_w(x0);
+              x1 = rbf_w(x1);
             }
-            dst[j] = make_uint4(w[0], w[1], w[2], w[3]);
+            float y0 = div_nrm(x0), y1 = div_nrm(x1);
+            if (!single) {
+              y0 = rbf_w(y0);           // the quotient is a bf16 tensor                 (:90)
+              y1 = rbf_w(y1);
+            }
+            const __nv_bfloat162 pk = __floats2bfloat162_rn(y0 * mk, y1 * mk);
+            w[u] = *reinterpret_cast<const uint32_t*>(&pk);
+          }
+          dst[j] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      };
+      auto release = [&]() {  // the whole accumulator has been read twice: hand it back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[a]);
+      };
+      {
+        uint32_t va[32], vb[32];
+        tmem_ld_x32(taddr, va);
+#pragma unroll 1
+        for (int c = 0; c < n_chunks; c += 2) {
+          tmem_ld_wait();
+          reg_fence32(va);
+          if (c + 1 < n_chunks) tmem_ld_x32(taddr + (c + 1) * 32, vb); else release();
+          out_chunk(va, c);
+          if (c + 1 < n_chunks) {
+            tmem_ld_wait();
+            reg_fence32(vb);
+            if (c + 2 < n_chunks) tmem_ld_x32(taddr + (c + 2) * 32, va); else release();
+            out_chunk(vb, c + 1);
           }
         }
       }

@@ -262,7 +262,7 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
   int am[R];
   uint32_t job = 0;
   const bool dbg = (p.flags & CPB_DBG_CLOCKS) != 0;
-  long long e_wait = 0, e_hold = 0, e_post = 0, e_hold2 = 0;
+  long long e_wait = 0, e_hold = 0, e_post = 0, e_hold2 = 0, e_genwait = 0;
   int n_path2 = 0;
 
   // ---- balanced mode: which document contains the first row of my partition, and is it cut? ----------------
@@ -564,7 +564,9 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
             tmem_ld_x32(taddr, w);
 #pragma unroll 1
             for (int cb = 0; cb < n_valid; cb += 32) {
+              const long long tw = dbg ? clock64() : 0;
               tmem_ld_wait();
+              if (dbg) e_genwait += clock64() - tw;
               reg_fence32(w);
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = w[i];
@@ -640,7 +642,7 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
     o[2] = static_cast<float>(e_wait);
     o[3] = static_cast<float>(e_hold);
     o[4] = static_cast<float>(e_post);
-    o[5] = static_cast<float>(e_hold2);
+    o[5] = static_cast<float>(kMode == kModeMax ? e_hold2 : e_genwait);  // argmax / smooth: cycles blocked in tcgen05.wait::ld
     o[6] = static_cast<float>(n_path2);
     o[7] = static_cast<float>(job);
   }

@@ -127,8 +127,8 @@ __global__ void __launch_bounds__(kThreads) smooth_bwd_dq_kernel(const BwdParams
     const float w_lo = ok_lo ? __ldg(p.g + static_cast<int64_t>(b_lo) * p.C + c) * scale : 0.f;
     const float w_hi = ok_hi ? __ldg(p.g + static_cast<int64_t>(b_hi) * p.C + c) * scale : 0.f;
     // exponent offsets in base-2 units: P = 2^(c * s - c * lse)
-    const float l_lo = ok_lo ? __ldg(p.lse + static_cast<int64_t>(c) * p.q_rows + r_lo) * p.smooth_c : 0.f;
-    const float l_hi = ok_hi ? __ldg(p.lse + static_cast<int64_t>(c) * p.q_rows + r_hi) * p.smooth_c : 0.f;
+    const float l_lo = ok_lo ? __ldg(p.lse + static_cast<int64_t>(c) * p.q_rows + r_lo) * p.smooth_c : INFINITY;
+    const float l_hi = ok_hi ? __ldg(p.lse + static_cast<int64_t>(c) * p.q_rows + r_hi) * p.smooth_c : INFINITY;
     for (int t0 = 0; t0 < len; t0 += kTile) {
       __syncthreads();  // the previous tile has been consumed by every warp
       load_tile(tile, p.docs, start + t0, start + len);
@@ -139,10 +139,11 @@ __global__ void __launch_bounds__(kThreads) smooth_bwd_dq_kernel(const BwdParams
       uint32_t pa[4][4];
 #pragma unroll
       for (int nb = 0; nb < 8; ++nb) {
-        const float p0 = ok_lo ? w_lo * ex2(fmaf(s[nb][0], p.smooth_c, -l_lo)) : 0.f;
-        const float p1 = ok_lo ? w_lo * ex2(fmaf(s[nb][1], p.smooth_c, -l_lo)) : 0.f;
-        const float p2 = ok_hi ? w_hi * ex2(fmaf(s[nb][2], p.smooth_c, -l_hi)) : 0.f;
-        const float p3 = ok_hi ? w_hi * ex2(fmaf(s[nb][3], p.smooth_c, -l_hi)) : 0.f;
+        // rows that do not count carry w = 0 and an exponent offset of +inf: 2^(-inf) = 0, no branch, no 0 * inf
+        const float p0 = w_lo * ex2(fmaf(s[nb][0], p.smooth_c, -l_lo));
+        const float p1 = w_lo * ex2(fmaf(s[nb][1], p.smooth_c, -l_lo));
+        const float p2 = w_hi * ex2(fmaf(s[nb][2], p.smooth_c, -l_hi));
+        const float p3 = w_hi * ex2(fmaf(s[nb][3], p.smooth_c, -l_hi));
         pa[nb >> 1][(nb & 1) * 2 + 0] = pack_bf16(p0, p1);
         pa[nb >> 1][(nb & 1) * 2 + 1] = pack_bf16(p2, p3);
       }
@@ -199,22 +200,20 @@ __global__ void __launch_bounds__(kThreads) smooth_bwd_dd_kernel(const BwdParams
       const int qrow = q0 + nb * 8 + 2 * t;  // and qrow + 1: same query (nq_pad is even)
       const bool okq0 = qrow < p.q_rows && (qrow % p.nq_pad) < p.nq_real;
       const bool okq1 = qrow + 1 < p.q_rows && ((qrow + 1) % p.nq_pad) < p.nq_real;
-      const int b = qrow / p.nq_pad;
-      float pv[4] = {0.f, 0.f, 0.f, 0.f};
-      if (c_lo >= 0 && okq0) {
-        const float w = __ldg(p.g + static_cast<int64_t>(b) * p.C + c_lo) * scale;
-        const float2 l = __ldg(reinterpret_cast<const float2*>(p.lse + static_cast<int64_t>(c_lo) * p.q_rows + qrow));
-        pv[0] = w * ex2((s[nb][0] - l.x) * p.smooth_c);
-        if (okq1) pv[1] = w * ex2((s[nb][1] - l.y) * p.smooth_c);
-      }
-      if (c_hi >= 0 && okq0) {
-        const float w = __ldg(p.g + static_cast<int64_t>(b) * p.C + c_hi) * scale;
-        const float2 l = __ldg(reinterpret_cast<const float2*>(p.lse + static_cast<int64_t>(c_hi) * p.q_rows + qrow));
-        pv[2] = w * ex2((s[nb][2] - l.x) * p.smooth_c);
-        if (okq1) pv[3] = w * ex2((s[nb][3] - l.y) * p.smooth_c);
-      }
-      pa[nb >> 1][(nb & 1) * 2 + 0] = pack_bf16(pv[0], pv[1]);
-      pa[nb >> 1][(nb & 1) * 2 + 1] = pack_bf16(pv[2], pv[3]);
+      const int b = min(qrow, p.q_rows - 1) / p.nq_pad;
+      const int qr = min(qrow, p.q_rows - 2);  // clamped address of the (even-aligned) lse pair
+      // select the operands, then compute unconditionally: invalid (row, column) pairs get weight 0 and exponent -inf
+      const int cl = max(c_lo, 0), ch = max(c_hi, 0);
+      const float w_l = (c_lo >= 0) ? __ldg(p.g + static_cast<int64_t>(b) * p.C + cl) * scale : 0.f;
+      const float w_h = (c_hi >= 0) ? __ldg(p.g + static_cast<int64_t>(b) * p.C + ch) * scale : 0.f;
+      const float2 ll = __ldg(reinterpret_cast<const float2*>(p.lse + static_cast<int64_t>(cl) * p.q_rows + qr));
+      const float2 lh = __ldg(reinterpret_cast<const float2*>(p.lse + static_cast<int64_t>(ch) * p.q_rows + qr));
+      const float e0 = (c_lo >= 0 && okq0) ? (s[nb][0] - ll.x) * p.smooth_c : -INFINITY;
+      const float e1 = (c_lo >= 0 && okq1) ? (s[nb][1] - ll.y) * p.smooth_c : -INFINITY;
+      const float e2 = (c_hi >= 0 && okq0) ? (s[nb][2] - lh.x) * p.smooth_c : -INFINITY;
+      const float e3 = (c_hi >= 0 && okq1) ? (s[nb][3] - lh.y) * p.smooth_c : -INFINITY;
+      pa[nb >> 1][(nb & 1) * 2 + 0] = pack_bf16(w_l * ex2(e0), w_l * ex2(e1));
+      pa[nb >> 1][(nb & 1) * 2 + 1] = pack_bf16(w_h * ex2(e2), w_h * ex2(e3));
     }
     gemm_pv(acc, pa, tile, lane);  // rows of the tile past q_rows are zero
   }

@@ -36,3 +36,22 @@ for n_d, docs in ((1030, d), (1024, d[:, :1024].contiguous())):
             "hold_boundary_per_job": float((c[:, 5] / c[:, 6].clamp_min(1)).mean()), "boundary_jobs_share": float((c[:, 6] / jobs).mean()),
         }), flush=True)
 _lib.set_option("boundary_mode", 1)
+
+# ---- the training forward (argmax mode, generic epilogue walk) at cfg3: 64 queries x 64 left-padded documents --------
+q3, d3, _ = O.cfg3_inputs()
+qb3, bank3 = cb.QueryBlock(q3.to(dev), dev), cb.DocBank.from_passages(d3.to(dev), dev)
+_lib.set_option("debug_flags", 0x40000)
+try:
+    raw, _am = cb.maxsim(qb3, bank3, want_argmax=True)
+    torch.cuda.synchronize()
+finally:
+    _lib.set_option("debug_flags", 0)
+raw = raw.flatten().cpu()
+n_cta = 144
+cyc = raw[0:2 * n_cta:2]
+c = raw[512:512 + 8 * n_cta].view(n_cta, 8)
+jobs = c[:, 7].clamp_min(1)
+print(json.dumps({"mode": "argmax, cfg3", "ctas": int((c[:, 7] > 0).sum()), "jobs_per_cta": float(jobs.mean()),
+                  "cycles_per_job_mean": float((cyc / jobs).mean()), "hold_per_job": float((c[:, 3] / jobs).mean()),
+                  "blocked_in_wait_ld_per_job": float((c[:, 5] / jobs).mean()), "epilogue_wait_for_mma_per_job": float((c[:, 2] / jobs).mean()),
+                  "post_release_per_job": float((c[:, 4] / jobs).mean())}), flush=True)

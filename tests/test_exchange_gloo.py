@@ -42,6 +42,9 @@ def _worker(rank, world, port, pad_first, out_dir):
     out.update(loss2=loss2.detach().numpy(), dq2=q.grad.numpy().copy(), dd2=d.grad.numpy().copy(), dn2=neg.grad.numpy().copy())
     docs, offset = X.gather_documents(d.detach(), pad_first=pad_first)
     out.update(shape=np.array(docs.shape), offset=np.array(offset))
+    # gradient-accumulation micro-step (the reference gathers only when accelerator.sync_gradients, :143): local loss
+    local = X.compute_loss_from_outputs(O.colbert_loss_port, q.detach(), d.detach(), pad_first=pad_first, gather=False)
+    out.update(local=local.numpy(), local_ref=O.colbert_loss_port(q.detach(), d.detach(), offset=0).numpy())
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), **out)
     dist.barrier()
     dist.destroy_process_group()
@@ -66,6 +69,7 @@ def test_exchange_equals_single_process(tmp_path, world, pad_first):
     got = [np.load(os.path.join(str(tmp_path), f"r{r}.npz")) for r in range(world)]
     for r in range(world):
         assert tuple(got[r]["shape"]) == (world * B, l_max, DIM) and int(got[r]["offset"]) == r * B
+        assert float(got[r]["local"]) == float(got[r]["local_ref"])  # gather=False: no exchange, offset 0
         assert abs(float(got[r]["loss"]) - float(losses[r].detach())) < 1e-6
         assert np.allclose(got[r]["dq"], qs[r].grad.numpy(), rtol=1e-5, atol=1e-7)
         assert np.allclose(got[r]["dd"], ds[r].grad.numpy(), rtol=1e-5, atol=1e-7)
