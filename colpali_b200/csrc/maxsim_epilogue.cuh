@@ -93,35 +93,43 @@ __device__ __forceinline__ float max32_range(const uint32_t (&v)[32], float m, i
   return max32(x, m);
 }
 
-// (value, first index) of the maximum of a chunk folded into the running pair; strict '>' keeps the earliest maximum,
-// which is what torch.max(dim) returns on ties.  The chunk maximum comes from the FMNMX3 tree; only if it beats some
-// lane's running maximum is the position of its first occurrence looked up (compare + select per column, then a min
-// tree) -- everything data-parallel instead of a 32-deep chain of dependent compare / select pairs.
-__device__ __forceinline__ void argmax32_core(const uint32_t (&x)[32], float& m, int& idx, int idx0) {
-  const float t = tree32(x);
-  const bool take = t > m;
-  if (__any_sync(0xffffffffu, take)) {
-    int c[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) c[i] = (__uint_as_float(x[i]) == t) ? i : 64;
-#pragma unroll
-    for (int w = 16; w > 0; w >>= 1) {
-#pragma unroll
-      for (int i = 0; i < w; ++i) c[i] = min(c[i], c[i + w]);
-    }
-    m = take ? t : m;
-    idx = take ? (idx0 + c[0]) : idx;
-  }
-}
-// the same over columns lo <= i < hi; idx0 = document-relative index of column 0 of the chunk
-__device__ __forceinline__ void argmax32_range(const uint32_t (&v)[32], float& m, int& idx, int idx0, int lo, int hi) {
+// Argmax (training forward).  Looking up WHERE a chunk's maximum sits costs ~95 instructions (compare + select per
+// column, min tree) against 16 for the maximum itself, and one warp per scheduler issues them at 0.3-0.5 IPC.  So the
+// position is resolved lazily: per lane the epilogue keeps the running maximum, the 32 values of the chunk it came from
+// (`bc`, one predicated move per column when a chunk takes over) and that chunk's first document-relative index
+// (`bidx0`); the first-occurrence lookup runs ONCE PER DOCUMENT in argmax_resolve.  Strict '>' between chunks and the
+// first equal column inside the chunk give the earliest maximum, which is what torch.max(dim) returns on ties.
+__device__ __forceinline__ void argmax_fold(const uint32_t (&v)[32], float& m, int& bidx0, uint32_t (&bc)[32], int idx0,
+                                            int lo, int hi) {
   if (lo == 0 && hi == 32) {
-    argmax32_core(v, m, idx, idx0);
+    const float t = tree32(v);
+    const bool take = t > m;
+    m = take ? t : m;
+    bidx0 = take ? idx0 : bidx0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) bc[i] = take ? v[i] : bc[i];
   } else {
     uint32_t x[32];
     mask32(v, x, lo, hi);
-    argmax32_core(x, m, idx, idx0);
+    const float t = tree32(x);
+    const bool take = t > m;
+    m = take ? t : m;
+    bidx0 = take ? idx0 : bidx0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) bc[i] = take ? x[i] : bc[i];
   }
+}
+// document-relative index of the first maximal token, -1 if no token beat the initial value (the floor won)
+__device__ __forceinline__ int argmax_resolve(const uint32_t (&bc)[32], float m, int bidx0) {
+  int c[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) c[i] = (__uint_as_float(bc[i]) == m) ? i : 64;
+#pragma unroll
+  for (int w = 16; w > 0; w >>= 1) {
+#pragma unroll
+    for (int i = 0; i < w; ++i) c[i] = min(c[i], c[i + w]);
+  }
+  return (bidx0 < 0) ? -1 : bidx0 + c[0];
 }
 
 __device__ __forceinline__ float round_bf16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
@@ -258,8 +266,11 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
     return (!kSmooth && p.doc_floor != nullptr) ? __ldg(p.doc_floor + doc) : -INFINITY;
   };
 
+  static_assert(R == 1 || kMode != kModeArgmax, "the argmax mode keeps one best-chunk cache: one query tile per CTA");
   float m[R], ls[R];
   int am[R];
+  uint32_t bc[32];  // argmax mode: the chunk the running maximum came from, and its first document-relative index
+  int bidx0 = -1;
   uint32_t job = 0;
   const bool dbg = (p.flags & CPB_DBG_CLOCKS) != 0;
   long long e_wait = 0, e_hold = 0, e_post = 0, e_hold2 = 0, e_genwait = 0;
@@ -343,6 +354,7 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
         am[r] = -1;
         ls[r] = 0.f;
       }
+      bidx0 = -1;
     }
     for (int row = run.row0; row < run.row1; row += kTileN) {
       const int n_valid = min(kTileN, run.row1 - row);
@@ -371,6 +383,7 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
 
           // the current document is complete: emit it and step to the next one of the run
           auto finish_doc = [&]() {
+            if constexpr (kArgmax) ai = argmax_resolve(bc, mm, bidx0);
             if (head_frag && doc == first_doc) publish(r, mm, ai); else finalize(doc, r, mm, ai, ll);
             ++doc;
             if (doc >= run.e) {
@@ -381,6 +394,7 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
             doc_end = doc_row0 + doc_nlen;
             mm = doc_ninit;
             ai = -1;
+            bidx0 = -1;
             ll = 0.f;
             doc_nlen = (doc + 1 < run.e) ? __ldg(p.doc_len + doc + 1) : 0;
             doc_ninit = (doc + 1 < run.e) ? doc_init(doc + 1) : -INFINITY;
@@ -558,19 +572,8 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
             mm = mb;
             while (doc_end <= tile_end) finish_doc();
           } else {
-            // generic walk, software-pipelined: chunk c + 1 is in flight (into `w`) while chunk c folds (from `v`); one
-            // copy of the fold code, 32 register moves per chunk
-            uint32_t v[32], w[32];
-            tmem_ld_x32(taddr, w);
-#pragma unroll 1
-            for (int cb = 0; cb < n_valid; cb += 32) {
-              const long long tw = dbg ? clock64() : 0;
-              tmem_ld_wait();
-              if (dbg) e_genwait += clock64() - tw;
-              reg_fence32(w);
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = w[i];
-              if (cb + 32 < n_valid) tmem_ld_x32(taddr + cb + 32, w);
+            // generic walk, software-pipelined over two register buffers: chunk c + 1 is in flight while chunk c folds
+            auto fold_chunk = [&](const uint32_t (&v)[32], int cb) {
               const int abs0 = row + cb;
               const int abs1 = min(abs0 + 32, tile_end);
               int pos = abs0;
@@ -581,7 +584,7 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
                     if (pos == abs0 && seg_end == abs0 + 32) lse32_full(v, mm, ll, p.smooth_c);
                     else lse32_range(v, mm, ll, p.smooth_c, pos - abs0, seg_end - abs0);
                   } else if constexpr (kArgmax) {
-                    argmax32_range(v, mm, ai, abs0 - doc_row0, pos - abs0, seg_end - abs0);
+                    argmax_fold(v, mm, bidx0, bc, abs0 - doc_row0, pos - abs0, seg_end - abs0);
                   } else {
                     mm = max32_range(v, mm, pos - abs0, seg_end - abs0);
                   }
@@ -589,6 +592,24 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
                 pos = seg_end;
                 if (doc_end > abs1) break;  // the current document continues past this chunk
                 finish_doc();
+              }
+            };
+            uint32_t va[32], vb[32];
+            tmem_ld_x32(taddr, va);
+#pragma unroll 1
+            for (int cb = 0; cb < n_valid; cb += 64) {
+              const long long tw = dbg ? clock64() : 0;
+              tmem_ld_wait();
+              if (dbg) e_genwait += clock64() - tw;
+              reg_fence32(va);
+              const bool has_b = cb + 32 < n_valid;
+              if (has_b) tmem_ld_x32(taddr + cb + 32, vb);
+              fold_chunk(va, cb);
+              if (has_b) {
+                tmem_ld_wait();
+                reg_fence32(vb);
+                if (cb + 64 < n_valid) tmem_ld_x32(taddr + cb + 64, va);
+                fold_chunk(vb, cb + 32);
               }
             }
             release_acc();
@@ -627,6 +648,7 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
       for (int r = 0; r < r_cnt; ++r) {
         float mm = (r == 0) ? m[0] : m[R - 1];
         int ai = (r == 0) ? am[0] : am[R - 1];
+        if constexpr (kArgmax) ai = argmax_resolve(bc, mm, bidx0);
         if (head_frag && cur == first_doc) {
           // (a document longer than a whole partition is excluded by the host: it would need a chain)
           __trap();

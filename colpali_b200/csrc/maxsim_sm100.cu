@@ -419,12 +419,14 @@ static cudaError_t launch_variant(const CUtensorMap& tq, const CUtensorMap& td, 
 // mode: kModeMax / kModeArgmax / kModeSmooth (maxsim_epilogue.cuh)
 cudaError_t maxsim_launch(const CUtensorMap& tq, const CUtensorMap& td, const CUtensorMap& tt, const MaxSimParams& p,
                           const LossParams& lp, int r, int mode, int grid, cudaStream_t stream) {
+  if (mode == kModeArgmax) {  // one resident query tile per CTA (the host sizes the grid accordingly)
+    if (r != 1) return cudaErrorInvalidValue;
+    return launch_variant<1, kModeArgmax>(tq, td, tt, p, lp, grid, stream);
+  }
   if (r == 1) {
-    if (mode == kModeArgmax) return launch_variant<1, kModeArgmax>(tq, td, tt, p, lp, grid, stream);
     if (mode == kModeSmooth) return launch_variant<1, kModeSmooth>(tq, td, tt, p, lp, grid, stream);
     return launch_variant<1, kModeMax>(tq, td, tt, p, lp, grid, stream);
   }
-  if (mode == kModeArgmax) return launch_variant<2, kModeArgmax>(tq, td, tt, p, lp, grid, stream);
   if (mode == kModeSmooth) return launch_variant<2, kModeSmooth>(tq, td, tt, p, lp, grid, stream);
   return launch_variant<2, kModeMax>(tq, td, tt, p, lp, grid, stream);
 }
