@@ -119,6 +119,9 @@ __device__ __forceinline__ void argmax_fold(const uint32_t (&v)[32], float& m, i
     for (int i = 0; i < 32; ++i) bc[i] = take ? x[i] : bc[i];
   }
 }
+// `bidx0` of a lane whose running maximum is still the initial value.  (Not -1: the first chunk of a document that starts
+// in the middle of a 32-column chunk has a NEGATIVE first index, down to -31.)
+constexpr int kNoChunk = -0x40000000;
 // document-relative index of the first maximal token, -1 if no token beat the initial value (the floor won)
 __device__ __forceinline__ int argmax_resolve(const uint32_t (&bc)[32], float m, int bidx0) {
   int c[32];
@@ -129,7 +132,7 @@ __device__ __forceinline__ int argmax_resolve(const uint32_t (&bc)[32], float m,
 #pragma unroll
     for (int i = 0; i < w; ++i) c[i] = min(c[i], c[i + w]);
   }
-  return (bidx0 < 0) ? -1 : bidx0 + c[0];
+  return (bidx0 == kNoChunk) ? -1 : bidx0 + c[0];
 }
 
 __device__ __forceinline__ float round_bf16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
@@ -270,7 +273,7 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
   float m[R], ls[R];
   int am[R];
   uint32_t bc[32];  // argmax mode: the chunk the running maximum came from, and its first document-relative index
-  int bidx0 = -1;
+  int bidx0 = kNoChunk;
   uint32_t job = 0;
   const bool dbg = (p.flags & CPB_DBG_CLOCKS) != 0;
   long long e_wait = 0, e_hold = 0, e_post = 0, e_hold2 = 0, e_genwait = 0;
@@ -354,7 +357,7 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
         am[r] = -1;
         ls[r] = 0.f;
       }
-      bidx0 = -1;
+      bidx0 = kNoChunk;
     }
     for (int row = run.row0; row < run.row1; row += kTileN) {
       const int n_valid = min(kTileN, run.row1 - row);
@@ -394,7 +397,7 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
             doc_end = doc_row0 + doc_nlen;
             mm = doc_ninit;
             ai = -1;
-            bidx0 = -1;
+            bidx0 = kNoChunk;
             ll = 0.f;
             doc_nlen = (doc + 1 < run.e) ? __ldg(p.doc_len + doc + 1) : 0;
             doc_ninit = (doc + 1 < run.e) ? doc_init(doc + 1) : -INFINITY;
