@@ -347,7 +347,6 @@ int cpb_maxsim_launch(cpb_maxsim_args* a) {
     // Two resident query tiles per CTA halve the L2->SMEM traffic per flop; a single tile only when there is just one.
     int R = (p.num_qtiles >= 2) ? 2 : 1;
     if (opt_r == 1 || opt_r == 2) R = opt_r;
-    if (mode == 1) R = 1;  // argmax: the epilogue keeps one best-chunk cache per lane (maxsim_epilogue.cuh)
     p.q_groups = (p.num_qtiles + R - 1) / R;
     // CTAs of a cluster hold different query-tile groups and share every document tile through TMA multicast.  Pairs
     // tile the 148 SMs exactly; clusters of 4 strand SMs in GPCs whose SM count is not a multiple of 4 (opt-in).

@@ -95,35 +95,72 @@ __device__ __forceinline__ float max32_range(const uint32_t (&v)[32], float m, i
 
 // Argmax (training forward).  Looking up WHERE a chunk's maximum sits costs ~95 instructions (compare + select per
 // column, min tree) against 16 for the maximum itself, and one warp per scheduler issues them at 0.3-0.5 IPC.  So the
-// position is resolved lazily: per lane the epilogue keeps the running maximum, the 32 values of the chunk it came from
-// (`bc`, one predicated move per column when a chunk takes over) and that chunk's first document-relative index
-// (`bidx0`); the first-occurrence lookup runs ONCE PER DOCUMENT in argmax_resolve.  Strict '>' between chunks and the
+// position is resolved lazily: per lane the epilogue keeps the running maximum, the first document-relative index of the
+// chunk it came from (`bidx0`) and that chunk's 32 values in a 128-byte slot of shared memory -- eight predicated
+// 16-byte stores when a chunk takes over (keeping them in registers cost 32 selects per chunk, twice the maximum
+// itself).  The first-occurrence lookup runs ONCE PER DOCUMENT in argmax_resolve.  Strict '>' between chunks and the
 // first equal column inside the chunk give the earliest maximum, which is what torch.max(dim) returns on ties.
-__device__ __forceinline__ void argmax_fold(const uint32_t (&v)[32], float& m, int& bidx0, uint32_t (&bc)[32], int idx0,
-                                            int lo, int hi) {
-  if (lo == 0 && hi == 32) {
-    const float t = tree32(v);
-    const bool take = t > m;
-    m = take ? t : m;
-    bidx0 = take ? idx0 : bidx0;
+//
+// Slot layout: lane l of epilogue warp w owns bytes [(32 w + l) * 128, +128) of the query tile's 16 KiB area; its k-th
+// 16-byte piece sits at ((k ^ (l & 7)) << 4), so the eight lanes of a quarter-warp cover all 32 banks.
+constexpr int kBcBytesPerTile = 4 * 32 * 128;  // per resident query tile
+
+// the four stores of one half chunk, all under one predicate (a C++ `if` would become a BSSY / BRA / BSYNC diamond)
+__device__ __forceinline__ void bc_store_half(uint32_t slot, uint32_t sw, int half, bool take, const uint32_t* v) {
+  const uint32_t a0 = slot + (((4 * half + 0) << 4) ^ sw), a1 = slot + (((4 * half + 1) << 4) ^ sw);
+  const uint32_t a2 = slot + (((4 * half + 2) << 4) ^ sw), a3 = slot + (((4 * half + 3) << 4) ^ sw);
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %20, 0;\n\t"
+      "@p st.shared.v4.b32 [%0], {%4, %5, %6, %7};\n\t"
+      "@p st.shared.v4.b32 [%1], {%8, %9, %10, %11};\n\t"
+      "@p st.shared.v4.b32 [%2], {%12, %13, %14, %15};\n\t"
+      "@p st.shared.v4.b32 [%3], {%16, %17, %18, %19};\n\t}"
+      ::"r"(a0), "r"(a1), "r"(a2), "r"(a3),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+        "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+        "r"(static_cast<uint32_t>(take))
+      : "memory");
+}
+__device__ __forceinline__ void bc_store(uint32_t slot, uint32_t sw, bool take, const uint32_t (&v)[32]) {
+  bc_store_half(slot, sw, 0, take, &v[0]);
+  bc_store_half(slot, sw, 1, take, &v[16]);
+}
+__device__ __forceinline__ void bc_load(uint32_t slot, uint32_t sw, uint32_t (&v)[32]) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) bc[i] = take ? v[i] : bc[i];
+  for (int k = 0; k < 8; ++k)
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v[4 * k]), "=r"(v[4 * k + 1]), "=r"(v[4 * k + 2]), "=r"(v[4 * k + 3])
+                 : "r"(slot + ((k << 4) ^ sw))
+                 : "memory");
+}
+
+// a whole 32-column chunk
+__device__ __forceinline__ void argmax_fold_full(const uint32_t (&v)[32], float& m, int& bidx0, uint32_t slot, uint32_t sw,
+                                                 int idx0) {
+  const float t = tree32(v);
+  const bool take = t > m;
+  m = take ? t : m;
+  bidx0 = take ? idx0 : bidx0;
+  bc_store(slot, sw, take, v);
+}
+// columns lo <= i < hi of a chunk
+__device__ __forceinline__ void argmax_fold(const uint32_t (&v)[32], float& m, int& bidx0, uint32_t slot, uint32_t sw,
+                                            int idx0, int lo, int hi) {
+  if (lo == 0 && hi == 32) {
+    argmax_fold_full(v, m, bidx0, slot, sw, idx0);
   } else {
     uint32_t x[32];
     mask32(v, x, lo, hi);
-    const float t = tree32(x);
-    const bool take = t > m;
-    m = take ? t : m;
-    bidx0 = take ? idx0 : bidx0;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) bc[i] = take ? x[i] : bc[i];
+    argmax_fold_full(x, m, bidx0, slot, sw, idx0);
   }
 }
 // `bidx0` of a lane whose running maximum is still the initial value.  (Not -1: the first chunk of a document that starts
 // in the middle of a 32-column chunk has a NEGATIVE first index, down to -31.)
 constexpr int kNoChunk = -0x40000000;
 // document-relative index of the first maximal token, -1 if no token beat the initial value (the floor won)
-__device__ __forceinline__ int argmax_resolve(const uint32_t (&bc)[32], float m, int bidx0) {
+__device__ __forceinline__ int argmax_resolve(uint32_t slot, uint32_t sw, float m, int bidx0) {
+  uint32_t bc[32];
+  bc_load(slot, sw, bc);
   int c[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) c[i] = (__uint_as_float(bc[i]) == m) ? i : 64;
@@ -216,7 +253,8 @@ __device__ __forceinline__ void multimem_st_f32(uint64_t mc_addr, float x) {
 // Runs on warps 2..5 (one TMEM lane quadrant each).  R = resident query tiles per CTA.
 template <int R, int kMode>
 __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const CtaSlice& sl, uint32_t tmem_base,
-                                                uint64_t* tmem_full, uint64_t* tmem_empty, int warp, int lane) {
+                                                uint64_t* tmem_full, uint64_t* tmem_empty, int warp, int lane,
+                                                uint8_t* bc_smem = nullptr) {
   constexpr int kTileM = kEpiTileM;
   constexpr int kTileN = kEpiTileN;
   constexpr bool kArgmax = (kMode == kModeArgmax);
@@ -269,11 +307,12 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
     return (!kSmooth && p.doc_floor != nullptr) ? __ldg(p.doc_floor + doc) : -INFINITY;
   };
 
-  static_assert(R == 1 || kMode != kModeArgmax, "the argmax mode keeps one best-chunk cache: one query tile per CTA");
   float m[R], ls[R];
-  int am[R];
-  uint32_t bc[32];  // argmax mode: the chunk the running maximum came from, and its first document-relative index
-  int bidx0 = kNoChunk;
+  int am[R];  // argmax mode: first document-relative index of the chunk the running maximum came from (`bidx0`)
+  constexpr int kNoIdx = kArgmax ? kNoChunk : -1;
+  // argmax mode: this lane's best-chunk slot of resident query tile 0 (tile r: + r * kBcBytesPerTile) and its swizzle
+  const uint32_t bc_slot0 = kArgmax ? smem_u32(bc_smem) + static_cast<uint32_t>((quad * 32 + lane) * 128) : 0u;
+  const uint32_t bc_sw = static_cast<uint32_t>(lane & 7) << 4;
   uint32_t job = 0;
   const bool dbg = (p.flags & CPB_DBG_CLOCKS) != 0;
   long long e_wait = 0, e_hold = 0, e_post = 0, e_hold2 = 0, e_genwait = 0;
@@ -354,10 +393,9 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         m[r] = init;
-        am[r] = -1;
+        am[r] = kNoIdx;
         ls[r] = 0.f;
       }
-      bidx0 = kNoChunk;
     }
     for (int row = run.row0; row < run.row1; row += kTileN) {
       const int n_valid = min(kTileN, run.row1 - row);
@@ -381,12 +419,13 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
           // per-tile state by select, not by index: r is a run-time value when the loop is not unrolled
           float mm = (r == 0) ? m[0] : m[R - 1], ll = (r == 0) ? ls[0] : ls[R - 1];
           int ai = (r == 0) ? am[0] : am[R - 1];
+          const uint32_t bc_slot = bc_slot0 + static_cast<uint32_t>(r * kBcBytesPerTile);
           int doc = cur, doc_row0 = cur_row0, doc_end = cur_end, doc_nlen = cur_nlen;
           float doc_ninit = cur_ninit;
 
           // the current document is complete: emit it and step to the next one of the run
           auto finish_doc = [&]() {
-            if constexpr (kArgmax) ai = argmax_resolve(bc, mm, bidx0);
+            if constexpr (kArgmax) ai = argmax_resolve(bc_slot, bc_sw, mm, ai);
             if (head_frag && doc == first_doc) publish(r, mm, ai); else finalize(doc, r, mm, ai, ll);
             ++doc;
             if (doc >= run.e) {
@@ -396,8 +435,7 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
             doc_row0 = doc_end;
             doc_end = doc_row0 + doc_nlen;
             mm = doc_ninit;
-            ai = -1;
-            bidx0 = kNoChunk;
+            ai = kNoIdx;
             ll = 0.f;
             doc_nlen = (doc + 1 < run.e) ? __ldg(p.doc_len + doc + 1) : 0;
             doc_ninit = (doc + 1 < run.e) ? doc_init(doc + 1) : -INFINITY;
@@ -414,10 +452,10 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
           // new document per 32-column chunk, plus one masked pass over the chunk that holds the boundary.
           // (3) anything else (short documents, last tile of a run, argmax): generic masked walk.
           int path = 3;
-          if (!kArgmax && !kSmooth && n_valid == kTileN) {
+          if (!kSmooth && n_valid == kTileN) {
             if (doc_end >= tile_end) {
               path = 1;
-            } else if (doc_end > row && doc + 1 < run.e) {
+            } else if (!kArgmax && doc_end > row && doc + 1 < run.e) {
               if (doc_end + doc_nlen >= tile_end) path = 2;
             }
           }
@@ -438,6 +476,11 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
           } else if (path == 1) {
             // software pipeline: the loads of columns [64k+64, 64k+128) are in flight while [64k, 64k+64) fold
             // (TMEM reads are ~64 B/clk per lane quadrant: ~490 cycles for 128 x 256 fp32 whatever the warp count)
+            const int idx_t = row - doc_row0;  // document-relative index of the tile's first column (argmax)
+            auto fold = [&](const uint32_t (&v)[32], int k) {
+              if constexpr (kArgmax) argmax_fold_full(v, mm, ai, bc_slot, bc_sw, idx_t + 32 * k);
+              else mm = max32(v, mm);
+            };
             uint32_t va[32], vb[32], vc[32], vd[32];
             tmem_ld_x32(taddr, va);
             tmem_ld_x32(taddr + 32, vb);
@@ -446,28 +489,28 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
             reg_fence32(vb);
             tmem_ld_x32(taddr + 64, vc);
             tmem_ld_x32(taddr + 96, vd);
-            mm = max32(va, mm);
-            mm = max32(vb, mm);
+            fold(va, 0);
+            fold(vb, 1);
             tmem_ld_wait();
             reg_fence32(vc);
             reg_fence32(vd);
             tmem_ld_x32(taddr + 128, va);
             tmem_ld_x32(taddr + 160, vb);
-            mm = max32(vc, mm);
-            mm = max32(vd, mm);
+            fold(vc, 2);
+            fold(vd, 3);
             tmem_ld_wait();
             reg_fence32(va);
             reg_fence32(vb);
             tmem_ld_x32(taddr + 192, vc);
             tmem_ld_x32(taddr + 224, vd);
-            mm = max32(va, mm);
-            mm = max32(vb, mm);
+            fold(va, 4);
+            fold(vb, 5);
             tmem_ld_wait();
             reg_fence32(vc);
             reg_fence32(vd);
             release_acc();  // every accumulator read has landed in registers
-            mm = max32(vc, mm);
-            mm = max32(vd, mm);
+            fold(vc, 6);
+            fold(vd, 7);
             while (doc_end <= tile_end) finish_doc();  // document (and empty followers) ending at the tile end
           } else if (path == 2 && shifted_boundary && doc_end - row >= 32 && doc_end - row <= kTileN - 32) {
             // one boundary at column b, at least 32 columns from either edge: read the tile as 32-column chunks
@@ -587,7 +630,7 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
                     if (pos == abs0 && seg_end == abs0 + 32) lse32_full(v, mm, ll, p.smooth_c);
                     else lse32_range(v, mm, ll, p.smooth_c, pos - abs0, seg_end - abs0);
                   } else if constexpr (kArgmax) {
-                    argmax_fold(v, mm, bidx0, bc, abs0 - doc_row0, pos - abs0, seg_end - abs0);
+                    argmax_fold(v, mm, ai, bc_slot, bc_sw, abs0 - doc_row0, pos - abs0, seg_end - abs0);
                   } else {
                     mm = max32_range(v, mm, pos - abs0, seg_end - abs0);
                   }
@@ -651,7 +694,8 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
       for (int r = 0; r < r_cnt; ++r) {
         float mm = (r == 0) ? m[0] : m[R - 1];
         int ai = (r == 0) ? am[0] : am[R - 1];
-        if constexpr (kArgmax) ai = argmax_resolve(bc, mm, bidx0);
+        if constexpr (kArgmax)
+          ai = argmax_resolve(bc_slot0 + static_cast<uint32_t>(r * kBcBytesPerTile), bc_sw, mm, ai);
         if (head_frag && cur == first_doc) {
           // (a document longer than a whole partition is excluded by the host: it would need a chain)
           __trap();

@@ -35,11 +35,13 @@ template <int KP>
 struct SmemLayout {
   static constexpr int kQOff = 0;
   static constexpr int kDOff = KP * kQPanelBytes;
-  static constexpr int kBarOff = kDOff + kStages * kDPanelBytes;
+  static constexpr int kBcOff = kDOff + kStages * kDPanelBytes;  // argmax mode: per-lane best-chunk cache (one query tile)
+  static constexpr int kBarOff = kBcOff + kBcBytesPerTile;
   static constexpr int kNumBars = 1 + 2 * kStages + 4;  // q_full, full[S], empty[S], tmem_full[2], tmem_empty[2]
   static constexpr int kTmemPtrOff = kBarOff + kNumBars * 8;
   static constexpr int kBytes = kTmemPtrOff + 16;
   static constexpr int kAlloc = kBytes + 1024;
+  static_assert(kAlloc <= 227 * 1024, "shared memory budget of one CTA");
 };
 
 template <int KP, int kMode>
@@ -242,7 +244,7 @@ maxsim_kpipe_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   } else {
     // ================================ epilogue (maxsim_epilogue.cuh) ==========================
     const CtaSlice sl{g, part, r_cnt, d0, d1, bal_r0, bal_r1};
-    maxsim_epilogue<R, kMode>(p, sl, tmem_base, tmem_full, tmem_empty, warp, lane);
+    maxsim_epilogue<R, kMode>(p, sl, tmem_base, tmem_full, tmem_empty, warp, lane, smem + L::kBcOff);
   }
 
   // ---- teardown ---------------------------------------------------------------------------

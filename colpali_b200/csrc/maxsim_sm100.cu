@@ -53,24 +53,28 @@ constexpr int kThreads = 192;
 #endif
 constexpr uint32_t kTmemCols = 512;
 
-template <int R>
+template <int R, int kMode>
 struct SmemLayout {
-  static constexpr int kStages = (R == 1) ? 3 : 2;
+  // argmax mode: 16 KiB per resident query tile for the per-lane best-chunk cache (maxsim_epilogue.cuh)
+  static constexpr int kBcBytes = (kMode == kModeArgmax) ? R * kBcBytesPerTile : 0;
+  static constexpr int kStages = (R == 1 && kMode != kModeArgmax) ? 3 : 2;
   static constexpr int kQOff = 0;
   static constexpr int kDOff = R * kQTileBytes;
-  static constexpr int kBarOff = kDOff + kStages * kDTileBytes;
+  static constexpr int kBcOff = kDOff + kStages * kDTileBytes;
+  static constexpr int kBarOff = kBcOff + kBcBytes;
   // barriers: q_full, full[S], empty[S], tmem_full[2], tmem_empty[2]
   static constexpr int kNumBars = 1 + 2 * kStages + 4;
   static constexpr int kTmemPtrOff = kBarOff + kNumBars * 8;
   static constexpr int kBytes = kTmemPtrOff + 16;
   static constexpr int kAlloc = kBytes + 1024;  // slack for manual 1024-B alignment
+  static_assert(kAlloc <= 227 * 1024, "shared memory budget of one CTA");
 };
 
 template <int R, int kMode>
 __global__ void __launch_bounds__(kThreads, 1)
 maxsim_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_d,
                   const __grid_constant__ CUtensorMap tmap_tail, const MaxSimParams p, const LossParams lp) {
-  using L = SmemLayout<R>;
+  using L = SmemLayout<R, kMode>;
   constexpr int S = L::kStages;
 
   extern __shared__ uint8_t smem_raw[];
@@ -323,7 +327,7 @@ maxsim_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   } else {
     // ================================ epilogue (maxsim_epilogue.cuh) ==========================
     const CtaSlice sl{g, part, r_cnt, d0, d1, bal_r0, bal_r1};
-    maxsim_epilogue<R, kMode>(p, sl, tmem_base, tmem_full, tmem_empty, warp, lane);
+    maxsim_epilogue<R, kMode>(p, sl, tmem_base, tmem_full, tmem_empty, warp, lane, smem + L::kBcOff);
   }
 
   // ---- teardown ---------------------------------------------------------------------------
@@ -376,12 +380,11 @@ __global__ void maxsim_reduce_segments_kernel(const float* __restrict__ partial,
   out[i] = round_ref ? round_bf16(s) : s;
 }
 
-template <int R>
-static void fill_cluster_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int grid, int cluster,
+static void fill_cluster_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int grid, int cluster, int smem_bytes,
                              cudaStream_t stream, int pdl = 0) {
   cfg.gridDim = dim3(static_cast<unsigned>(grid));
   cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = SmemLayout<R>::kAlloc;
+  cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = static_cast<unsigned>(cluster);
@@ -406,27 +409,25 @@ static cudaError_t launch_variant(const CUtensorMap& tq, const CUtensorMap& td, 
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   if (dev < 0 || dev >= 64 || !attr_set[dev].load(std::memory_order_acquire)) {
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<R>::kAlloc);
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<R, kMode>::kAlloc);
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) attr_set[dev].store(true, std::memory_order_release);
   }
   cudaLaunchConfig_t cfg{};
   cudaLaunchAttribute attr[2];
-  fill_cluster_cfg<R>(cfg, attr, grid, p.cluster, stream, p.pdl);
+  fill_cluster_cfg(cfg, attr, grid, p.cluster, SmemLayout<R, kMode>::kAlloc, stream, p.pdl);
   return cudaLaunchKernelEx(&cfg, kern, tq, td, tt, p, lp);
 }
 
 // mode: kModeMax / kModeArgmax / kModeSmooth (maxsim_epilogue.cuh)
 cudaError_t maxsim_launch(const CUtensorMap& tq, const CUtensorMap& td, const CUtensorMap& tt, const MaxSimParams& p,
                           const LossParams& lp, int r, int mode, int grid, cudaStream_t stream) {
-  if (mode == kModeArgmax) {  // one resident query tile per CTA (the host sizes the grid accordingly)
-    if (r != 1) return cudaErrorInvalidValue;
-    return launch_variant<1, kModeArgmax>(tq, td, tt, p, lp, grid, stream);
-  }
   if (r == 1) {
+    if (mode == kModeArgmax) return launch_variant<1, kModeArgmax>(tq, td, tt, p, lp, grid, stream);
     if (mode == kModeSmooth) return launch_variant<1, kModeSmooth>(tq, td, tt, p, lp, grid, stream);
     return launch_variant<1, kModeMax>(tq, td, tt, p, lp, grid, stream);
   }
+  if (mode == kModeArgmax) return launch_variant<2, kModeArgmax>(tq, td, tt, p, lp, grid, stream);
   if (mode == kModeSmooth) return launch_variant<2, kModeSmooth>(tq, td, tt, p, lp, grid, stream);
   return launch_variant<2, kModeMax>(tq, td, tt, p, lp, grid, stream);
 }
@@ -435,11 +436,11 @@ cudaError_t maxsim_launch(const CUtensorMap& tq, const CUtensorMap& td, const CU
 template <int R>
 static int max_clusters_variant(int cluster) {
   auto kern = maxsim_fwd_kernel<R, kModeMax>;
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<R>::kAlloc) != cudaSuccess)
-    return 0;
+  constexpr int kSmem = SmemLayout<R, kModeMax>::kAlloc;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) != cudaSuccess) return 0;
   cudaLaunchConfig_t cfg{};
   cudaLaunchAttribute attr[2];
-  fill_cluster_cfg<R>(cfg, attr, cluster, cluster, nullptr);
+  fill_cluster_cfg(cfg, attr, cluster, cluster, kSmem, nullptr);
   int n = 0;
   if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) return 0;
   return n;
