@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libcolpali_b200.so")
-SOURCES = ["cabi.cu", "maxsim_sm100.cu", "maxsim_kpipe_sm100.cu", "loss_sm100.cu", "smooth_bwd_sm100.cu", "exchange_sm100.cu", "head_sm100.cu",
+SOURCES = ["cabi.cu", "maxsim_sm100.cu", "maxsim_kpipe_sm100.cu", "maxsim_pair_sm100.cu", "loss_sm100.cu", "smooth_bwd_sm100.cu", "exchange_sm100.cu", "head_sm100.cu",
            "head_wide_sm100.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",  # explicit -gencode: the -arch shorthand emits compute_100 PTX

@@ -25,6 +25,9 @@ int maxsim_tile_n();
 cudaError_t maxsim_kpipe_launch(const CUtensorMap& tq, const CUtensorMap& td, const CUtensorMap& tt, const MaxSimParams& p,
                                 const LossParams& lp, int dim_panels, int mode, int grid, cudaStream_t stream);
 int maxsim_kpipe_max_clusters(int dim_panels, int cluster);
+cudaError_t maxsim_pair_launch(const CUtensorMap& tq, const CUtensorMap& td, const MaxSimParams& p, const LossParams& lp,
+                               int r, int mode, int grid, cudaStream_t stream);
+int maxsim_pair_max_clusters(int r);
 cudaError_t wait_flags_launch(const uint32_t* flags, const uint32_t* values, int n, uint32_t value, uint32_t timeout_ms,
                               uint32_t* status, cudaStream_t stream);
 cudaError_t maxsim_reduce_segments(const float* partial, float* out, int64_t plane, int nseg, int round_ref,
@@ -44,6 +47,7 @@ std::atomic<int> g_opt_dbg_delay{0};
 std::atomic<int> g_opt_balanced{1};
 std::atomic<int> g_opt_pdl{1};
 std::atomic<int> g_opt_boundary_mode{1};
+std::atomic<int> g_opt_pair{0};  // CTA-pair MMAs (maxsim_pair_sm100.cu) where the shape allows
 std::atomic<int> g_opt_wait_timeout_ms{120000};
 std::mutex g_cache_mu;  // guards the device-property / occupancy caches below
 
@@ -122,12 +126,15 @@ int current_device_info(DevInfo* out) {
 
 
 // co-resident cluster count of a kernel variant: a property of (device, variant, cluster size), queried once
-int max_clusters_cached(int dev, int variant, int cluster) {  // variant: 1 / 2 = R of the dim-128 kernel, 3..5 = K panels
-  static int cache[64][6][5];
+// variant: 1 / 2 = R of the dim-128 kernel, 3..5 = K panels, 6 / 7 = R + 5 of the CTA-pair kernel
+int max_clusters_cached(int dev, int variant, int cluster) {
+  static int cache[64][8][5];
   std::lock_guard<std::mutex> lock(g_cache_mu);
   int* slot = (dev >= 0 && dev < 64) ? &cache[dev][variant][cluster] : nullptr;
   if (slot && *slot != 0) return *slot;
-  const int n = variant <= 2 ? cpb::maxsim_max_clusters(variant, cluster) : cpb::maxsim_kpipe_max_clusters(variant, cluster);
+  const int n = variant <= 2   ? cpb::maxsim_max_clusters(variant, cluster)
+                : variant <= 5 ? cpb::maxsim_kpipe_max_clusters(variant, cluster)
+                               : cpb::maxsim_pair_max_clusters(variant - 5);
   if (slot) *slot = n;
   return n;
 }
@@ -215,6 +222,9 @@ int cpb_set_option(const char* name, int value) {
   } else if (!strcmp(name, "boundary_mode")) {
     if (value < 0 || value > 1) return fail(CPB_E_INVALID, "boundary_mode must be 0 or 1");
     g_opt_boundary_mode = value;
+  } else if (!strcmp(name, "pair")) {
+    if (value < 0 || value > 1) return fail(CPB_E_INVALID, "pair must be 0 or 1");
+    g_opt_pair = value;
   } else if (!strcmp(name, "head_cluster")) {
     if (value < 0 || value > 2) return fail(CPB_E_INVALID, "head_cluster must be 0, 1 or 2");
     g_head_cluster = value;
@@ -352,7 +362,15 @@ int cpb_maxsim_launch(cpb_maxsim_args* a) {
     // tile the 148 SMs exactly; clusters of 4 strand SMs in GPCs whose SM count is not a multiple of 4 (opt-in).
     int cluster = (p.q_groups >= 2) ? 2 : 1;
     if (opt_cluster == 1 || opt_cluster == 2 || opt_cluster == 4) cluster = opt_cluster;
-    int max_clusters = max_clusters_cached(dev, R, cluster);
+    // CTA pairs: one M = 256 MMA per two query tiles (one per CTA), half of every document tile per CTA.  Needs every
+    // CTA to own all R query tiles and a bank that can be read past the end of a partition (contiguous).
+    bool use_pair = g_opt_pair.load() != 0 && cluster == 2 && (flags & CPB_FLAG_CONTIGUOUS) != 0 &&
+                    p.num_qtiles % (2 * R) == 0 && !(p.flags & CPB_DBG_NO_TMA);
+    int max_clusters = use_pair ? max_clusters_cached(dev, 5 + R, 2) : 0;
+    if (max_clusters <= 0) {
+      use_pair = false;
+      max_clusters = max_clusters_cached(dev, R, cluster);
+    }
     if (max_clusters <= 0) {
       if (cluster == 1) return fail(CPB_E_CUDA, "kernel cannot be resident on this device (shared memory?)");
       cluster = 1;
@@ -396,7 +414,11 @@ int cpb_maxsim_launch(cpb_maxsim_args* a) {
     if (rc != CPB_OK) return rc;
     rc = make_bf16_rowmajor_map(&tt, a->d_docs, a->doc_rows, 128, 32);
     if (rc != CPB_OK) return rc;
-    CPB_CUDA(cpb::maxsim_launch(tq, td, tt, p, lp, R, mode, grid, stream));
+    if (use_pair) {
+      CPB_CUDA(cpb::maxsim_pair_launch(tq, td, p, lp, R, mode, grid, stream));
+    } else {
+      CPB_CUDA(cpb::maxsim_launch(tq, td, tt, p, lp, R, mode, grid, stream));
+    }
   } else {
     // K-pipelined kernel: one query tile per CTA, whole-document partitions
     const int panels = dim / 64;

@@ -125,15 +125,6 @@ __device__ __forceinline__ void bc_store(uint32_t slot, uint32_t sw, bool take, 
   bc_store_half(slot, sw, 0, take, &v[0]);
   bc_store_half(slot, sw, 1, take, &v[16]);
 }
-__device__ __forceinline__ void bc_load(uint32_t slot, uint32_t sw, uint32_t (&v)[32]) {
-#pragma unroll
-  for (int k = 0; k < 8; ++k)
-    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(v[4 * k]), "=r"(v[4 * k + 1]), "=r"(v[4 * k + 2]), "=r"(v[4 * k + 3])
-                 : "r"(slot + ((k << 4) ^ sw))
-                 : "memory");
-}
-
 // a whole 32-column chunk
 __device__ __forceinline__ void argmax_fold_full(const uint32_t (&v)[32], float& m, int& bidx0, uint32_t slot, uint32_t sw,
                                                  int idx0) {
@@ -159,17 +150,20 @@ __device__ __forceinline__ void argmax_fold(const uint32_t (&v)[32], float& m, i
 constexpr int kNoChunk = -0x40000000;
 // document-relative index of the first maximal token, -1 if no token beat the initial value (the floor won)
 __device__ __forceinline__ int argmax_resolve(uint32_t slot, uint32_t sw, float m, int bidx0) {
-  uint32_t bc[32];
-  bc_load(slot, sw, bc);
-  int c[32];
+  int best = 64;
 #pragma unroll
-  for (int i = 0; i < 32; ++i) c[i] = (__uint_as_float(bc[i]) == m) ? i : 64;
+  for (int k = 0; k < 8; k += 2) {  // eight columns at a time: the slot is read back in pieces to keep few registers live
+    uint32_t w[8];
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(slot + ((k << 4) ^ sw)) : "memory");
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "r"(slot + (((k + 1) << 4) ^ sw)) : "memory");
+    int c[8];
 #pragma unroll
-  for (int w = 16; w > 0; w >>= 1) {
-#pragma unroll
-    for (int i = 0; i < w; ++i) c[i] = min(c[i], c[i + w]);
+    for (int i = 0; i < 8; ++i) c[i] = (__uint_as_float(w[i]) == m) ? 4 * k + i : 64;
+    best = min(best, min(min(min(c[0], c[1]), min(c[2], c[3])), min(min(c[4], c[5]), min(c[6], c[7]))));
   }
-  return (bidx0 == kNoChunk) ? -1 : bidx0 + c[0];
+  return (bidx0 == kNoChunk) ? -1 : bidx0 + best;
 }
 
 __device__ __forceinline__ float round_bf16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
@@ -251,7 +245,13 @@ __device__ __forceinline__ void multimem_st_f32(uint64_t mc_addr, float x) {
 }
 
 // Runs on warps 2..5 (one TMEM lane quadrant each).  R = resident query tiles per CTA.
-template <int R, int kMode>
+// kPair: the CTA is half of a cta_group::2 pair -- the accumulator is handed back on the LEADER's tmem_empty barrier
+// (rank 0 of the cluster, where the MMA issuer waits for eight arrivals: four epilogue warps in each CTA).
+// kGroups: 1 = warps 2..5 walk all R query tiles; 2 (R = 2 only) = warps 2..5 take query tile 0 and warps 6..9 query tile
+// 1, i.e. one accumulator of the ping-pong each.  A warp alone on its scheduler issues at 0.3-0.5 IPC, so two warps per
+// scheduler nearly double what the epilogue can fold per tensor cycle (it is the bottleneck in the argmax and smooth
+// modes); the per-tile state never crosses warps because every query tile has its own running maxima.
+template <int R, int kMode, bool kPair = false, int kGroups = 1>
 __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const CtaSlice& sl, uint32_t tmem_base,
                                                 uint64_t* tmem_full, uint64_t* tmem_empty, int warp, int lane,
                                                 uint8_t* bc_smem = nullptr) {
@@ -260,10 +260,13 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
   constexpr bool kArgmax = (kMode == kModeArgmax);
   constexpr bool kSmooth = (kMode == kModeSmooth);
   const int g = sl.g, part = sl.part, r_cnt = sl.r_cnt, d0 = sl.d0, d1 = sl.d1, bal_r0 = sl.bal_r0, bal_r1 = sl.bal_r1;
+  static_assert(kGroups == 1 || (kGroups == 2 && R == 2), "two epilogue warp groups = one per resident query tile");
   const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+  const int grp = (warp - 2) >> 2;  // which query tile this warp folds when kGroups == 2
   const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
   const bool round_ref = (p.flags & CPB_FLAG_ROUND_BF16) != 0;
   const bool skip = (p.flags & CPB_DBG_SKIP_EPILOGUE) != 0;
+  const uint32_t empty_leader = kPair ? mapa_u32(smem_u32(tmem_empty), 0u) : 0u;
   const bool shifted_boundary = p.boundary_mode == 1;  // read once: a constant-bank load inside the hold window costs ~60 cycles
 
   // document `doc` is complete for resident query tile r: fold this query segment's 32 token maxima
@@ -376,7 +379,8 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
       // nothing but empty documents: their score is the sum of the floors (balanced mode: an empty partition)
       if (!p.balanced)
         for (int e = d; e < run.e; ++e)
-          for (int r = 0; r < r_cnt; ++r) finalize(e, r, doc_init(e), -1, 0.f);
+          for (int r = 0; r < r_cnt; ++r)
+            if (kGroups == 1 || r == grp) finalize(e, r, doc_init(e), -1, 0.f);
       d = run.e;
       continue;
     }
@@ -407,9 +411,10 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
       // ran at ~12 k cycles per job).  The max mode keeps the unrolled form its per-job budget was tuned with.
 #pragma unroll(kMode == kModeMax ? R : 1)
       for (int r = 0; r < R; ++r) {
-        if (r < r_cnt) {
-          const uint32_t a = job & 1u;
-          const uint32_t aphase = (job >> 1) & 1u;
+        if (r < r_cnt && (kGroups == 1 || r == grp)) {
+          const uint32_t jb = job + static_cast<uint32_t>(r);  // jobs are numbered tile-major, query tile minor
+          const uint32_t a = jb & 1u;
+          const uint32_t aphase = (jb >> 1) & 1u;
           const long long t0 = dbg ? clock64() : 0;
           mbar_wait(&tmem_full[a], aphase);
           const long long t1 = dbg ? clock64() : 0;
@@ -443,7 +448,9 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
           auto release_acc = [&]() {  // accumulator drained: hand the TMEM stage back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[a]);
+            if (lane == 0) {
+              if constexpr (kPair) mbar_arrive_cluster(empty_leader + a * 8u); else mbar_arrive(&tmem_empty[a]);
+            }
             if (dbg) t2 = clock64();
           };
 
@@ -481,6 +488,23 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
               if constexpr (kArgmax) argmax_fold_full(v, mm, ai, bc_slot, bc_sw, idx_t + 32 * k);
               else mm = max32(v, mm);
             };
+            if constexpr (kGroups == 2) {
+              // two warps per scheduler hide each other's latencies: one chunk in flight is enough, and the register
+              // budget of a 320-thread CTA (168 per thread) has no room for four buffers
+              uint32_t va[32], vb[32];
+              tmem_ld_x32(taddr, va);
+#pragma unroll
+              for (int k = 0; k < 8; k += 2) {
+                tmem_ld_wait();
+                reg_fence32(va);
+                tmem_ld_x32(taddr + 32 * (k + 1), vb);
+                fold(va, k);
+                tmem_ld_wait();
+                reg_fence32(vb);
+                if (k + 2 < 8) tmem_ld_x32(taddr + 32 * (k + 2), va); else release_acc();
+                fold(vb, k + 1);
+              }
+            } else {
             uint32_t va[32], vb[32], vc[32], vd[32];
             tmem_ld_x32(taddr, va);
             tmem_ld_x32(taddr + 32, vb);
@@ -511,6 +535,7 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
             release_acc();  // every accumulator read has landed in registers
             fold(vc, 6);
             fold(vd, 7);
+            }
             while (doc_end <= tile_end) finish_doc();  // document (and empty followers) ending at the tile end
           } else if (path == 2 && shifted_boundary && doc_end - row >= 32 && doc_end - row <= kTileN - 32) {
             // one boundary at column b, at least 32 columns from either edge: read the tile as 32-column chunks
@@ -680,9 +705,9 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
           nxt_end = doc_end;
           nxt_nlen = doc_nlen;
           nxt_ninit = doc_ninit;
-          ++job;
         }
       }
+      job += static_cast<uint32_t>(r_cnt);
       cur = nxt;
       cur_row0 = nxt_row0;
       cur_end = nxt_end;
@@ -692,6 +717,7 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
     if (p.balanced && !skip && cur < p.n_docs && cur_end != 0x7fffffff && cur_row0 < bal_r1 && cur_end > bal_r1) {
       // my last document continues in the next partition: combine with the neighbour's partial and emit it
       for (int r = 0; r < r_cnt; ++r) {
+        if (kGroups == 2 && r != grp) continue;
         float mm = (r == 0) ? m[0] : m[R - 1];
         int ai = (r == 0) ? am[0] : am[R - 1];
         if constexpr (kArgmax)

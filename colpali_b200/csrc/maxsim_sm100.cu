@@ -47,7 +47,12 @@ constexpr int kQTileBytes = kTileM * kDim * 2;  // 32 KiB
 constexpr int kQPanelBytes = kTileM * 64 * 2;   // 16 KiB
 constexpr int kDTileBytes = kTileN * kDim * 2;  // 64 KiB
 constexpr int kDPanelBytes = kTileN * 64 * 2;   // 32 KiB
-constexpr int kThreads = 192;
+// warp 0: TMA, warp 1: MMA issuer, then one or two groups of four epilogue warps (maxsim_epilogue.cuh: two groups, one per
+// resident query tile, in the modes whose epilogue is the bottleneck)
+template <int R, int kMode>
+constexpr int kEpiGroups = (R == 2 && kMode != kModeMax) ? 2 : 1;
+template <int R, int kMode>
+constexpr int kThreads = 64 + 128 * kEpiGroups<R, kMode>;
 #ifndef CPB_MMA_SPLIT
 #define CPB_MMA_SPLIT 6
 #endif
@@ -71,7 +76,7 @@ struct SmemLayout {
 };
 
 template <int R, int kMode>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads<R, kMode>, 1)
 maxsim_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_d,
                   const __grid_constant__ CUtensorMap tmap_tail, const MaxSimParams p, const LossParams lp) {
   using L = SmemLayout<R, kMode>;
@@ -276,6 +281,10 @@ maxsim_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         j.a_desc0 = make_sw128_kmajor_desc(q_addr + j.r * kQTileBytes);
         j.b_desc0 = make_sw128_kmajor_desc(d_addr + j.stage * kDTileBytes);
       };
+      auto ready = [&](const Job& j) {  // would prepare(j) return without waiting?
+        if (j.first_of_tile && !mbar_test_wait(&full[j.stage], j.phase)) return false;
+        return mbar_test_wait(&tmem_empty[j.job & 1u], ((j.job >> 1) & 1u) ^ 1u);
+      };
       auto issue = [&](const Job& j, int k_lo, int k_hi) {
         const uint32_t d_tmem = tmem_base + (j.job & 1u) * kTileN;
 #pragma unroll
@@ -308,7 +317,11 @@ maxsim_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         advance(nxt);
         if (elect_one()) issue(cur, 0, kSplit);
         __syncwarp();
-        if (nxt.valid) prepare(nxt);
+        // Prepare the next job between the K-steps only if that does not block: when the epilogue is the slower side
+        // the wait for its accumulator would hold back the last K-steps (and the commit) of THIS job, and the epilogue
+        // would in turn wait for them -- a serialisation of ~400 cycles per job in the argmax forward.
+        const bool early = nxt.valid && ready(nxt);
+        if (early) prepare(nxt);
         if (elect_one()) {
           issue(cur, kSplit, kDim / 16);
           umma_commit(&tmem_full[cur.job & 1u]);
@@ -317,6 +330,7 @@ maxsim_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
           }
         }
         __syncwarp();
+        if (nxt.valid && !early) prepare(nxt);
         cur = nxt;
       }
       if (dbg && lane == 0) {  // cycles the issuer spent blocked on TMA data / on the epilogue
@@ -327,7 +341,8 @@ maxsim_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   } else {
     // ================================ epilogue (maxsim_epilogue.cuh) ==========================
     const CtaSlice sl{g, part, r_cnt, d0, d1, bal_r0, bal_r1};
-    maxsim_epilogue<R, kMode>(p, sl, tmem_base, tmem_full, tmem_empty, warp, lane, smem + L::kBcOff);
+    maxsim_epilogue<R, kMode, false, kEpiGroups<R, kMode>>(p, sl, tmem_base, tmem_full, tmem_empty, warp, lane,
+                                                           smem + L::kBcOff);
   }
 
   // ---- teardown ---------------------------------------------------------------------------
@@ -380,10 +395,10 @@ __global__ void maxsim_reduce_segments_kernel(const float* __restrict__ partial,
   out[i] = round_ref ? round_bf16(s) : s;
 }
 
-static void fill_cluster_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int grid, int cluster, int smem_bytes,
-                             cudaStream_t stream, int pdl = 0) {
+static void fill_cluster_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int grid, int cluster, int threads,
+                             int smem_bytes, cudaStream_t stream, int pdl = 0) {
   cfg.gridDim = dim3(static_cast<unsigned>(grid));
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(static_cast<unsigned>(threads));
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -415,7 +430,7 @@ static cudaError_t launch_variant(const CUtensorMap& tq, const CUtensorMap& td, 
   }
   cudaLaunchConfig_t cfg{};
   cudaLaunchAttribute attr[2];
-  fill_cluster_cfg(cfg, attr, grid, p.cluster, SmemLayout<R, kMode>::kAlloc, stream, p.pdl);
+  fill_cluster_cfg(cfg, attr, grid, p.cluster, kThreads<R, kMode>, SmemLayout<R, kMode>::kAlloc, stream, p.pdl);
   return cudaLaunchKernelEx(&cfg, kern, tq, td, tt, p, lp);
 }
 
@@ -440,7 +455,7 @@ static int max_clusters_variant(int cluster) {
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) != cudaSuccess) return 0;
   cudaLaunchConfig_t cfg{};
   cudaLaunchAttribute attr[2];
-  fill_cluster_cfg(cfg, attr, cluster, cluster, kSmem, nullptr);
+  fill_cluster_cfg(cfg, attr, cluster, cluster, kThreads<R, kModeMax>, kSmem, nullptr);
   int n = 0;
   if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) return 0;
   return n;
