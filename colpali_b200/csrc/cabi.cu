@@ -541,6 +541,9 @@ int cpb_maxsim_bwd_launch(const cpb_maxsim_bwd_args* a) {
   if (a->max_doc_len <= 0) return fail(CPB_E_INVALID, "max_doc_len must be positive");
   const uint64_t* dd_doc_base = CPB_HAS(a, cpb_maxsim_bwd_args, d_dd_doc_base) ? a->d_dd_doc_base : nullptr;
   if (dd_doc_base && smooth) return fail(CPB_E_UNSUPPORTED, "the peer-scatter dD serves the hard max only");
+  const bool grad_bf16 = (a->flags & CPB_FLAG_GRAD_BF16) != 0;
+  if (grad_bf16 && (smooth || dd_doc_base))
+    return fail(CPB_E_UNSUPPORTED, "CPB_FLAG_GRAD_BF16 serves the hard max without the peer scatter (those accumulate in fp32)");
   cpb::BwdParams p{};
   p.g = a->d_grad_scores;
   p.grad_out = a->d_grad_out;
@@ -551,8 +554,9 @@ int cpb_maxsim_bwd_launch(const cpb_maxsim_bwd_args* a) {
   p.docs = static_cast<const __nv_bfloat16*>(a->d_docs);
   p.doc_start = a->d_doc_start;
   p.doc_len = a->d_doc_len;
-  p.dq = a->d_dq;
-  p.dd = a->d_dd;
+  p.dq = static_cast<float*>(a->d_dq);
+  p.dd = static_cast<float*>(a->d_dd);
+  p.out_bf16 = grad_bf16 ? 1 : 0;
   p.dd_doc_base = dd_doc_base;
   p.B = a->n_queries;
   p.C = a->n_docs;
