@@ -462,7 +462,7 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
           if (!kSmooth && n_valid == kTileN) {
             if (doc_end >= tile_end) {
               path = 1;
-            } else if (!kArgmax && doc_end > row && doc + 1 < run.e) {
+            } else if (doc_end > row && doc + 1 < run.e) {
               if (doc_end + doc_nlen >= tile_end) path = 2;
             }
           }
@@ -537,7 +537,32 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
             fold(vd, 7);
             }
             while (doc_end <= tile_end) finish_doc();  // document (and empty followers) ending at the tile end
-          } else if (path == 2 && shifted_boundary && doc_end - row >= 32 && doc_end - row <= kTileN - 32) {
+          } else if (kArgmax && path == 2 && doc_end - row >= 32 && doc_end - row <= kTileN - 32) {
+            // one boundary, argmax: the same boundary-aligned chunks as the max mode below, but in order -- the old
+            // document's chunks, its lookup (which reads the best-chunk slot back), then the new document's chunks into
+            // the same slot.  Overlapping chunks are harmless: a repeated value is not GREATER than the running maximum.
+            const int b = doc_end - row;
+            const int n_old = (b + 31) >> 5;
+            auto col = [&](int i) { return (i < n_old) ? min(32 * i, b - 32) : min(b + 32 * (i - n_old), kTileN - 32); };
+            uint32_t va[32], vb[32];
+            tmem_ld_x32(taddr + col(0), va);
+#pragma unroll 1
+            for (int i = 0; i < 9; i += 2) {
+              tmem_ld_wait();
+              reg_fence32(va);
+              if (i + 1 < 9) tmem_ld_x32(taddr + col(i + 1), vb); else release_acc();
+              if (i == n_old) finish_doc();
+              argmax_fold_full(va, mm, ai, bc_slot, bc_sw, row + col(i) - doc_row0);
+              if (i + 1 < 9) {
+                tmem_ld_wait();
+                reg_fence32(vb);
+                tmem_ld_x32(taddr + col(i + 2), va);  // i + 2 <= 8
+                if (i + 1 == n_old) finish_doc();
+                argmax_fold_full(vb, mm, ai, bc_slot, bc_sw, row + col(i + 1) - doc_row0);
+              }
+            }
+            while (doc_end <= tile_end) finish_doc();
+          } else if (!kArgmax && path == 2 && shifted_boundary && doc_end - row >= 32 && doc_end - row <= kTileN - 32) {
             // one boundary at column b, at least 32 columns from either edge: read the tile as 32-column chunks
             // ALIGNED TO THE BOUNDARY -- the old document's columns [0, b) as chunks at min(32 i, b - 32), the new
             // one's [b, 256) at min(b + 32 j, 224).  Chunks of one document may overlap (a maximum is idempotent), so
@@ -589,7 +614,7 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
             finish_doc();  // old document (running max mm); the cursor moves to the new one, whose max is mb
             mm = mb;
             while (doc_end <= tile_end) finish_doc();
-          } else if (path == 2) {
+          } else if (!kArgmax && path == 2) {
             // one boundary at column b: per 32-column chunk the FMNMX3 tree goes to the old document (chunk < kb)
             // or the new one (chunk > kb) through selects; the boundary chunk itself is re-read at the end and split
             // element-wise after the release (branching per chunk would be if-converted into doing everything).
