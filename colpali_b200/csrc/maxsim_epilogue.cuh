@@ -319,7 +319,7 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
   uint32_t job = 0;
   const bool dbg = (p.flags & CPB_DBG_CLOCKS) != 0;
   long long e_wait = 0, e_hold = 0, e_post = 0, e_hold2 = 0, e_genwait = 0;
-  int n_path2 = 0;
+  int n_path2 = 0, n_own = 0;
 
   // ---- balanced mode: which document contains the first row of my partition, and is it cut? ----------------
   int first_doc = d0;
@@ -714,7 +714,10 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
             const long long t3 = clock64();
             e_wait += t1 - t0;
             e_post += t3 - t2;
-            if (path == 2) { e_hold2 += t2 - t1; ++n_path2; } else { e_hold += t2 - t1; }
+            // max mode: boundary tiles apart; argmax / smooth: everything that is not a whole-tile fast path apart
+            const bool other = (kMode == kModeMax) ? (path == 2) : (path != 1);
+            if (other) { e_hold2 += t2 - t1; ++n_path2; } else { e_hold += t2 - t1; }
+            ++n_own;
           }
           if (r == 0) {
             m[0] = mm;
@@ -762,9 +765,9 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
     o[2] = static_cast<float>(e_wait);
     o[3] = static_cast<float>(e_hold);
     o[4] = static_cast<float>(e_post);
-    o[5] = static_cast<float>(kMode == kModeMax ? e_hold2 : e_genwait);  // argmax / smooth: cycles blocked in tcgen05.wait::ld
+    o[5] = static_cast<float>(e_hold2);
     o[6] = static_cast<float>(n_path2);
-    o[7] = static_cast<float>(job);
+    o[7] = static_cast<float>(n_own);  // jobs THIS warp folded (half of the CTA's with two epilogue groups)
   }
 }
 
