@@ -249,8 +249,8 @@ maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           }
         }
       };
-      constexpr long long kEarlySpin = 128 * (CPB_EARLY_SPIN_KSTEPS);
-      constexpr int kSplit = CPB_PAIR_SPLIT;
+      const long long kEarlySpin = p.early_spin;
+      const int kSplit = p.mma_split;  // K-steps issued before the next job's waits
       advance(cur);
       if (cur.valid) prepare(cur);
       while (cur.valid) {
