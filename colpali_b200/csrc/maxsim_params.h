@@ -67,7 +67,6 @@ struct MaxSimParams {
   int mma_split;   // K-steps of a job issued before the issuer looks at the next job's barriers (1..8)
   int early_spin;  // cycles the issuer probes those barriers before finishing the current job first
   int dbg_delay;   // profiling only: cycles the epilogue holds an unread accumulator in CPB_DBG_SKIP_EPILOGUE mode
-  int mma_split;   // K-steps of a job issued before the next job's barrier waits (5..8)
 };
 
 }  // namespace cpb
