@@ -36,6 +36,7 @@ CPB_ABI_VERSION = 2
 CPB_FLAG_ROUND_BF16 = 1
 CPB_FLAG_CONTIGUOUS = 2
 CPB_FLAG_INDEPENDENT = 4
+CPB_FLAG_GRAD_BF16 = 8
 CPB_HEAD_CLAMP_NORM = 1
 CPB_HEAD_SINGLE_ROUNDING = 2
 CPB_LOSS_CE = 0

@@ -48,6 +48,7 @@ std::atomic<int> g_opt_balanced{1};
 std::atomic<int> g_opt_pdl{1};
 std::atomic<int> g_opt_boundary_mode{1};
 std::atomic<int> g_opt_pair{0};  // CTA-pair MMAs (maxsim_pair_sm100.cu) where the shape allows
+std::atomic<int> g_opt_mma_split{6}, g_opt_early_spin{512};  // MMA issuer pacing (MaxSimParams::mma_split / early_spin)
 std::atomic<int> g_opt_wait_timeout_ms{120000};
 std::mutex g_cache_mu;  // guards the device-property / occupancy caches below
 
@@ -222,6 +223,12 @@ int cpb_set_option(const char* name, int value) {
   } else if (!strcmp(name, "boundary_mode")) {
     if (value < 0 || value > 1) return fail(CPB_E_INVALID, "boundary_mode must be 0 or 1");
     g_opt_boundary_mode = value;
+  } else if (!strcmp(name, "mma_split")) {
+    if (value < 1 || value > 8) return fail(CPB_E_INVALID, "mma_split must be 1..8");
+    g_opt_mma_split = value;
+  } else if (!strcmp(name, "early_spin")) {
+    if (value < 0) return fail(CPB_E_INVALID, "early_spin must be >= 0");
+    g_opt_early_spin = value;
   } else if (!strcmp(name, "pair")) {
     if (value < 0 || value > 1) return fail(CPB_E_INVALID, "pair must be 0 or 1");
     g_opt_pair = value;
@@ -349,6 +356,8 @@ int cpb_maxsim_launch(cpb_maxsim_args* a) {
   p.boundary_mode = g_opt_boundary_mode.load();
   p.flags = (flags & 0xffffu) | g_opt_debug_flags.load();
   p.dbg_delay = g_opt_dbg_delay.load();
+  p.mma_split = g_opt_mma_split.load();
+  p.early_spin = g_opt_early_spin.load();
 
   const int opt_cluster = g_opt_cluster.load(), opt_r = g_opt_qtiles_per_cta.load();
   int grid = 0;
@@ -541,6 +550,9 @@ int cpb_maxsim_bwd_launch(const cpb_maxsim_bwd_args* a) {
   if (a->max_doc_len <= 0) return fail(CPB_E_INVALID, "max_doc_len must be positive");
   const uint64_t* dd_doc_base = CPB_HAS(a, cpb_maxsim_bwd_args, d_dd_doc_base) ? a->d_dd_doc_base : nullptr;
   if (dd_doc_base && smooth) return fail(CPB_E_UNSUPPORTED, "the peer-scatter dD serves the hard max only");
+  const bool grad_bf16 = (a->flags & CPB_FLAG_GRAD_BF16) != 0;
+  if (grad_bf16 && (smooth || dd_doc_base))
+    return fail(CPB_E_UNSUPPORTED, "CPB_FLAG_GRAD_BF16 serves the hard max without the peer scatter (those accumulate in fp32)");
   cpb::BwdParams p{};
   p.g = a->d_grad_scores;
   p.grad_out = a->d_grad_out;
@@ -551,8 +563,9 @@ int cpb_maxsim_bwd_launch(const cpb_maxsim_bwd_args* a) {
   p.docs = static_cast<const __nv_bfloat16*>(a->d_docs);
   p.doc_start = a->d_doc_start;
   p.doc_len = a->d_doc_len;
-  p.dq = a->d_dq;
-  p.dd = a->d_dd;
+  p.dq = static_cast<float*>(a->d_dq);
+  p.dd = static_cast<float*>(a->d_dd);
+  p.out_bf16 = grad_bf16 ? 1 : 0;
   p.dd_doc_base = dd_doc_base;
   p.B = a->n_queries;
   p.C = a->n_docs;

@@ -44,6 +44,7 @@ struct BwdParams {
   int dim;                    // padded embedding dim: 128, 192, 256 or 320
   int max_doc_len;            // longest document
   int contiguous;             // documents back to back and covering the bank: no row of dd is outside a document
+  int out_bf16;               // dq / dd point to bf16 buffers (hard max without dd_doc_base)
   int64_t doc_rows;
 };
 

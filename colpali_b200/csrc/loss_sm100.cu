@@ -35,6 +35,21 @@ cudaError_t colbert_loss_launch(const LossParams& p, cudaStream_t stream) {
 // ------------------------------------------------------------------------------------------------
 // Embedding dim = 64 * P (P = 2..5): a lane owns the bf16 pairs {lane, lane + 32, ...} of a row.
 
+// one gradient row of 64 P elements, two per lane and step: fp32, or bf16 rounded to nearest even (what a cast of the
+// fp32 row would give)
+template <int P>
+__device__ __forceinline__ void store_grad_row(float* base, int out_bf16, int64_t row, int lane, const float2 (&acc)[P]) {
+  if (out_bf16) {
+    __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(base) + row * (32 * P);
+#pragma unroll
+    for (int j = 0; j < P; ++j) dst[j * 32 + lane] = __float22bfloat162_rn(acc[j]);
+  } else {
+    float2* dst = reinterpret_cast<float2*>(base) + row * (32 * P);
+#pragma unroll
+    for (int j = 0; j < P; ++j) dst[j * 32 + lane] = acc[j];
+  }
+}
+
 // dQ: one warp per query row, a gather over the C winning document tokens.  The (index, weight, start) triples of 32
 // documents are fetched by the 32 lanes at once and broadcast by shuffles, and four row gathers are in flight before the
 // first is consumed: the loop is a chain of dependent 256-byte loads otherwise (C = 64..512 iterations).
@@ -101,9 +116,7 @@ __global__ void __launch_bounds__(256) maxsim_bwd_dq_kernel(const BwdParams p) {
       for (int u = 0; u < 4; ++u) fma_row(raw[u], wk[u]);
     }
   }
-  float2* dst = reinterpret_cast<float2*>(p.dq + static_cast<int64_t>(row) * kDim);
-#pragma unroll
-  for (int j = 0; j < P; ++j) dst[j * 32 + lane] = acc[j];
+  store_grad_row<P>(p.dq, p.out_bf16, row, lane, acc);
 }
 
 // dD without atomics: a CTA owns tokens [t0, t0 + kDdTokens) of ONE document.  It buckets the (query row -> winning
@@ -223,9 +236,7 @@ __global__ void __launch_bounds__(kDdThreads) maxsim_bwd_dd_kernel(const BwdPara
 #pragma unroll
       for (int j = 0; j < P; ++j) atomicAdd(dst + j * 32 + lane, acc[j]);  // red.global.add.v2.f32 over NVLink
     } else {
-      float2* dst = reinterpret_cast<float2*>(p.dd + (doc_row0 + t) * kDim);
-#pragma unroll
-      for (int j = 0; j < P; ++j) dst[j * 32 + lane] = acc[j];
+      store_grad_row<P>(p.dd, p.out_bf16, doc_row0 + t, lane, acc);
     }
   }
 }
@@ -246,7 +257,7 @@ static cudaError_t maxsim_bwd_launch_p(const BwdParams& p, cudaStream_t stream) 
       if (e != cudaSuccess) return e;
     }
     if (!p.contiguous && p.dd_doc_base == nullptr) {  // rows between documents belong to nobody: zero them
-      cudaError_t e = cudaMemsetAsync(p.dd, 0, static_cast<size_t>(p.doc_rows) * 64 * P * sizeof(float), stream);
+      cudaError_t e = cudaMemsetAsync(p.dd, 0, static_cast<size_t>(p.doc_rows) * 64 * P * (p.out_bf16 ? 2 : 4), stream);
       if (e != cudaSuccess) return e;
     }
     const dim3 grid(static_cast<unsigned>(p.C), static_cast<unsigned>((p.max_doc_len + kDdTokens - 1) / kDdTokens));

@@ -319,7 +319,7 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
   uint32_t job = 0;
   const bool dbg = (p.flags & CPB_DBG_CLOCKS) != 0;
   long long e_wait = 0, e_hold = 0, e_post = 0, e_hold2 = 0, e_genwait = 0;
-  int n_path2 = 0;
+  int n_path2 = 0, n_own = 0;
 
   // ---- balanced mode: which document contains the first row of my partition, and is it cut? ----------------
   int first_doc = d0;
@@ -462,7 +462,7 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
           if (!kSmooth && n_valid == kTileN) {
             if (doc_end >= tile_end) {
               path = 1;
-            } else if (!kArgmax && doc_end > row && doc + 1 < run.e) {
+            } else if (doc_end > row && doc + 1 < run.e) {
               if (doc_end + doc_nlen >= tile_end) path = 2;
             }
           }
@@ -537,7 +537,32 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
             fold(vd, 7);
             }
             while (doc_end <= tile_end) finish_doc();  // document (and empty followers) ending at the tile end
-          } else if (path == 2 && shifted_boundary && doc_end - row >= 32 && doc_end - row <= kTileN - 32) {
+          } else if (kArgmax && path == 2 && doc_end - row >= 32 && doc_end - row <= kTileN - 32) {
+            // one boundary, argmax: the same boundary-aligned chunks as the max mode below, but in order -- the old
+            // document's chunks, its lookup (which reads the best-chunk slot back), then the new document's chunks into
+            // the same slot.  Overlapping chunks are harmless: a repeated value is not GREATER than the running maximum.
+            const int b = doc_end - row;
+            const int n_old = (b + 31) >> 5;
+            auto col = [&](int i) { return (i < n_old) ? min(32 * i, b - 32) : min(b + 32 * (i - n_old), kTileN - 32); };
+            uint32_t va[32], vb[32];
+            tmem_ld_x32(taddr + col(0), va);
+#pragma unroll 1
+            for (int i = 0; i < 9; i += 2) {
+              tmem_ld_wait();
+              reg_fence32(va);
+              if (i + 1 < 9) tmem_ld_x32(taddr + col(i + 1), vb); else release_acc();
+              if (i == n_old) finish_doc();
+              argmax_fold_full(va, mm, ai, bc_slot, bc_sw, row + col(i) - doc_row0);
+              if (i + 1 < 9) {
+                tmem_ld_wait();
+                reg_fence32(vb);
+                tmem_ld_x32(taddr + col(i + 2), va);  // i + 2 <= 8
+                if (i + 1 == n_old) finish_doc();
+                argmax_fold_full(vb, mm, ai, bc_slot, bc_sw, row + col(i + 1) - doc_row0);
+              }
+            }
+            while (doc_end <= tile_end) finish_doc();
+          } else if (!kArgmax && path == 2 && shifted_boundary && doc_end - row >= 32 && doc_end - row <= kTileN - 32) {
             // one boundary at column b, at least 32 columns from either edge: read the tile as 32-column chunks
             // ALIGNED TO THE BOUNDARY -- the old document's columns [0, b) as chunks at min(32 i, b - 32), the new
             // one's [b, 256) at min(b + 32 j, 224).  Chunks of one document may overlap (a maximum is idempotent), so
@@ -589,7 +614,7 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
             finish_doc();  // old document (running max mm); the cursor moves to the new one, whose max is mb
             mm = mb;
             while (doc_end <= tile_end) finish_doc();
-          } else if (path == 2) {
+          } else if (!kArgmax && path == 2) {
             // one boundary at column b: per 32-column chunk the FMNMX3 tree goes to the old document (chunk < kb)
             // or the new one (chunk > kb) through selects; the boundary chunk itself is re-read at the end and split
             // element-wise after the release (branching per chunk would be if-converted into doing everything).
@@ -689,7 +714,10 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
             const long long t3 = clock64();
             e_wait += t1 - t0;
             e_post += t3 - t2;
-            if (path == 2) { e_hold2 += t2 - t1; ++n_path2; } else { e_hold += t2 - t1; }
+            // max mode: boundary tiles apart; argmax / smooth: everything that is not a whole-tile fast path apart
+            const bool other = (kMode == kModeMax) ? (path == 2) : (path != 1);
+            if (other) { e_hold2 += t2 - t1; ++n_path2; } else { e_hold += t2 - t1; }
+            ++n_own;
           }
           if (r == 0) {
             m[0] = mm;
@@ -737,9 +765,9 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
     o[2] = static_cast<float>(e_wait);
     o[3] = static_cast<float>(e_hold);
     o[4] = static_cast<float>(e_post);
-    o[5] = static_cast<float>(kMode == kModeMax ? e_hold2 : e_genwait);  // argmax / smooth: cycles blocked in tcgen05.wait::ld
+    o[5] = static_cast<float>(e_hold2);
     o[6] = static_cast<float>(n_path2);
-    o[7] = static_cast<float>(job);
+    o[7] = static_cast<float>(n_own);  // jobs THIS warp folded (half of the CTA's with two epilogue groups)
   }
 }
 

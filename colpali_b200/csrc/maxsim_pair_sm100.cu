@@ -29,6 +29,10 @@
 #include "maxsim_params.h"
 #include "sm100_ptx.cuh"
 
+#ifndef CPB_EARLY_SPIN_KSTEPS
+#define CPB_EARLY_SPIN_KSTEPS 4  /* how long (in 128-cycle K-steps) the issuer probes for the next job's resources */
+#endif
+
 namespace cpb {
 namespace pair {
 
@@ -245,7 +249,8 @@ maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           }
         }
       };
-      constexpr int kSplit = CPB_PAIR_SPLIT;
+      const long long kEarlySpin = p.early_spin;
+      const int kSplit = p.mma_split;  // K-steps issued before the next job's waits
       advance(cur);
       if (cur.valid) prepare(cur);
       while (cur.valid) {
@@ -256,7 +261,16 @@ maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         // Prepare the next job between the K-steps only if that does not block: when the epilogue is the slower side
         // the wait for its accumulator would hold back the last K-steps (and the commit) of THIS job, and the epilogue
         // would in turn wait for them -- a serialisation of ~400 cycles per job in the argmax forward.
-        const bool early = nxt.valid && ready(nxt);
+        // (the probe is repeated for at most ~kEarlySpin cycles: the K-steps already queued cover that, and in the
+        // MMA-bound modes the accumulator usually frees within that time -- going the late way there costs ~50 cycles
+        // per job because only two K-steps are then in flight across the next job's set-up)
+        bool early = false;
+        if (nxt.valid) {
+          const long long t_probe = clock64();
+          do {
+            early = ready(nxt);
+          } while (!early && clock64() - t_probe < kEarlySpin);
+        }
         if (early) prepare(nxt);
         if (elect_one()) {
           issue(cur, kSplit, kDim / 16);

@@ -83,18 +83,23 @@ def _maxsim_for_loss(qb: QueryBlock, bank: DocBank, need_grad: bool, smooth_tau:
 
 
 def _maxsim_backward(g, go, aux, smooth_tau, nq_real, q_flat, b, nq_pad, bank_flat, bank_start, bank_len, n_docs,
-                     max_len, need_dq, need_dd, dd_doc_base=None):
-    """dq [b * nq_pad, dim], dd [rows, dim] (fp32, fully written by the kernels) for one score matrix.  With
+                     max_len, need_dq, need_dd, dd_doc_base=None, bf16_out=False):
+    """dq [b * nq_pad, dim], dd [rows, dim] (fp32, fully written by the kernels) for one score matrix.  ``bf16_out``
+    (hard max only): the kernels round the rows to bf16 themselves, saving the two cast kernels of a bf16 model.  With
     ``dd_doc_base`` (int64 device tensor of per-document peer addresses) the document gradients are added straight into
     their owner ranks' accumulators instead (multi-GPU exchange) and ``dd`` is None."""
     dev = q_flat.device
     dim = q_flat.shape[1]
-    dq = torch.empty(b * nq_pad, dim, dtype=torch.float32, device=dev) if need_dq else None
-    dd = torch.empty(bank_flat.shape[0], dim, dtype=torch.float32, device=dev) if (need_dd and dd_doc_base is None) else None
+    bf16_out = bool(bf16_out) and not smooth_tau > 0 and dd_doc_base is None
+    gdt = torch.bfloat16 if bf16_out else torch.float32
+    dq = torch.empty(b * nq_pad, dim, dtype=gdt, device=dev) if need_dq else None
+    dd = torch.empty(bank_flat.shape[0], dim, dtype=gdt, device=dev) if (need_dd and dd_doc_base is None) else None
     if not (need_dq or need_dd):
         return None, None
     a = _lib.MaxSimBwdArgs()
     a.flags = _lib.CPB_FLAG_CONTIGUOUS  # the banks of the losses are dense [C, L, D] tensors
+    if bf16_out:
+        a.flags |= _lib.CPB_FLAG_GRAD_BF16
     a.d_grad_scores, a.d_grad_out = g.data_ptr(), go.data_ptr()
     if smooth_tau > 0:
         a.d_lse, a.smooth_tau = aux.data_ptr(), float(smooth_tau)
@@ -165,8 +170,9 @@ class _InBatchLossFn(torch.autograd.Function):
         want_q, want_d = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         dim = q_flat.shape[1]  # padded embedding dim (128, or 192 / 256 / 320 for wide models)
         go = grad_out.detach().to(torch.float32).reshape(1).contiguous()
+        both_bf16 = (q_dtype == torch.bfloat16 or not want_q) and (d_dtype == torch.bfloat16 or not want_d)
         dq, dd = _maxsim_backward(g, go, aux, smooth_tau, nq_real, q_flat, b, nq_pad, d_flat, d_start, d_len, c, max_len,
-                                  want_q, want_d)
+                                  want_q, want_d, bf16_out=both_bf16)
         grad_q = grad_d = None
         if want_q:
             grad_q = dq.view(b, nq_pad, dim)[:, : q_shape[1], : q_shape[2]].to(q_dtype)

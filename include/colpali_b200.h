@@ -49,6 +49,9 @@ extern "C" {
 #define CPB_FLAG_CONTIGUOUS 2u /* the caller guarantees d_doc_start[j+1] == d_doc_start[j] + d_doc_len[j]
                                   for every j (documents stored back to back): tiles then run across
                                   document boundaries and no short per-document tail tiles are issued. */
+#define CPB_FLAG_GRAD_BF16 8u /* cpb_maxsim_bwd_launch (hard max, no peer scatter): d_dq / d_dd are bf16 buffers -- the
+                                 kernels round every gradient row once (round-to-nearest-even, the same value a cast of
+                                 the fp32 row gives) instead of leaving two cast kernels to the caller */
 #define CPB_FLAG_INDEPENDENT 4u /* this launch reads nothing that the previous kernel on the stream wrote
                                    (e.g. the next query batch against a resident bank): it may start
                                    while that kernel is still draining (programmatic dependent launch
@@ -221,8 +224,8 @@ typedef struct cpb_maxsim_bwd_args {
   const int32_t* d_doc_len;     /* [n_docs] (rows of the bank outside every document are zero-filled in dd) */
   int32_t n_docs;
   int32_t max_doc_len;          /* longest document */
-  float* d_dq;                  /* fp32 [n_queries * nq_pad, dim] out, or NULL to skip */
-  float* d_dd;                  /* fp32 [doc_rows, dim] out, or NULL to skip */
+  void* d_dq;                   /* fp32 (bf16 with CPB_FLAG_GRAD_BF16) [n_queries * nq_pad, dim] out, or NULL to skip */
+  void* d_dd;                   /* fp32 (bf16 with CPB_FLAG_GRAD_BF16) [doc_rows, dim] out, or NULL to skip */
   const uint64_t* d_dd_doc_base; /* or NULL.  Hard max only, multi-GPU exchange: device array [n_docs] of addresses of each
                                    document's [len, dim] fp32 gradient block in its OWNER rank's pre-zeroed accumulator
                                    (NVLink peer mapping); gradient rows are then ADDED there (red.global.add) instead of

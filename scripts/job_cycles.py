@@ -37,7 +37,30 @@ for n_d, docs in ((1030, d), (1024, d[:, :1024].contiguous())):
         }), flush=True)
 _lib.set_option("boundary_mode", 1)
 
-# ---- the training forward (argmax mode, generic epilogue walk) at cfg3: 64 queries x 64 left-padded documents --------
+# ---- the CTA-pair kernel (option pair=1) at cfg2: leader and peer CTAs apart ------------------------------------------
+_lib.set_option("pair", 1)
+_lib.set_option("debug_flags", 0x40000)
+try:
+    raw = cb.maxsim(qb, bank)
+    torch.cuda.synchronize()
+finally:
+    _lib.set_option("debug_flags", 0)
+    _lib.set_option("pair", 0)
+raw = raw.flatten().cpu()
+n_cta = 148
+cyc = raw[0:2 * n_cta:2]
+c = raw[512:512 + 8 * n_cta].view(n_cta, 8)
+for name, sel in (("leader", slice(0, n_cta, 2)), ("peer", slice(1, n_cta, 2))):
+    cc, cy = c[sel], cyc[sel]
+    jobs = cc[:, 7].clamp_min(1)
+    print(json.dumps({"mode": "pair, cfg2", "cta": name, "cycles_per_job_mean": float((cy / jobs).mean()),
+                      "issuer_wait_full_per_job": float((cc[:, 0] / jobs).mean()), "issuer_wait_tmem_per_job": float((cc[:, 1] / jobs).mean()),
+                      "epilogue_wait_per_job": float((cc[:, 2] / jobs).mean()),
+                      "hold_plain_per_job": float((cc[:, 3] / (jobs - cc[:, 6]).clamp_min(1)).mean()),
+                      "hold_boundary_per_job": float((cc[:, 5] / cc[:, 6].clamp_min(1)).mean())}), flush=True)
+
+# ---- the training forward (argmax mode) at cfg3: 64 queries x 64 left-padded documents; counters of warp 2 = epilogue
+# group 0, which folds query tile 0 of every document tile (half of the CTA's jobs) --------------------------------------
 q3, d3, _ = O.cfg3_inputs()
 qb3, bank3 = cb.QueryBlock(q3.to(dev), dev), cb.DocBank.from_passages(d3.to(dev), dev)
 _lib.set_option("debug_flags", 0x40000)
@@ -50,8 +73,11 @@ raw = raw.flatten().cpu()
 n_cta = 144
 cyc = raw[0:2 * n_cta:2]
 c = raw[512:512 + 8 * n_cta].view(n_cta, 8)
-jobs = c[:, 7].clamp_min(1)
-print(json.dumps({"mode": "argmax, cfg3", "ctas": int((c[:, 7] > 0).sum()), "jobs_per_cta": float(jobs.mean()),
-                  "cycles_per_job_mean": float((cyc / jobs).mean()), "hold_per_job": float((c[:, 3] / jobs).mean()),
-                  "blocked_in_wait_ld_per_job": float((c[:, 5] / jobs).mean()), "epilogue_wait_for_mma_per_job": float((c[:, 2] / jobs).mean()),
-                  "post_release_per_job": float((c[:, 4] / jobs).mean())}), flush=True)
+own = c[:, 7].clamp_min(1)
+print(json.dumps({"mode": "argmax, cfg3", "ctas": int((c[:, 7] > 0).sum()), "own_jobs_per_warp": float(own.mean()),
+                  "cta_cycles_mean": float(cyc.mean()), "cta_cycles_max": float(cyc.max()),
+                  "cycles_per_own_job": float((cyc / own).mean()),
+                  "hold_whole_tile_per_job": float((c[:, 3] / (own - c[:, 6]).clamp_min(1)).mean()),
+                  "hold_other_per_job": float((c[:, 5] / c[:, 6].clamp_min(1)).mean()), "other_jobs_share": float((c[:, 6] / own).mean()),
+                  "wait_for_mma_per_own_job": float((c[:, 2] / own).mean()),
+                  "post_release_per_own_job": float((c[:, 4] / own).mean())}), flush=True)

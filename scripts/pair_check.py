@@ -60,19 +60,22 @@ if what == "check":
 q, d = O.cfg2_inputs()
 qb, bank = cb.QueryBlock(q.to(dev), dev), cb.DocBank.from_passages(d.to(dev), dev)
 FLOPS = 2.0 * 32 * 32 * 1000 * 1030 * 128
-BURST, ROUNDS = 25, 30
-times = {0: [], 1: []}
+BURST, ROUNDS = 25, 24
+VARIANTS = [dict(pair=pr, early_spin=sp, mma_split=ms) for pr in (0, 1) for sp in (1 << 30, 512, 0) for ms in (6, 4)]
+VARIANTS += [dict(pair=1, early_spin=1 << 30, mma_split=7), dict(pair=1, early_spin=1 << 30, mma_split=2)]
+times = [[] for _ in VARIANTS]
 for r in range(ROUNDS):
-    for pair in (0, 1):
-        _lib.set_option("pair", pair)
+    for i, v in enumerate(VARIANTS):
+        for k, x in v.items(): _lib.set_option(k, x)
         for _ in range(3): cb.maxsim(qb, bank, independent=True)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(BURST): cb.maxsim(qb, bank, independent=True)
         e1.record(); torch.cuda.synchronize()
-        times[pair].append(e0.elapsed_time(e1) / BURST)
-for pair in (0, 1):
-    t = times[pair]
-    print(json.dumps({"pair": pair, "median_ms": statistics.median(t), "min_ms": min(t),
-                      "median_pflops": FLOPS / statistics.median(t) / 1e12,
-                      "median_ratio_to_single": statistics.median(a / b for a, b in zip(t, times[0]))}), flush=True)
+        times[i].append(e0.elapsed_time(e1) / BURST)
+for i, v in enumerate(VARIANTS):
+    t = times[i]
+    print(json.dumps({**v, "median_ms": round(statistics.median(t), 5), "min_ms": round(min(t), 5),
+                      "median_pflops": round(FLOPS / statistics.median(t) / 1e12, 4),
+                      "median_ratio_to_first": round(statistics.median(a / b for a, b in zip(t, times[0])), 4)}), flush=True)
+_lib.set_option("pair", 0); _lib.set_option("early_spin", 512); _lib.set_option("mma_split", 6)

@@ -290,3 +290,24 @@ def test_wide_dim320_losses_against_reference_golden(name, make):
     real_q, real_d = q.abs().sum(-1) > 0, d.abs().sum(-1) > 0
     assert torch.allclose(dq[real_q], torch.from_numpy(g[f"l_{name}_dq"])[real_q], rtol=1e-4, atol=2e-6)
     assert torch.allclose(dd[real_d], torch.from_numpy(g[f"l_{name}_dd"])[real_d], rtol=1e-4, atol=2e-6)
+
+
+def test_bf16_gradient_rows_are_the_cast_of_the_fp32_rows():
+    """CPB_FLAG_GRAD_BF16: the backward kernels round each gradient row themselves; bit-identical to casting the fp32 rows."""
+    from colpali_b200 import losses as L
+
+    torch.manual_seed(5)
+    q = torch.randn(6, 20, 128).bfloat16()
+    d = torch.randn(6, 300, 128).bfloat16()
+    d[1, :40] = 0
+    grads = {}
+    orig = L._maxsim_backward
+    try:
+        for bf16 in (False, True):
+            L._maxsim_backward = lambda *a, _o=orig, _b=bf16, **k: _o(*a, **{**k, "bf16_out": _b})
+            _, dq, dd = _run(cb.ColbertLoss(), q, d)
+            grads[bf16] = (dq, dd)
+    finally:
+        L._maxsim_backward = orig
+    assert grads[True][0].dtype == torch.bfloat16
+    assert torch.equal(grads[True][0], grads[False][0]) and torch.equal(grads[True][1], grads[False][1])
