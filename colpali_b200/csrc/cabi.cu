@@ -48,7 +48,7 @@ std::atomic<int> g_opt_balanced{1};
 std::atomic<int> g_opt_pdl{1};
 std::atomic<int> g_opt_boundary_mode{1};
 std::atomic<int> g_opt_pair{0};  // CTA-pair MMAs (maxsim_pair_sm100.cu) where the shape allows
-std::atomic<int> g_opt_mma_split{6}, g_opt_early_spin{512};  // MMA issuer pacing (MaxSimParams::mma_split / early_spin)
+std::atomic<int> g_opt_mma_split{6}, g_opt_early_spin{0};  // MMA issuer pacing (MaxSimParams::mma_split / early_spin)
 std::atomic<int> g_opt_wait_timeout_ms{120000};
 std::mutex g_cache_mu;  // guards the device-property / occupancy caches below
 

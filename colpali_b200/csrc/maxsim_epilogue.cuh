@@ -254,7 +254,7 @@ __device__ __forceinline__ void multimem_st_f32(uint64_t mc_addr, float x) {
 template <int R, int kMode, bool kPair = false, int kGroups = 1>
 __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const CtaSlice& sl, uint32_t tmem_base,
                                                 uint64_t* tmem_full, uint64_t* tmem_empty, int warp, int lane,
-                                                uint8_t* bc_smem = nullptr) {
+                                                uint8_t* bc_smem = nullptr, int grp = 0) {
   constexpr int kTileM = kEpiTileM;
   constexpr int kTileN = kEpiTileN;
   constexpr bool kArgmax = (kMode == kModeArgmax);
@@ -262,7 +262,6 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
   const int g = sl.g, part = sl.part, r_cnt = sl.r_cnt, d0 = sl.d0, d1 = sl.d1, bal_r0 = sl.bal_r0, bal_r1 = sl.bal_r1;
   static_assert(kGroups == 1 || (kGroups == 2 && R == 2), "two epilogue warp groups = one per resident query tile");
   const int quad = warp & 3;  // TMEM lane quadrant this warp may read
-  const int grp = (warp - 2) >> 2;  // which query tile this warp folds when kGroups == 2
   const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
   const bool round_ref = (p.flags & CPB_FLAG_ROUND_BF16) != 0;
   const bool skip = (p.flags & CPB_DBG_SKIP_EPILOGUE) != 0;
@@ -318,8 +317,13 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
   const uint32_t bc_sw = static_cast<uint32_t>(lane & 7) << 4;
   uint32_t job = 0;
   const bool dbg = (p.flags & CPB_DBG_CLOCKS) != 0;
-  long long e_wait = 0, e_hold = 0, e_post = 0, e_hold2 = 0, e_genwait = 0;
-  int n_path2 = 0, n_own = 0;
+  // debug cycle counters (CPB_DBG_CLOCKS) live in shared memory: in registers they were spilled, and re-loaded on every
+  // job whether the flag was set or not.  Only the warp whose counters are reported (group 0, quadrant 2) keeps them.
+  __shared__ int s_dbg[6];  // wait for MMA, hold (fast paths), after release, hold (other paths), other jobs, own jobs
+  const bool dbg_me = dbg && grp == 0 && quad == 2 && lane == 0;
+  if (dbg_me) {
+    for (int i = 0; i < 6; ++i) s_dbg[i] = 0;
+  }
 
   // ---- balanced mode: which document contains the first row of my partition, and is it cut? ----------------
   int first_doc = d0;
@@ -694,9 +698,7 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
             tmem_ld_x32(taddr, va);
 #pragma unroll 1
             for (int cb = 0; cb < n_valid; cb += 64) {
-              const long long tw = dbg ? clock64() : 0;
               tmem_ld_wait();
-              if (dbg) e_genwait += clock64() - tw;
               reg_fence32(va);
               const bool has_b = cb + 32 < n_valid;
               if (has_b) tmem_ld_x32(taddr + cb + 32, vb);
@@ -712,12 +714,14 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
           }
           if (dbg) {
             const long long t3 = clock64();
-            e_wait += t1 - t0;
-            e_post += t3 - t2;
+            if (dbg_me) {
+            s_dbg[0] += static_cast<int>(t1 - t0);
+            s_dbg[2] += static_cast<int>(t3 - t2);
             // max mode: boundary tiles apart; argmax / smooth: everything that is not a whole-tile fast path apart
             const bool other = (kMode == kModeMax) ? (path == 2) : (path != 1);
-            if (other) { e_hold2 += t2 - t1; ++n_path2; } else { e_hold += t2 - t1; }
-            ++n_own;
+            if (other) { s_dbg[3] += static_cast<int>(t2 - t1); ++s_dbg[4]; } else { s_dbg[1] += static_cast<int>(t2 - t1); }
+            ++s_dbg[5];
+            }
           }
           if (r == 0) {
             m[0] = mm;
@@ -760,14 +764,14 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
     }
     d = run.e;
   }
-  if (dbg && warp == 2 && lane == 0) {  // epilogue: blocked on MMA / holding the accumulator / after release
+  if (dbg && grp == 0 && quad == 2 && lane == 0) {  // epilogue: blocked on MMA / holding the accumulator / after release
     float* o = p.scores + 512 + 8 * blockIdx.x;
-    o[2] = static_cast<float>(e_wait);
-    o[3] = static_cast<float>(e_hold);
-    o[4] = static_cast<float>(e_post);
-    o[5] = static_cast<float>(e_hold2);
-    o[6] = static_cast<float>(n_path2);
-    o[7] = static_cast<float>(n_own);  // jobs THIS warp folded (half of the CTA's with two epilogue groups)
+    o[2] = static_cast<float>(s_dbg[0]);
+    o[3] = static_cast<float>(s_dbg[1]);
+    o[4] = static_cast<float>(s_dbg[2]);
+    o[5] = static_cast<float>(s_dbg[3]);
+    o[6] = static_cast<float>(s_dbg[4]);
+    o[7] = static_cast<float>(s_dbg[5]);  // jobs THIS warp folded (half of the CTA's with two epilogue groups)
   }
 }
 

@@ -48,8 +48,14 @@ constexpr int kDHalfPanelBytes = kHalfRows * 64 * 2; // 16 KiB
 // resident query tile, in the modes whose epilogue is the bottleneck)
 template <int R, int kMode>
 constexpr int kEpiGroups = (R == 2 && kMode != kModeMax) ? 2 : 1;
+// With two groups the CTA is three warpgroups: {TMA, MMA, idle, idle} gives registers away (setmaxnreg) and each
+// epilogue group is a warpgroup of its own with 224 registers per thread -- at a flat 168 (65536 / 384 threads) the
+// epilogue spilled, and local memory has almost no L1 behind it in a CTA that takes 224 KiB of shared memory.
 template <int R, int kMode>
-constexpr int kThreads = 64 + 128 * kEpiGroups<R, kMode>;
+constexpr int kEpiWarp0 = (kEpiGroups<R, kMode> == 2) ? 4 : 2;  // first epilogue warp
+template <int R, int kMode>
+constexpr int kThreads = 32 * (kEpiWarp0<R, kMode> + 4 * kEpiGroups<R, kMode>);
+constexpr int kRegsLaunch = 168, kRegsProducer = 56, kRegsEpilogue = 224;  // 128 x 56 + 256 x 224 = 384 x 168
 constexpr uint32_t kTmemCols = 512;
 #ifndef CPB_PAIR_SPLIT
 #define CPB_PAIR_SPLIT 6
@@ -137,6 +143,11 @@ maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   const long long dbg_c0 = clock64();
   const uint64_t dbg_t0 = global_timer_ns();
 
+  // Register budgets follow the roles (see kEpiWarp0): set at the top of each branch so that the allocation is
+  // unambiguous along every path, and restored to the launch value before the paths join again.
+  constexpr bool kRealloc = kEpiGroups<R, kMode> == 2;
+  if (warp < kEpiWarp0<R, kMode>) {
+  if constexpr (kRealloc) setmaxnreg_dec<kRegsProducer>();
   if (warp == 0) {
     // ================================ TMA producer (both CTAs) ==============================
     if (lane == 0) {
@@ -286,11 +297,15 @@ maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         p.scores[512 + 8 * blockIdx.x + 1] = static_cast<float>(w_tmem);
       }
     }
+  }
+  if constexpr (kRealloc) setmaxnreg_inc<kRegsLaunch>();
   } else {
     // ================================ epilogue (maxsim_epilogue.cuh) ==========================
+    if constexpr (kRealloc) setmaxnreg_inc<kRegsEpilogue>();
     const CtaSlice sl{g, part, r_cnt, d0, d1, bal_r0, bal_r1};
     maxsim_epilogue<R, kMode, true, kEpiGroups<R, kMode>>(p, sl, tmem_base, tmem_full, tmem_empty, warp, lane,
-                                                          smem + L::kBcOff);
+                                                          smem + L::kBcOff, (warp - kEpiWarp0<R, kMode>) >> 2);
+    if constexpr (kRealloc) setmaxnreg_dec<kRegsLaunch>();
   }
 
   // ---- teardown ---------------------------------------------------------------------------

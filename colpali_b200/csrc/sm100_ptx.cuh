@@ -273,6 +273,18 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mas
       : "memory");
 }
 
+// Register reallocation between the warpgroups (4 warps, executed by all of them) of a running CTA: the producer /
+// issuer warpgroup hands registers to the epilogue warpgroups.  Counts are multiples of 8; the sum over the CTA's
+// threads must not exceed what the launch allocated (threads x the kernel's compile-time register count).
+template <int kRegs>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs));
+}
+template <int kRegs>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs));
+}
+
 // ----------------------------------------------------------------------------------------
 // thread-block clusters
 // ----------------------------------------------------------------------------------------

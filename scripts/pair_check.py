@@ -78,4 +78,4 @@ for i, v in enumerate(VARIANTS):
     print(json.dumps({**v, "median_ms": round(statistics.median(t), 5), "min_ms": round(min(t), 5),
                       "median_pflops": round(FLOPS / statistics.median(t) / 1e12, 4),
                       "median_ratio_to_first": round(statistics.median(a / b for a, b in zip(t, times[0])), 4)}), flush=True)
-_lib.set_option("pair", 0); _lib.set_option("early_spin", 512); _lib.set_option("mma_split", 6)
+_lib.set_option("pair", 0); _lib.set_option("early_spin", 0); _lib.set_option("mma_split", 6)
