@@ -73,7 +73,6 @@ int cpb_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
  *   "pair"            0 (default) / 1: CTA-pair MMAs (tcgen05.mma.cta_group::2, maxsim_pair_sm100.cu) where the shape
  *                     allows (dim 128, contiguous bank, query-tile count a multiple of 2 x qtiles_per_cta); bit-identical
  *                     results, measured 9-27 % slower than the default kernel
- *   "mma_split"       1..8 (default 6): K-steps of a job issued before the issuer looks at the next job's barriers
  *   "early_spin"      cycles (default 0 = one probe) the issuer polls those barriers before it finishes the current
  *                     job first; a huge value restores round 1's blocking wait
  *   "head_cluster"    0 = auto, 1 / 2: CTAs sharing the projection weight block (wide head)
