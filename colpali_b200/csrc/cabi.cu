@@ -48,7 +48,7 @@ std::atomic<int> g_opt_balanced{1};
 std::atomic<int> g_opt_pdl{1};
 std::atomic<int> g_opt_boundary_mode{1};
 std::atomic<int> g_opt_pair{0};  // CTA-pair MMAs (maxsim_pair_sm100.cu) where the shape allows
-std::atomic<int> g_opt_mma_split{6}, g_opt_early_spin{0};  // MMA issuer pacing (MaxSimParams::mma_split / early_spin)
+std::atomic<int> g_opt_early_spin{0};  // MMA issuer pacing (MaxSimParams::early_spin)
 std::atomic<int> g_opt_wait_timeout_ms{120000};
 std::mutex g_cache_mu;  // guards the device-property / occupancy caches below
 
@@ -223,9 +223,6 @@ int cpb_set_option(const char* name, int value) {
   } else if (!strcmp(name, "boundary_mode")) {
     if (value < 0 || value > 1) return fail(CPB_E_INVALID, "boundary_mode must be 0 or 1");
     g_opt_boundary_mode = value;
-  } else if (!strcmp(name, "mma_split")) {
-    if (value < 1 || value > 8) return fail(CPB_E_INVALID, "mma_split must be 1..8");
-    g_opt_mma_split = value;
   } else if (!strcmp(name, "early_spin")) {
     if (value < 0) return fail(CPB_E_INVALID, "early_spin must be >= 0");
     g_opt_early_spin = value;
@@ -356,7 +353,6 @@ int cpb_maxsim_launch(cpb_maxsim_args* a) {
   p.boundary_mode = g_opt_boundary_mode.load();
   p.flags = (flags & 0xffffu) | g_opt_debug_flags.load();
   p.dbg_delay = g_opt_dbg_delay.load();
-  p.mma_split = g_opt_mma_split.load();
   p.early_spin = g_opt_early_spin.load();
 
   const int opt_cluster = g_opt_cluster.load(), opt_r = g_opt_qtiles_per_cta.load();

@@ -54,8 +54,8 @@ __device__ __forceinline__ void store_grad_row(float* base, int out_bf16, int64_
 // documents are fetched by the 32 lanes at once and broadcast by shuffles, and four row gathers are in flight before the
 // first is consumed: the loop is a chain of dependent 256-byte loads otherwise (C = 64..512 iterations).
 template <int P>
-__global__ void __launch_bounds__(256) maxsim_bwd_dq_kernel(const BwdParams p) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+__device__ __forceinline__ void maxsim_bwd_dq_body(const BwdParams& p, int block) {
+  const int row = block * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= p.q_rows) return;
   constexpr int kDim = 64 * P;
@@ -130,13 +130,12 @@ constexpr int kDdTokens = 64;
 constexpr int kDdThreads = 256;
 
 template <int P>
-__global__ void __launch_bounds__(kDdThreads) maxsim_bwd_dd_kernel(const BwdParams p) {
+__device__ __forceinline__ void maxsim_bwd_dd_body(const BwdParams& p, int c, int token_block) {
   extern __shared__ int s_list[];  // [q_rows] query rows grouped by token
   __shared__ int s_cnt[kDdTokens];
   __shared__ int s_off[kDdTokens + 1];
   constexpr int kDim = 64 * P;
-  const int c = blockIdx.x;
-  const int t0 = blockIdx.y * kDdTokens;
+  const int t0 = token_block * kDdTokens;
   const int len = __ldg(p.doc_len + c);
   if (t0 >= len) return;
   const int nt = min(kDdTokens, len - t0);
@@ -241,31 +240,35 @@ __global__ void __launch_bounds__(kDdThreads) maxsim_bwd_dd_kernel(const BwdPara
   }
 }
 
+// ONE launch for both gradients: blocks [0, n_dd) are dD blocks (document = block % C, token block = block / C), the
+// rest dQ blocks.  The two are independent chains of small dependent loads, so co-resident they overlap instead of
+// running back to back (cfg3: 38 + 19 us as two launches); the longer-running dD blocks are scheduled first.
+template <int P>
+__global__ void __launch_bounds__(kDdThreads) maxsim_bwd_kernel(const BwdParams p, int n_dd) {
+  const int block = static_cast<int>(blockIdx.x);
+  if (block < n_dd) maxsim_bwd_dd_body<P>(p, block % p.C, block / p.C);
+  else maxsim_bwd_dq_body<P>(p, block - n_dd);
+}
+
 template <int P>
 static cudaError_t maxsim_bwd_launch_p(const BwdParams& p, cudaStream_t stream) {
-  const int wpb = 8;
-  if (p.dq != nullptr) {
-    maxsim_bwd_dq_kernel<P><<<(p.q_rows + wpb - 1) / wpb, wpb * 32, 0, stream>>>(p);
-    cudaError_t e = cudaGetLastError();
+  const int wpb = kDdThreads / 32;
+  const bool want_dd = p.dd != nullptr || p.dd_doc_base != nullptr;
+  const int n_dq = (p.dq != nullptr) ? (p.q_rows + wpb - 1) / wpb : 0;
+  const int n_dd = want_dd ? p.C * ((p.max_doc_len + kDdTokens - 1) / kDdTokens) : 0;
+  if (n_dq + n_dd == 0) return cudaSuccess;
+  const size_t smem = want_dd ? static_cast<size_t>(p.q_rows) * sizeof(int) : 0;
+  auto kern = maxsim_bwd_kernel<P>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
   }
-  if (p.dd != nullptr || p.dd_doc_base != nullptr) {
-    const size_t smem = static_cast<size_t>(p.q_rows) * sizeof(int);
-    auto kern = maxsim_bwd_dd_kernel<P>;
-    if (smem > 48 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-      if (e != cudaSuccess) return e;
-    }
-    if (!p.contiguous && p.dd_doc_base == nullptr) {  // rows between documents belong to nobody: zero them
-      cudaError_t e = cudaMemsetAsync(p.dd, 0, static_cast<size_t>(p.doc_rows) * 64 * P * (p.out_bf16 ? 2 : 4), stream);
-      if (e != cudaSuccess) return e;
-    }
-    const dim3 grid(static_cast<unsigned>(p.C), static_cast<unsigned>((p.max_doc_len + kDdTokens - 1) / kDdTokens));
-    kern<<<grid, kDdThreads, smem, stream>>>(p);
-    cudaError_t e = cudaGetLastError();
+  if (want_dd && !p.contiguous && p.dd_doc_base == nullptr) {  // rows between documents belong to nobody: zero them
+    cudaError_t e = cudaMemsetAsync(p.dd, 0, static_cast<size_t>(p.doc_rows) * 64 * P * (p.out_bf16 ? 2 : 4), stream);
     if (e != cudaSuccess) return e;
   }
-  return cudaSuccess;
+  kern<<<static_cast<unsigned>(n_dd + n_dq), kDdThreads, smem, stream>>>(p, n_dd);
+  return cudaGetLastError();
 }
 
 cudaError_t maxsim_bwd_launch(const BwdParams& p, cudaStream_t stream) {

@@ -64,7 +64,6 @@ struct MaxSimParams {
   float* lse;                   // [n_docs, q_rows] per-(document, query row) smooth maximum, or nullptr
   int pdl;                      // programmatic dependent launch: 0 off, 1 wait before the first global access, 2 never wait
   int boundary_mode;            // epilogue path for tiles holding one document boundary (0 re-read, 1 shifted chunks)
-  int mma_split;   // K-steps of a job issued before the issuer looks at the next job's barriers (1..8)
   int early_spin;  // cycles the issuer probes those barriers before finishing the current job first
   int dbg_delay;   // profiling only: cycles the epilogue holds an unread accumulator in CPB_DBG_SKIP_EPILOGUE mode
 };

@@ -325,7 +325,9 @@ maxsim_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         }
       }
       const long long kEarlySpin = p.early_spin;
-      const int kSplit = p.mma_split;  // K-steps issued before the next job's waits
+      // K-steps issued before the next job's waits.  Compile-time: with run-time bounds every issue() became eight
+      // predicated UTCHMMAs and the MMA stream ran 40 % slower (measured, profiles/r02_notes.md).
+      constexpr int kSplit = 6;
       advance(cur);
       if (cur.valid) prepare(cur);
       while (cur.valid) {

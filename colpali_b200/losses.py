@@ -115,7 +115,8 @@ def _maxsim_backward(g, go, aux, smooth_tau, nq_real, q_flat, b, nq_pad, bank_fl
         a.stream = torch.cuda.current_stream(dev).cuda_stream
         rc = _lib.load().cpb_maxsim_bwd_launch(ctypes.byref(a))
     _lib.check(rc, "cpb_maxsim_bwd_launch")
-    _lib.count_launches(int(need_dq) + int(need_dd))
+    # hard max: dQ and dD blocks share one launch; smooth max: one recompute kernel each
+    _lib.count_launches(int(need_dq) + int(need_dd) if smooth_tau > 0 else 1)
     return dq, dd
 
 

@@ -70,6 +70,11 @@ int cpb_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
  *   "balanced"        1 (default) / 0: allow tile-balanced partitions
  *   "pdl"             1 (default) / 0: programmatic dependent launch of the MaxSim kernels
  *   "boundary_mode"   1 (default) / 0: shifted-chunk epilogue for tiles that hold a document boundary
+ *   "pair"            0 (default) / 1: CTA-pair MMAs (tcgen05.mma.cta_group::2, maxsim_pair_sm100.cu) where the shape
+ *                     allows (dim 128, contiguous bank, query-tile count a multiple of 2 x qtiles_per_cta); bit-identical
+ *                     results, measured 9-27 % slower than the default kernel
+ *   "early_spin"      cycles (default 0 = one probe) the issuer polls those barriers before it finishes the current
+ *                     job first; a huge value restores round 1's blocking wait
  *   "head_cluster"    0 = auto, 1 / 2: CTAs sharing the projection weight block (wide head)
  *   "wait_timeout_ms" time-out of cpb_wait_flags (default 120000)
  *   "debug_delay", "debug_flags"  profiling only

@@ -61,8 +61,7 @@ q, d = O.cfg2_inputs()
 qb, bank = cb.QueryBlock(q.to(dev), dev), cb.DocBank.from_passages(d.to(dev), dev)
 FLOPS = 2.0 * 32 * 32 * 1000 * 1030 * 128
 BURST, ROUNDS = 25, 24
-VARIANTS = [dict(pair=pr, early_spin=sp, mma_split=ms) for pr in (0, 1) for sp in (1 << 30, 512, 0) for ms in (6, 4)]
-VARIANTS += [dict(pair=1, early_spin=1 << 30, mma_split=7), dict(pair=1, early_spin=1 << 30, mma_split=2)]
+VARIANTS = [dict(pair=pr, early_spin=sp) for pr in (0, 1) for sp in (1 << 30, 512, 128, 0)]
 times = [[] for _ in VARIANTS]
 for r in range(ROUNDS):
     for i, v in enumerate(VARIANTS):
@@ -78,4 +77,4 @@ for i, v in enumerate(VARIANTS):
     print(json.dumps({**v, "median_ms": round(statistics.median(t), 5), "min_ms": round(min(t), 5),
                       "median_pflops": round(FLOPS / statistics.median(t) / 1e12, 4),
                       "median_ratio_to_first": round(statistics.median(a / b for a, b in zip(t, times[0])), 4)}), flush=True)
-_lib.set_option("pair", 0); _lib.set_option("early_spin", 0); _lib.set_option("mma_split", 6)
+_lib.set_option("pair", 0); _lib.set_option("early_spin", 0)
