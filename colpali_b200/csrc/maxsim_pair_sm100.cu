@@ -300,7 +300,13 @@ maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       }
     }
   }
-  if constexpr (kRealloc) setmaxnreg_inc<kRegsLaunch>();
+  if constexpr (kRealloc) {
+    // All four warps take their registers back TOGETHER, after the TMA and MMA loops: the two idle warps get here at
+    // once, and if they grew back to 168 on their own (setmaxnreg is not a barrier) they would take half of what the
+    // epilogue warpgroups are still waiting for in their setmaxnreg.inc -- a dead CTA about once in 300 launches.
+    named_bar_sync(1, 128);
+    setmaxnreg_inc<kRegsLaunch>();
+  }
   } else {
     // ================================ epilogue (maxsim_epilogue.cuh) ==========================
     if constexpr (kRealloc) setmaxnreg_inc<kRegsEpilogue>();

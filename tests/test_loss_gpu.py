@@ -311,3 +311,20 @@ def test_bf16_gradient_rows_are_the_cast_of_the_fp32_rows():
         L._maxsim_backward = orig
     assert grads[True][0].dtype == torch.bfloat16
     assert torch.equal(grads[True][0], grads[False][0]) and torch.equal(grads[True][1], grads[False][1])
+
+
+def test_back_to_back_training_forwards_do_not_deadlock():
+    """400 argmax-mode forwards without host synchronisation (a training loop): the epilogue warpgroups of every CTA must
+    get their registers (setmaxnreg) in every launch -- a race there killed one launch in a few hundred."""
+    q, d, _ = O.cfg3_inputs()
+    q, d = q.to(DEV).requires_grad_(True), d.to(DEV).requires_grad_(True)
+    mod = cb.ColbertLoss()
+    losses = [mod(q, d).detach() for _ in range(400)]
+    torch.cuda.synchronize()
+    assert all(torch.equal(x, losses[0]) for x in losses)
+    q.grad = None
+    d.grad = None
+    for _ in range(100):
+        mod(q, d).backward()
+    torch.cuda.synchronize()
+    assert torch.isfinite(q.grad).all() and torch.isfinite(d.grad).all()
