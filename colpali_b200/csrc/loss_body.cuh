@@ -35,6 +35,175 @@ struct Top {
 };
 __device__ __forceinline__ bool better(const Top& a, const Top& b) { return a.v > b.v || (a.v == b.v && a.i < b.i); }
 
+// The row of scores a warp works on: column c = lane + 32 j.  Up to 32 * kLossCols columns are fetched from L2 ONCE
+// into registers (kCached) -- every pass over the row was a dependent L2 round trip before, five per row, and the
+// last CTA of the fused forward spent ~25 us in them at cfg3 (B = C = 64); wider rows are re-read pass by pass.
+constexpr int kLossCols = 16;
+template <bool kCached, typename F>
+__device__ __forceinline__ void loss_for_cols(int C, int lane, const float (&sv)[kLossCols], const float* row, float inv,
+                                              F&& fn) {
+  if constexpr (kCached) {
+#pragma unroll
+    for (int j = 0; j < kLossCols; ++j) {
+      const int c = lane + 32 * j;
+      if (c < C) fn(c, sv[j]);
+    }
+  } else {
+    for (int c = lane; c < C; c += 32) fn(c, __ldcg(row + c) * inv);
+  }
+}
+
+// one query row b: loss contribution (returned, warp-uniform), gradients written, running min / max updated
+template <bool kCached>
+__device__ __forceinline__ float colbert_loss_row(const LossParams& p, int b, int lane, float& mn, float& mx) {
+  const bool has_neg = p.neg_scores != nullptr;
+  const float w_ib = has_neg ? p.in_batch_weight : 1.f;     // late_interaction_losses.py:248-250 / :394-396
+  const float w_out = has_neg ? 1.f - p.in_batch_weight : 0.f;
+  const float* row = p.scores + static_cast<int64_t>(b) * p.C;
+  const int pidx = b + p.offset;                              // :33-38
+  // all loads of the row first (scores, the positive, column 0 of the query's tokens), then the arithmetic
+  float sv[kLossCols];
+  if constexpr (kCached) {
+#pragma unroll
+    for (int j = 0; j < kLossCols; ++j) {
+      const int c = lane + 32 * j;
+      sv[j] = (c < p.C) ? __ldcg(row + c) : 0.f;
+    }
+  }
+  const float pos_raw = __ldcg(row + pidx);
+  // lengths = (q[:, :, 0] != 0).sum(1)                       late_interaction_losses.py:152
+  float cnt = 0.f;
+  for (int n = lane; n < p.nq_pad; n += 32)
+    cnt += (__bfloat162float(p.q[(static_cast<int64_t>(b) * p.nq_pad + n) * p.q_dim]) != 0.f) ? 1.f : 0.f;
+  cnt = warp_sum_f(cnt);
+  const float inv = p.normalize ? 1.f / cnt : 1.f;          // :155-156 -> :59-62
+  if constexpr (kCached) {
+#pragma unroll
+    for (int j = 0; j < kLossCols; ++j) sv[j] *= inv;
+  }
+  const float pos = pos_raw * inv;
+  const float thr = p.filter_threshold * pos;                 // :101-104
+  const float invT = 1.f / p.temperature;
+  const float invB = w_ib / static_cast<float>(p.B);
+  float loss = 0.f;
+
+  // filtered score of column c (normalised score s) and the factor it was multiplied by      (:105-107)
+  auto filtered = [&](int c, float s, float& f) {
+    f = (p.filter && c != pidx && s > thr) ? p.filter_factor : 1.f;
+    return s * f;
+  };
+  auto for_cols = [&](auto&& fn) { loss_for_cols<kCached>(p.C, lane, sv, row, inv, fn); };
+
+  if (p.mode == 0) {
+    // cross entropy of scores / T against pidx                (:164)
+    float m = -INFINITY;
+    for_cols([&](int c, float s) {
+      float f;
+      mn = fminf(mn, s);
+      mx = fmaxf(mx, s);
+      m = fmaxf(m, filtered(c, s, f) * invT);
+    });
+    m = warp_max_f(m);
+    float se = 0.f;
+    for_cols([&](int c, float s) {
+      float f;
+      se += __expf(filtered(c, s, f) * invT - m);
+    });
+    se = warp_sum_f(se);
+    const float lse = m + __logf(se);
+    loss += w_ib * (lse - pos * invT);  // the positive column is never filtered
+    if (p.grad != nullptr) {
+      float* g = p.grad + static_cast<int64_t>(b) * p.C;
+      for_cols([&](int c, float s) {
+        float f;
+        const float sm = __expf(filtered(c, s, f) * invT - lse);
+        g[c] = (sm - (c == pidx ? 1.f : 0.f)) * invT * f * inv * invB;
+      });
+    }
+  } else if (p.mode == 1) {
+    // pos = diagonal(offset); top-2 of the row; neg = top1 == pos ? top2 : top1      (:309-311)
+    Top t1{-INFINITY, 0x7fffffff}, t2{-INFINITY, 0x7fffffff};
+    for_cols([&](int c, float s) {
+      float f;
+      const Top x{filtered(c, s, f), c};
+      mn = fminf(mn, s);
+      mx = fmaxf(mx, s);
+      if (better(x, t1)) {
+        t2 = t1;
+        t1 = x;
+      } else if (better(x, t2)) {
+        t2 = x;
+      }
+    });
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      Top a1{__shfl_xor_sync(0xffffffffu, t1.v, o), __shfl_xor_sync(0xffffffffu, t1.i, o)};
+      Top a2{__shfl_xor_sync(0xffffffffu, t2.v, o), __shfl_xor_sync(0xffffffffu, t2.i, o)};
+      // merge two sorted pairs
+      if (better(a1, t1)) {
+        t2 = better(t1, a2) ? t1 : a2;
+        t1 = a1;
+      } else {
+        t2 = better(a1, t2) ? a1 : t2;
+      }
+    }
+    const Top neg = (t1.v == pos) ? t2 : t1;
+    const float x = (neg.v - pos) * invT;
+    loss += w_ib * (fmaxf(x, 0.f) + log1pf(__expf(-fabsf(x))));   // softplus           (:313)
+    if (p.grad != nullptr) {
+      const float sig = 1.f / (1.f + __expf(-x));
+      float* g = p.grad + static_cast<int64_t>(b) * p.C;
+      const int ni = neg.i < p.C ? neg.i : pidx;
+      float fneg;
+      (void)filtered(ni, __ldcg(row + ni) * inv, fneg);
+      for_cols([&](int c, float) {
+        float v = 0.f;
+        if (c == neg.i) v += sig * invT * fneg * inv * invB;
+        if (c == pidx) v -= sig * invT * inv * invB;
+        g[c] = v;
+      });
+    }
+  } else {
+    // sigmoid loss: softplus(-s/T * m), m = +1 on the diagonal, -1 elsewhere; mean over B*B   (:452-465)
+    float* g = p.grad ? p.grad + static_cast<int64_t>(b) * p.C : nullptr;
+    const float invBB = invB / static_cast<float>(p.C);
+    float part = 0.f;  // per-lane partial sum, reduced below (the returned loss must stay warp-uniform)
+    for_cols([&](int c, float s0) {
+      float f;
+      const float s = filtered(c, s0, f);
+      mn = fminf(mn, s0);
+      mx = fmaxf(mx, s0);
+      const float msk = (c == b) ? 1.f : -1.f;
+      const float z = -s * invT * msk;
+      part += (fmaxf(z, 0.f) + log1pf(__expf(-fabsf(z)))) / static_cast<float>(p.C);
+      if (g) g[c] = -msk * invT * f * inv * invBB / (1.f + __expf(-z));
+    });
+    loss += warp_sum_f(part);
+  }
+
+  if (has_neg) {
+    // softplus((neg - pos) / T) over this query's own negatives, mean over B * n_neg          (:235-246, :381-392)
+    const float* nrow = p.neg_scores + static_cast<int64_t>(b) * p.B * p.n_neg;
+    float* gn = p.grad_neg ? p.grad_neg + static_cast<int64_t>(b) * p.B * p.n_neg : nullptr;
+    const float scale = w_out / (static_cast<float>(p.B) * static_cast<float>(p.n_neg));
+    float gpos = 0.f, part = 0.f;
+    for (int c = lane; c < p.B * p.n_neg; c += 32) {
+      float gv = 0.f;
+      if (c / p.n_neg == b) {
+        const float x = (__ldcg(nrow + c) * inv - pos) * invT;
+        part += (fmaxf(x, 0.f) + log1pf(__expf(-fabsf(x)))) * w_out / static_cast<float>(p.n_neg);
+        gv = scale * invT * inv / (1.f + __expf(-x));
+        gpos -= gv;
+      }
+      if (gn) gn[c] = gv;
+    }
+    gpos = warp_sum_f(gpos);
+    loss += warp_sum_f(part);
+    if (p.grad != nullptr && lane == (pidx & 31)) p.grad[static_cast<int64_t>(b) * p.C + pidx] += gpos;
+  }
+  return loss;
+}
+
 // Whole-CTA device function (every thread of the block must call it: it ends with a __syncthreads reduction).
 // Used by the stand-alone colbert_loss_kernel (loss_sm100.cu) and by the last CTA of the fused MaxSim kernels, which
 // read the score matrix other CTAs have just written (hence the L2 loads).
@@ -45,139 +214,10 @@ __device__ __forceinline__ void colbert_loss_body(const LossParams& p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nwarps = blockDim.x >> 5;
   float loss_acc = 0.f, mn = INFINITY, mx = -INFINITY;
-  const bool has_neg = p.neg_scores != nullptr;
-  const float w_ib = has_neg ? p.in_batch_weight : 1.f;     // late_interaction_losses.py:248-250 / :394-396
-  const float w_out = has_neg ? 1.f - p.in_batch_weight : 0.f;
-
-  for (int b = warp; b < p.B; b += nwarps) {
-    // lengths = (q[:, :, 0] != 0).sum(1)                       late_interaction_losses.py:152
-    float cnt = 0.f;
-    for (int n = lane; n < p.nq_pad; n += 32)
-      cnt += (__bfloat162float(p.q[(static_cast<int64_t>(b) * p.nq_pad + n) * p.q_dim]) != 0.f) ? 1.f : 0.f;
-    cnt = warp_sum_f(cnt);
-    const float inv = p.normalize ? 1.f / cnt : 1.f;          // :155-156 -> :59-62
-    const float* row = p.scores + static_cast<int64_t>(b) * p.C;
-    const int pidx = b + p.offset;                              // :33-38
-    const float pos = __ldcg(row + pidx) * inv;
-    const float thr = p.filter_threshold * pos;                 // :101-104
-    const float invT = 1.f / p.temperature;
-    const float invB = w_ib / static_cast<float>(p.B);
-
-    // filtered score of column c and the factor it was multiplied by      (:105-107)
-    auto filtered = [&](int c, float& f) {
-      float s = __ldcg(row + c) * inv;
-      f = (p.filter && c != pidx && s > thr) ? p.filter_factor : 1.f;
-      return s * f;
-    };
-
-    if (p.mode == 0) {
-      // cross entropy of scores / T against pidx                (:164)
-      float m = -INFINITY;
-      for (int c = lane; c < p.C; c += 32) {
-        float f;
-        const float s = filtered(c, f);
-        mn = fminf(mn, __ldcg(row + c) * inv);
-        mx = fmaxf(mx, __ldcg(row + c) * inv);
-        m = fmaxf(m, s * invT);
-      }
-      m = warp_max_f(m);
-      float se = 0.f;
-      for (int c = lane; c < p.C; c += 32) {
-        float f;
-        se += __expf(filtered(c, f) * invT - m);
-      }
-      se = warp_sum_f(se);
-      const float lse = m + __logf(se);
-      loss_acc += w_ib * (lse - pos * invT);  // the positive column is never filtered
-      if (p.grad != nullptr) {
-        float* g = p.grad + static_cast<int64_t>(b) * p.C;
-        for (int c = lane; c < p.C; c += 32) {
-          float f;
-          const float s = filtered(c, f);
-          const float sm = __expf(s * invT - lse);
-          g[c] = (sm - (c == pidx ? 1.f : 0.f)) * invT * f * inv * invB;
-        }
-      }
-    } else if (p.mode == 1) {
-      // pos = diagonal(offset); top-2 of the row; neg = top1 == pos ? top2 : top1      (:309-311)
-      Top t1{-INFINITY, 0x7fffffff}, t2{-INFINITY, 0x7fffffff};
-      for (int c = lane; c < p.C; c += 32) {
-        float f;
-        const Top x{filtered(c, f), c};
-        mn = fminf(mn, __ldcg(row + c) * inv);
-        mx = fmaxf(mx, __ldcg(row + c) * inv);
-        if (better(x, t1)) {
-          t2 = t1;
-          t1 = x;
-        } else if (better(x, t2)) {
-          t2 = x;
-        }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        Top a1{__shfl_xor_sync(0xffffffffu, t1.v, o), __shfl_xor_sync(0xffffffffu, t1.i, o)};
-        Top a2{__shfl_xor_sync(0xffffffffu, t2.v, o), __shfl_xor_sync(0xffffffffu, t2.i, o)};
-        // merge two sorted pairs
-        if (better(a1, t1)) {
-          t2 = better(t1, a2) ? t1 : a2;
-          t1 = a1;
-        } else {
-          t2 = better(a1, t2) ? a1 : t2;
-        }
-      }
-      const Top neg = (t1.v == pos) ? t2 : t1;
-      const float x = (neg.v - pos) * invT;
-      loss_acc += w_ib * (fmaxf(x, 0.f) + log1pf(__expf(-fabsf(x))));   // softplus           (:313)
-      if (p.grad != nullptr) {
-        const float sig = 1.f / (1.f + __expf(-x));
-        float* g = p.grad + static_cast<int64_t>(b) * p.C;
-        float fneg;
-        (void)filtered(neg.i < p.C ? neg.i : pidx, fneg);
-        for (int c = lane; c < p.C; c += 32) {
-          float v = 0.f;
-          if (c == neg.i) v += sig * invT * fneg * inv * invB;
-          if (c == pidx) v -= sig * invT * inv * invB;
-          g[c] = v;
-        }
-      }
-    } else {
-      // sigmoid loss: softplus(-s/T * m), m = +1 on the diagonal, -1 elsewhere; mean over B*B   (:452-465)
-      float* g = p.grad ? p.grad + static_cast<int64_t>(b) * p.C : nullptr;
-      const float invBB = invB / static_cast<float>(p.C);
-      float part = 0.f;  // per-lane partial sum, reduced below (loss_acc must stay warp-uniform)
-      for (int c = lane; c < p.C; c += 32) {
-        float f;
-        const float s = filtered(c, f);
-        mn = fminf(mn, __ldcg(row + c) * inv);
-        mx = fmaxf(mx, __ldcg(row + c) * inv);
-        const float msk = (c == b) ? 1.f : -1.f;
-        const float z = -s * invT * msk;
-        part += (fmaxf(z, 0.f) + log1pf(__expf(-fabsf(z)))) / static_cast<float>(p.C);
-        if (g) g[c] = -msk * invT * f * inv * invBB / (1.f + __expf(-z));
-      }
-      loss_acc += warp_sum_f(part);
-    }
-
-    if (has_neg) {
-      // softplus((neg - pos) / T) over this query's own negatives, mean over B * n_neg          (:235-246, :381-392)
-      const float* nrow = p.neg_scores + static_cast<int64_t>(b) * p.B * p.n_neg;
-      float* gn = p.grad_neg ? p.grad_neg + static_cast<int64_t>(b) * p.B * p.n_neg : nullptr;
-      const float scale = w_out / (static_cast<float>(p.B) * static_cast<float>(p.n_neg));
-      float gpos = 0.f, part = 0.f;
-      for (int c = lane; c < p.B * p.n_neg; c += 32) {
-        float gv = 0.f;
-        if (c / p.n_neg == b) {
-          const float x = (__ldcg(nrow + c) * inv - pos) * invT;
-          part += (fmaxf(x, 0.f) + log1pf(__expf(-fabsf(x)))) * w_out / static_cast<float>(p.n_neg);
-          gv = scale * invT * inv / (1.f + __expf(-x));
-          gpos -= gv;
-        }
-        if (gn) gn[c] = gv;
-      }
-      gpos = warp_sum_f(gpos);
-      loss_acc += warp_sum_f(part);
-      if (p.grad != nullptr && lane == (pidx & 31)) p.grad[static_cast<int64_t>(b) * p.C + pidx] += gpos;
-    }
+  if (p.C <= 32 * kLossCols) {
+    for (int b = warp; b < p.B; b += nwarps) loss_acc += colbert_loss_row<true>(p, b, lane, mn, mx);
+  } else {
+    for (int b = warp; b < p.B; b += nwarps) loss_acc += colbert_loss_row<false>(p, b, lane, mn, mx);
   }
 
   // mean over the batch (CrossEntropyLoss default reduction / .mean())
