@@ -270,10 +270,15 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
 
   // document `doc` is complete for resident query tile r: fold this query segment's 32 token maxima
   // (smooth mode: mm / ll are the online log-sum-exp pair in base-2 units, late_interaction_losses.py:40-44)
+  // first padded query row / query / 32-row segment of this warp for resident query tile 0 and R - 1 (computed once:
+  // the two divisions sat in every inlined copy of the emission code)
+  const int f_row0[2] = {(g * R) * kTileM + quad * 32, (g * R + R - 1) * kTileM + quad * 32};
+  const int f_q[2] = {f_row0[0] / p.nq_pad, f_row0[1] / p.nq_pad};
+  const int f_seg[2] = {(f_row0[0] % p.nq_pad) >> 5, (f_row0[1] % p.nq_pad) >> 5};
   auto finalize = [&](int doc, int r, float mm, int ai, float ll) {
-    const int row0 = (g * R + r) * kTileM + quad * 32;  // first padded query row of this warp
-    const int q = row0 / p.nq_pad;
-    const int seg = (row0 % p.nq_pad) >> 5;
+    const int row0 = (r == 0) ? f_row0[0] : f_row0[1];
+    const int q = (r == 0) ? f_q[0] : f_q[1];
+    const int seg = (r == 0) ? f_seg[0] : f_seg[1];
     if (kArgmax && p.argmax != nullptr && row0 + lane < p.q_rows)
       p.argmax[static_cast<int64_t>(doc) * p.q_rows + row0 + lane] = ai;
     float x;
@@ -433,9 +438,10 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
           float doc_ninit = cur_ninit;
 
           // the current document is complete: emit it and step to the next one of the run
-          auto finish_doc = [&]() {
-            if constexpr (kArgmax) ai = argmax_resolve(bc_slot, bc_sw, mm, ai);
-            if (head_frag && doc == first_doc) publish(r, mm, ai); else finalize(doc, r, mm, ai, ll);
+          auto emit_doc = [&](int e_doc, float e_mm, int e_ai, float e_ll) {  // stores only: may run after the release
+            if (head_frag && e_doc == first_doc) publish(r, e_mm, e_ai); else finalize(e_doc, r, e_mm, e_ai, e_ll);
+          };
+          auto advance_doc = [&]() {  // step the cursor to the next document of the run
             ++doc;
             if (doc >= run.e) {
               doc_end = 0x7fffffff;  // run exhausted
@@ -448,6 +454,11 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
             ll = 0.f;
             doc_nlen = (doc + 1 < run.e) ? __ldg(p.doc_len + doc + 1) : 0;
             doc_ninit = (doc + 1 < run.e) ? doc_init(doc + 1) : -INFINITY;
+          };
+          auto finish_doc = [&]() {
+            if constexpr (kArgmax) ai = argmax_resolve(bc_slot, bc_sw, mm, ai);
+            emit_doc(doc, mm, ai, ll);
+            advance_doc();
           };
           auto release_acc = [&]() {  // accumulator drained: hand the TMEM stage back to the MMA warp
             tc_fence_before();
@@ -492,23 +503,6 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
               if constexpr (kArgmax) argmax_fold_full(v, mm, ai, bc_slot, bc_sw, idx_t + 32 * k);
               else mm = max32(v, mm);
             };
-            if constexpr (kGroups == 2) {
-              // two warps per scheduler hide each other's latencies: one chunk in flight is enough, and the register
-              // budget of a 320-thread CTA (168 per thread) has no room for four buffers
-              uint32_t va[32], vb[32];
-              tmem_ld_x32(taddr, va);
-#pragma unroll
-              for (int k = 0; k < 8; k += 2) {
-                tmem_ld_wait();
-                reg_fence32(va);
-                tmem_ld_x32(taddr + 32 * (k + 1), vb);
-                fold(va, k);
-                tmem_ld_wait();
-                reg_fence32(vb);
-                if (k + 2 < 8) tmem_ld_x32(taddr + 32 * (k + 2), va); else release_acc();
-                fold(vb, k + 1);
-              }
-            } else {
             uint32_t va[32], vb[32], vc[32], vd[32];
             tmem_ld_x32(taddr, va);
             tmem_ld_x32(taddr + 32, vb);
@@ -539,7 +533,6 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
             release_acc();  // every accumulator read has landed in registers
             fold(vc, 6);
             fold(vd, 7);
-            }
             while (doc_end <= tile_end) finish_doc();  // document (and empty followers) ending at the tile end
           } else if (kArgmax && path == 2 && doc_end - row >= 32 && doc_end - row <= kTileN - 32) {
             // one boundary, argmax: the same boundary-aligned chunks as the max mode below, but in order -- the old
@@ -548,23 +541,46 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
             const int b = doc_end - row;
             const int n_old = (b + 31) >> 5;
             auto col = [&](int i) { return (i < n_old) ? min(32 * i, b - 32) : min(b + 32 * (i - n_old), kTileN - 32); };
-            uint32_t va[32], vb[32];
+            // the old document's result is looked up at the boundary (the slot is about to be reused) but STORED after
+            // the accumulator has been handed back: the emission code is several hundred instructions
+            int s_doc = 0, s_ai = 0;
+            float s_mm = 0.f;
+            auto step = [&](const uint32_t (&v)[32], int i) {
+              if (i == n_old) {  // warp-uniform: the old document is complete, the cursor moves on
+                s_doc = doc;
+                s_mm = mm;
+                s_ai = argmax_resolve(bc_slot, bc_sw, mm, ai);
+                advance_doc();
+              }
+              argmax_fold_full(v, mm, ai, bc_slot, bc_sw, row + col(i) - doc_row0);
+            };
+            // two loads in flight while two chunks fold (tcgen05.wait::ld waits for ALL outstanding loads, so the
+            // pipeline advances in pairs): with one in flight the walk ran at the TMEM load latency, ~150 cycles a chunk
+            uint32_t va[32], vb[32], vc[32], vd[32];
             tmem_ld_x32(taddr + col(0), va);
+            tmem_ld_x32(taddr + col(1), vb);
 #pragma unroll 1
-            for (int i = 0; i < 9; i += 2) {
+            for (int i = 0; i < 8; i += 4) {
               tmem_ld_wait();
               reg_fence32(va);
-              if (i + 1 < 9) tmem_ld_x32(taddr + col(i + 1), vb); else release_acc();
-              if (i == n_old) finish_doc();
-              argmax_fold_full(va, mm, ai, bc_slot, bc_sw, row + col(i) - doc_row0);
-              if (i + 1 < 9) {
-                tmem_ld_wait();
-                reg_fence32(vb);
-                tmem_ld_x32(taddr + col(i + 2), va);  // i + 2 <= 8
-                if (i + 1 == n_old) finish_doc();
-                argmax_fold_full(vb, mm, ai, bc_slot, bc_sw, row + col(i + 1) - doc_row0);
-              }
+              reg_fence32(vb);
+              tmem_ld_x32(taddr + col(i + 2), vc);
+              tmem_ld_x32(taddr + col(i + 3), vd);
+              step(va, i);
+              step(vb, i + 1);
+              tmem_ld_wait();
+              reg_fence32(vc);
+              reg_fence32(vd);
+              tmem_ld_x32(taddr + col(i + 4), va);                  // chunk 4, then chunk 8
+              if (i == 0) tmem_ld_x32(taddr + col(i + 5), vb);      // chunk 5
+              step(vc, i + 2);
+              step(vd, i + 3);
             }
+            tmem_ld_wait();
+            reg_fence32(va);
+            release_acc();
+            step(va, 8);
+            emit_doc(s_doc, s_mm, s_ai, 0.f);
             while (doc_end <= tile_end) finish_doc();
           } else if (!kArgmax && path == 2 && shifted_boundary && doc_end - row >= 32 && doc_end - row <= kTileN - 32) {
             // one boundary at column b, at least 32 columns from either edge: read the tile as 32-column chunks

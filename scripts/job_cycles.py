@@ -72,9 +72,17 @@ finally:
 raw = raw.flatten().cpu()
 n_cta = 144
 cyc = raw[0:2 * n_cta:2]
+ns = raw[1:2 * n_cta:2]
 c = raw[512:512 + 8 * n_cta].view(n_cta, 8)
 own = c[:, 7].clamp_min(1)
-print(json.dumps({"mode": "argmax, cfg3", "ctas": int((c[:, 7] > 0).sum()), "own_jobs_per_warp": float(own.mean()),
+for _ in range(5): cb.maxsim(qb3, bank3, want_argmax=True)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(50): cb.maxsim(qb3, bank3, want_argmax=True)
+e1.record(); torch.cuda.synchronize()
+warm_us = 1e3 * e0.elapsed_time(e1) / 50
+print(json.dumps({"mode": "argmax, cfg3", "kernel_us_back_to_back": warm_us, "cta_main_loop_us_mean": float(ns.mean()) / 1e3,
+                  "cta_main_loop_us_max": float(ns.max()) / 1e3, "ctas": int((c[:, 7] > 0).sum()), "own_jobs_per_warp": float(own.mean()),
                   "cta_cycles_mean": float(cyc.mean()), "cta_cycles_max": float(cyc.max()),
                   "cycles_per_own_job": float((cyc / own).mean()),
                   "hold_whole_tile_per_job": float((c[:, 3] / (own - c[:, 6]).clamp_min(1)).mean()),
