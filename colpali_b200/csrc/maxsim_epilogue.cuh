@@ -376,6 +376,10 @@ __device__ __forceinline__ void maxsim_epilogue(const MaxSimParams& p, const Cta
     __threadfence();
     const float om = __ldcg(p.split_max + slot * 128 + quad * 32 + lane);
     const int oi = kArgmax ? __ldcg(p.split_idx + slot * 128 + quad * 32 + lane) : -1;
+    // hand the slot back: a CUDA-graph replay repeats this launch with the SAME epoch, and must not mistake the flag
+    // its previous replay left behind for the neighbour's new partial (all lanes have read the partial first)
+    __syncwarp();
+    if (lane == 0) *reinterpret_cast<volatile uint32_t*>(p.split_flag + slot * 4 + quad) = 0u;
     if (om > mm) {  // on a tie the earlier (left) token wins, like torch.max
       mm = om;
       ai = oi;

@@ -374,3 +374,33 @@ def test_cfg4_geometry_128_queries_planted_positives(n_docs):
             assert torch.equal(cb.maxsim(cb.QueryBlock(q, dev), bank), got), opt
         finally:
             _lib.set_option(opt, 1 if opt == "balanced" else 0)
+
+
+def test_cuda_graph_replays_with_new_queries():
+    """A captured launch repeats with the same per-launch epoch; the partition-boundary exchange (balanced mode) must
+    still hand over THIS replay's partials: replays with new queries in the static buffer equal eager launches."""
+    dev = torch.device(DEV)
+    g = torch.Generator().manual_seed(77)
+    docs = torch.randn(60, 1030, 128, generator=g).bfloat16().to(dev)
+    bank = cb.DocBank.from_passages(docs, dev)
+    q_static = torch.randn(16, 32, 128, generator=g).bfloat16().to(dev)
+    qb = cb.QueryBlock(q_static, dev)
+    assert qb.flat.data_ptr() == q_static.data_ptr()  # zero-copy: replays see what is written into q_static
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        cb.maxsim(qb, bank)
+    torch.cuda.current_stream().wait_stream(s)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out_a = cb.maxsim(qb, bank)
+        out_b = cb.maxsim(qb, bank, want_argmax=True)[0]
+    for trial in range(4):
+        q_new = torch.randn(16, 32, 128, generator=g).bfloat16().to(dev)
+        q_static.copy_(q_new)
+        graph.replay()
+        torch.cuda.synchronize()
+        got_a, got_b = out_a.clone(), out_b.clone()
+        want = cb.maxsim(cb.QueryBlock(q_new, dev), bank)
+        torch.cuda.synchronize()
+        assert torch.equal(got_a, want) and torch.equal(got_b, want), trial
