@@ -8,7 +8,7 @@ the GPU box (baseline/_ref is git-ignored, not gpurun-ignored; the repo's histor
    and not in /opt/wheelhouse.
 2. Fallback = what that wheel would contain: the pure-Python package directory `colpali_engine/`
    (`[tool.hatch.build.targets.wheel] include = ["colpali_engine"]`, pyproject.toml:8-9), copied byte for byte, plus
-   the reference's own offline hot-path tests (tests/utils/test_processing_utils.py, tests/loss/test_li_losses.py)
+   the reference's own offline hot-path tests (tests/utils/test_processing_utils.py, tests/loss/test_li_losses.py, tests/loss/test_bi_losses.py)
    under baseline/_ref/ref_tests/ for the replay test (tests/test_reference_replay_gpu.py).
 Used by: bench.py --impl reference / cpu_baseline (kind "reference"), tests/test_reference_replay_gpu.py.
 """
@@ -16,7 +16,7 @@ import argparse, os, shutil, subprocess, sys, tempfile
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 DST = os.path.join(HERE, "_ref")
-REF_TESTS = ("tests/utils/test_processing_utils.py", "tests/loss/test_li_losses.py")
+REF_TESTS = ("tests/utils/test_processing_utils.py", "tests/loss/test_li_losses.py", "tests/loss/test_bi_losses.py")
 
 
 def install(src: str = "/root/reference", verbose: bool = True) -> str:

@@ -30,6 +30,7 @@ EXPORTED_SYMBOLS = (
     "cpb_exchange_push",
     "cpb_signal_peers",
     "cpb_head_fwd",
+    "cpb_dense_dot_launch",
 )
 
 CPB_ABI_VERSION = 2
@@ -42,6 +43,10 @@ CPB_HEAD_SINGLE_ROUNDING = 2
 CPB_LOSS_CE = 0
 CPB_LOSS_PAIRWISE = 1
 CPB_LOSS_SIGMOID = 2
+CPB_LOSS_SYMMETRIC_CE = 3
+CPB_DOT_A_F32 = 1
+CPB_DOT_ACCUMULATE = 2
+CPB_DOT_B_F32 = 4
 
 c_vp, c_i, c_i64, c_u32, c_u64, c_f = (ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32, ctypes.c_uint64,
                                        ctypes.c_float)
@@ -55,6 +60,7 @@ class LossDesc(ctypes.Structure):
         ("offset", c_i), ("temperature", c_f), ("filter_threshold", c_f), ("filter_factor", c_f),
         ("d_neg_scores", c_vp), ("n_neg", c_i), ("in_batch_term_weight", c_f),
         ("d_loss", c_vp), ("d_grad_scores", c_vp), ("d_grad_neg_scores", c_vp), ("d_bounds", c_vp),
+        ("neg_pos_offset_delta", c_i),
     ]
 
     def __init__(self, **kw):
@@ -117,6 +123,22 @@ class ExchangePushArgs(ctypes.Structure):
         self.struct_size = ctypes.sizeof(ExchangePushArgs)
 
 
+class DenseDotArgs(ctypes.Structure):
+    """``cpb_dense_dot_args`` (include/colpali_b200.h)."""
+
+    _fields_ = [
+        ("struct_size", c_u32), ("flags", c_u32), ("stream", c_vp),
+        ("d_a", c_vp), ("a_row_stride", c_i64), ("a_k_stride", c_i64),
+        ("d_b", c_vp), ("b_row_stride", c_i64), ("b_k_stride", c_i64), ("d_b_rows", c_vp),
+        ("m", c_i), ("n", c_i), ("k", c_i),
+        ("d_out", c_vp), ("out_row_stride", c_i64), ("d_alpha", c_vp),
+    ]
+
+    def __init__(self, **kw):
+        super().__init__(**kw)
+        self.struct_size = ctypes.sizeof(DenseDotArgs)
+
+
 _lib: Optional[ctypes.CDLL] = None
 
 
@@ -172,6 +194,8 @@ def load() -> ctypes.CDLL:
     lib.cpb_exchange_push.argtypes = [ctypes.POINTER(ExchangePushArgs)]
     lib.cpb_signal_peers.restype = ci
     lib.cpb_signal_peers.argtypes = [c_vp, c_u64, ci, c_i64, c_vp]
+    lib.cpb_dense_dot_launch.restype = ci
+    lib.cpb_dense_dot_launch.argtypes = [ctypes.POINTER(DenseDotArgs)]
     lib.cpb_head_fwd.restype = ci
     lib.cpb_head_fwd.argtypes = [
         c_vp, c_i64, ci,  # d_hidden, n_tokens, hidden

@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/colpali_b200.h"
+#include "dense_params.h"
 #include "exchange_params.h"
 #include "head_params.h"
 #include "loss_params.h"
@@ -145,19 +146,31 @@ int fill_loss_params(cpb::LossParams* p, const cpb_loss_desc* d, const float* d_
   if (!d || d->struct_size < offsetof(cpb_loss_desc, d_bounds) + sizeof(float*))
     return fail(CPB_E_INVALID, "cpb_loss_desc is null or its struct_size is too small");
   if (n_queries <= 0 || n_docs <= 0) return fail(CPB_E_INVALID, "n_queries=%d and n_docs=%d must be positive", n_queries, n_docs);
-  if (nq_pad <= 0 || (nq_pad % 32) != 0) return fail(CPB_E_INVALID, "nq_pad=%d must be a positive multiple of 32", nq_pad);
-  if (dim != 128 && dim != 192 && dim != 256 && dim != 320)
-    return fail(CPB_E_UNSUPPORTED, "embedding dim %d is not supported by this build (128, 192, 256, 320)", dim);
+  const bool bi = (d_q == nullptr);  // single-vector scores (bi-encoder losses): no query rows to count lengths from
+  if (!bi) {
+    if (nq_pad <= 0 || (nq_pad % 32) != 0) return fail(CPB_E_INVALID, "nq_pad=%d must be a positive multiple of 32", nq_pad);
+    if (dim != 128 && dim != 192 && dim != 256 && dim != 320)
+      return fail(CPB_E_UNSUPPORTED, "embedding dim %d is not supported by this build (128, 192, 256, 320)", dim);
+  } else if (d->normalize_scores) {
+    return fail(CPB_E_INVALID, "normalize_scores needs the query rows (d_q)");
+  }
   const int mode = d->mode;
-  if (mode != CPB_LOSS_CE && mode != CPB_LOSS_PAIRWISE && mode != CPB_LOSS_SIGMOID) return fail(CPB_E_INVALID, "unknown loss mode %d", mode);
-  if (mode == CPB_LOSS_SIGMOID && (n_docs != n_queries || d->offset != 0))
+  if (mode != CPB_LOSS_CE && mode != CPB_LOSS_PAIRWISE && mode != CPB_LOSS_SIGMOID && mode != CPB_LOSS_SYMMETRIC_CE)
+    return fail(CPB_E_INVALID, "unknown loss mode %d", mode);
+  // ColbertSigmoidLoss flattens a [B, B] matrix (late_interaction_losses.py:456-463); BiSigmoidLoss walks C / B blocks
+  if (mode == CPB_LOSS_SIGMOID && !bi && (n_docs != n_queries || d->offset != 0))
     return fail(CPB_E_INVALID, "the sigmoid loss needs n_docs == n_queries and offset == 0 (got %d, %d, %d)", n_docs, n_queries, d->offset);
+  if (mode == CPB_LOSS_SIGMOID && bi && (n_docs % n_queries) != 0)
+    return fail(CPB_E_INVALID, "the bi-encoder sigmoid loss needs n_docs (%d) to be a multiple of n_queries (%d)", n_docs, n_queries);
+  if (mode == CPB_LOSS_SYMMETRIC_CE && (n_docs != n_queries || d->offset != 0 || d->normalize_scores || d->d_neg_scores))
+    return fail(CPB_E_INVALID, "the symmetric loss needs a square score matrix, offset 0, no normalisation, no negatives");
   if (d->d_neg_scores && (d->n_neg <= 0 || mode == CPB_LOSS_SIGMOID || d->in_batch_term_weight < 0.f || d->in_batch_term_weight > 1.f))
     return fail(CPB_E_INVALID, "bad explicit-negative arguments (n_neg=%d, mode=%d, weight=%g)", d->n_neg, mode, static_cast<double>(d->in_batch_term_weight));
-  if (d->offset < 0 || d->offset + n_queries > n_docs)
-    return fail(CPB_E_INVALID, "positive index out of range: offset=%d + n_queries=%d > n_docs=%d", d->offset, n_queries, n_docs);
+  const int neg_delta = (d->d_neg_scores && CPB_HAS(d, cpb_loss_desc, neg_pos_offset_delta)) ? d->neg_pos_offset_delta : 0;
+  if (d->offset < 0 || d->offset + n_queries > n_docs || d->offset + neg_delta < 0 || d->offset + neg_delta + n_queries > n_docs)
+    return fail(CPB_E_INVALID, "positive index out of range: offset=%d (+%d) + n_queries=%d > n_docs=%d", d->offset, neg_delta, n_queries, n_docs);
   if (!(d->temperature > 0.f)) return fail(CPB_E_INVALID, "temperature must be positive");
-  if (!d_scores || !d_q || !d->d_loss) return fail(CPB_E_INVALID, "null device pointer");
+  if (!d_scores || !d->d_loss) return fail(CPB_E_INVALID, "null device pointer");
   *p = cpb::LossParams{};
   p->scores = d_scores;
   p->q = static_cast<const __nv_bfloat16*>(d_q);
@@ -179,6 +192,7 @@ int fill_loss_params(cpb::LossParams* p, const cpb_loss_desc* d, const float* d_
   p->grad_neg = d->d_grad_neg_scores;
   p->n_neg = d->n_neg;
   p->in_batch_weight = d->d_neg_scores ? d->in_batch_term_weight : 1.f;
+  p->neg_pos_delta = neg_delta;
   return CPB_OK;
 }
 
@@ -483,6 +497,34 @@ int cpb_colbert_loss_launch(const cpb_loss_desc* loss, const float* d_scores, co
   int rc = fill_loss_params(&p, loss, d_scores, d_q, n_queries, nq_pad, n_docs, dim);
   if (rc != CPB_OK) return rc;
   CPB_CUDA(cpb::colbert_loss_launch(p, static_cast<cudaStream_t>(stream_)));
+  return CPB_OK;
+}
+
+int cpb_dense_dot_launch(const cpb_dense_dot_args* a) {
+  if (!a || a->struct_size < offsetof(cpb_dense_dot_args, out_row_stride) + sizeof(int64_t))
+    return fail(CPB_E_INVALID, "cpb_dense_dot_args is null or its struct_size is too small");
+  if (a->m <= 0 || a->n <= 0 || a->k <= 0) return fail(CPB_E_INVALID, "m=%d, n=%d, k=%d must be positive", a->m, a->n, a->k);
+  if (!a->d_a || !a->d_b || !a->d_out) return fail(CPB_E_INVALID, "null device pointer");
+  if (a->out_row_stride < a->n) return fail(CPB_E_INVALID, "out_row_stride=%lld < n=%d", static_cast<long long>(a->out_row_stride), a->n);
+  if ((a->m + 31) / 32 > 65535) return fail(CPB_E_UNSUPPORTED, "m=%d: more than 65535 row tiles (put the long side in n)", a->m);
+  cpb::DenseDotParams p{};
+  p.a = a->d_a;
+  p.b = a->d_b;
+  p.b_rows = a->d_b_rows;
+  p.a_rs = a->a_row_stride;
+  p.a_ks = a->a_k_stride;
+  p.b_rs = a->b_row_stride;
+  p.b_ks = a->b_k_stride;
+  p.m = a->m;
+  p.n = a->n;
+  p.k = a->k;
+  p.out = a->d_out;
+  p.out_rs = a->out_row_stride;
+  p.alpha = CPB_HAS(a, cpb_dense_dot_args, d_alpha) ? a->d_alpha : nullptr;
+  p.accumulate = (a->flags & CPB_DOT_ACCUMULATE) ? 1 : 0;
+  p.a_f32 = (a->flags & CPB_DOT_A_F32) ? 1 : 0;
+  p.b_f32 = (a->flags & CPB_DOT_B_F32) ? 1 : 0;
+  CPB_CUDA(cpb::dense_dot_launch(p, static_cast<cudaStream_t>(a->stream)));
   return CPB_OK;
 }
 

@@ -57,7 +57,8 @@ __device__ __forceinline__ void loss_for_cols(int C, int lane, const float (&sv)
 template <bool kCached>
 __device__ __forceinline__ float colbert_loss_row(const LossParams& p, int b, int lane, float& mn, float& mx) {
   const bool has_neg = p.neg_scores != nullptr;
-  const float w_ib = has_neg ? p.in_batch_weight : 1.f;     // late_interaction_losses.py:248-250 / :394-396
+  // late_interaction_losses.py:248-250 / :394-396; the row half of the symmetric loss weighs 1/2 (bi_encoder_losses.py:168)
+  const float w_ib = (has_neg ? p.in_batch_weight : 1.f) * (p.mode == 3 ? 0.5f : 1.f);
   const float w_out = has_neg ? 1.f - p.in_batch_weight : 0.f;
   const float* row = p.scores + static_cast<int64_t>(b) * p.C;
   const int pidx = b + p.offset;                              // :33-38
@@ -73,10 +74,12 @@ __device__ __forceinline__ float colbert_loss_row(const LossParams& p, int b, in
   const float pos_raw = __ldcg(row + pidx);
   // lengths = (q[:, :, 0] != 0).sum(1)                       late_interaction_losses.py:152
   float cnt = 0.f;
-  for (int n = lane; n < p.nq_pad; n += 32)
-    cnt += (__bfloat162float(p.q[(static_cast<int64_t>(b) * p.nq_pad + n) * p.q_dim]) != 0.f) ? 1.f : 0.f;
-  cnt = warp_sum_f(cnt);
-  const float inv = p.normalize ? 1.f / cnt : 1.f;          // :155-156 -> :59-62
+  if (p.q != nullptr) {
+    for (int n = lane; n < p.nq_pad; n += 32)
+      cnt += (__bfloat162float(p.q[(static_cast<int64_t>(b) * p.nq_pad + n) * p.q_dim]) != 0.f) ? 1.f : 0.f;
+    cnt = warp_sum_f(cnt);
+  }
+  const float inv = (p.normalize && p.q != nullptr) ? 1.f / cnt : 1.f;   // :155-156 -> :59-62
   if constexpr (kCached) {
 #pragma unroll
     for (int j = 0; j < kLossCols; ++j) sv[j] *= inv;
@@ -94,8 +97,8 @@ __device__ __forceinline__ float colbert_loss_row(const LossParams& p, int b, in
   };
   auto for_cols = [&](auto&& fn) { loss_for_cols<kCached>(p.C, lane, sv, row, inv, fn); };
 
-  if (p.mode == 0) {
-    // cross entropy of scores / T against pidx                (:164)
+  if (p.mode == 0 || p.mode == 3) {
+    // cross entropy of scores / T against pidx                (:164; bi_encoder_losses.py:113, :165)
     float m = -INFINITY;
     for_cols([&](int c, float s) {
       float f;
@@ -164,7 +167,8 @@ __device__ __forceinline__ float colbert_loss_row(const LossParams& p, int b, in
       });
     }
   } else {
-    // sigmoid loss: softplus(-s/T * m), m = +1 on the diagonal, -1 elsewhere; mean over B*B   (:452-465)
+    // sigmoid loss: softplus(-s/T * m), m = +1 at the positive, -1 elsewhere; mean over B*C   (:452-465; the block
+    // loop of bi_encoder_losses.py:400-416 visits every column once when C is a multiple of B)
     float* g = p.grad ? p.grad + static_cast<int64_t>(b) * p.C : nullptr;
     const float invBB = invB / static_cast<float>(p.C);
     float part = 0.f;  // per-lane partial sum, reduced below (the returned loss must stay warp-uniform)
@@ -173,7 +177,7 @@ __device__ __forceinline__ float colbert_loss_row(const LossParams& p, int b, in
       const float s = filtered(c, s0, f);
       mn = fminf(mn, s0);
       mx = fmaxf(mx, s0);
-      const float msk = (c == b) ? 1.f : -1.f;
+      const float msk = (c == pidx) ? 1.f : -1.f;
       const float z = -s * invT * msk;
       part += (fmaxf(z, 0.f) + log1pf(__expf(-fabsf(z)))) / static_cast<float>(p.C);
       if (g) g[c] = -msk * invT * f * inv * invBB / (1.f + __expf(-z));
@@ -186,11 +190,13 @@ __device__ __forceinline__ float colbert_loss_row(const LossParams& p, int b, in
     const float* nrow = p.neg_scores + static_cast<int64_t>(b) * p.B * p.n_neg;
     float* gn = p.grad_neg ? p.grad_neg + static_cast<int64_t>(b) * p.B * p.n_neg : nullptr;
     const float scale = w_out / (static_cast<float>(p.B) * static_cast<float>(p.n_neg));
+    const int nidx = pidx + p.neg_pos_delta;
+    const float npos = p.neg_pos_delta ? __ldcg(row + nidx) * inv : pos;
     float gpos = 0.f, part = 0.f;
     for (int c = lane; c < p.B * p.n_neg; c += 32) {
       float gv = 0.f;
       if (c / p.n_neg == b) {
-        const float x = (__ldcg(nrow + c) * inv - pos) * invT;
+        const float x = (__ldcg(nrow + c) * inv - npos) * invT;
         part += (fmaxf(x, 0.f) + log1pf(__expf(-fabsf(x)))) * w_out / static_cast<float>(p.n_neg);
         gv = scale * invT * inv / (1.f + __expf(-x));
         gpos -= gv;
@@ -199,9 +205,47 @@ __device__ __forceinline__ float colbert_loss_row(const LossParams& p, int b, in
     }
     gpos = warp_sum_f(gpos);
     loss += warp_sum_f(part);
-    if (p.grad != nullptr && lane == (pidx & 31)) p.grad[static_cast<int64_t>(b) * p.C + pidx] += gpos;
+    if (p.grad != nullptr && lane == (nidx & 31)) p.grad[static_cast<int64_t>(b) * p.C + nidx] += gpos;
   }
   return loss;
+}
+
+// Column half of the symmetric loss (mode 3, bi_encoder_losses.py:166-168): cross entropy over the QUERIES b of
+// scores[b, c] / T against b == c, weight 1/2, gradient ADDED to what the row pass wrote.  The in-place filter of :160-161
+// was applied row-wise (threshold from row b's positive) before both halves, so it is re-derived per element here.
+__device__ __forceinline__ float symmetric_loss_col(const LossParams& p, int c, int lane) {
+  const float invT = 1.f / p.temperature;
+  auto filtered = [&](int b, float& f) {
+    const float* row = p.scores + static_cast<int64_t>(b) * p.C;
+    const float s = __ldcg(row + c);
+    const int pidx = b + p.offset;
+    f = (p.filter && c != pidx && s > p.filter_threshold * __ldcg(row + pidx)) ? p.filter_factor : 1.f;
+    return s * f;
+  };
+  float m = -INFINITY;
+  for (int b = lane; b < p.B; b += 32) {
+    float f;
+    m = fmaxf(m, filtered(b, f) * invT);
+  }
+  m = warp_max_f(m);
+  float se = 0.f;
+  for (int b = lane; b < p.B; b += 32) {
+    float f;
+    se += __expf(filtered(b, f) * invT - m);
+  }
+  se = warp_sum_f(se);
+  const float lse = m + __logf(se);
+  float ftgt;
+  const float tgt = filtered(c, ftgt) * invT;
+  if (p.grad != nullptr) {
+    const float w = 0.5f / static_cast<float>(p.C);
+    for (int b = lane; b < p.B; b += 32) {
+      float f;
+      const float sm = __expf(filtered(b, f) * invT - lse);
+      p.grad[static_cast<int64_t>(b) * p.C + c] += (sm - (b == c ? 1.f : 0.f)) * invT * f * w;
+    }
+  }
+  return 0.5f * (lse - tgt);
 }
 
 // Whole-CTA device function (every thread of the block must call it: it ends with a __syncthreads reduction).
@@ -218,6 +262,10 @@ __device__ __forceinline__ void colbert_loss_body(const LossParams& p) {
     for (int b = warp; b < p.B; b += nwarps) loss_acc += colbert_loss_row<true>(p, b, lane, mn, mx);
   } else {
     for (int b = warp; b < p.B; b += nwarps) loss_acc += colbert_loss_row<false>(p, b, lane, mn, mx);
+  }
+  if (p.mode == 3) {  // C == B: the column terms join the same sum / B
+    __syncthreads();  // the row pass's gradient stores (this CTA's own) before the column pass adds to them
+    for (int c = warp; c < p.C; c += nwarps) loss_acc += symmetric_loss_col(p, c, lane);
   }
 
   // mean over the batch (CrossEntropyLoss default reduction / .mean())

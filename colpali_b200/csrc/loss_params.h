@@ -8,14 +8,16 @@ namespace cpb {
 
 struct LossParams {
   const float* scores;        // [B, C] raw sums of per-token maxima
-  const __nv_bfloat16* q;     // [B * nq_pad, q_dim] padded queries (lengths are counted from column 0)
+  const __nv_bfloat16* q;     // [B * nq_pad, q_dim] padded queries (lengths are counted from column 0); nullptr = the
+                              // scores are plain dot products of single vectors (bi-encoder losses): no lengths
   int q_dim;                  // row stride of q in elements (128, or 192 / 256 / 320)
   float* loss;                // [1]
   float* grad;                // [B, C] dLoss/dScores (raw), or nullptr
   float* bounds;              // [2] min / max of the normalised scores, or nullptr
   int B, C, nq_pad, offset;
   int mode;                   // 0 = cross entropy (ColbertLoss), 1 = pairwise softplus (ColbertPairwiseCELoss),
-                              // 2 = sigmoid (ColbertSigmoidLoss, needs C == B and offset == 0)
+                              // 2 = sigmoid (+1 at column b + offset, -1 elsewhere, mean over B * C),
+                              // 3 = symmetric cross entropy (BiPairedEncoderLoss: rows and columns, C == B)
   int normalize, filter;
   float temperature, filter_threshold, filter_factor;
   // explicit negatives (ColbertNegativeCELoss / ColbertPairwiseNegativeCELoss); neg_scores == nullptr: none
@@ -23,6 +25,8 @@ struct LossParams {
   float* grad_neg;            // [B, B * n_neg] or nullptr
   int n_neg;
   float in_batch_weight;      // weight of the in-batch term (mode 0 / 1) when negatives are present
+  int neg_pos_delta;          // the explicit-negative term takes its positive from column b + offset + neg_pos_delta
+                              // (BiPairwiseNegativeCELoss: its in-batch term ignores `offset`, its explicit term does not)
 };
 
 struct BwdParams {

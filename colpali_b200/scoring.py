@@ -315,18 +315,3 @@ def score_multi_vector(
     out = scores.cpu()  # the reference contract: scores live on the CPU (:180)
     assert out.shape[0] == len(qs), f"Expected {len(qs)} scores, got {out.shape[0]}"
     return out.to(torch.float32)
-
-
-def score_single_vector(qs: TensorOrList, ps: TensorOrList,
-                        device: Optional[Union[str, torch.device]] = None) -> torch.Tensor:
-    """Dense dot-product scorer (processing_utils.py:103-130) as the N_q = N_d = 1 case of MaxSim."""
-    dev = _resolve_device(device)
-    if isinstance(qs, list) and isinstance(ps, list):
-        if len(qs) == 0:
-            raise ValueError("No queries provided")
-        if len(ps) == 0:
-            raise ValueError("No passages provided")
-        qs, ps = torch.stack(qs), torch.stack(ps)
-    q = QueryBlock(qs.unsqueeze(1), dev)
-    bank = DocBank.from_passages(ps.unsqueeze(1), dev)
-    return maxsim(q, bank).to(torch.float32)

@@ -93,7 +93,11 @@ int cpb_set_option(const char* name, int value);
  * ------------------------------------------------------------------------------------------------------------------ */
 #define CPB_LOSS_CE 0       /* ColbertLoss: cross entropy over in-batch documents          */
 #define CPB_LOSS_PAIRWISE 1 /* ColbertPairwiseCELoss: softplus(hardest negative - positive) */
-#define CPB_LOSS_SIGMOID 2  /* ColbertSigmoidLoss: n_docs == n_queries, offset 0            */
+#define CPB_LOSS_SIGMOID 2  /* ColbertSigmoidLoss: n_docs == n_queries, offset 0; with d_q == NULL BiSigmoidLoss
+                               (bi_encoder_losses.py:372-418): +1 at column b + offset, -1 elsewhere, n_docs a multiple
+                               of n_queries */
+#define CPB_LOSS_SYMMETRIC_CE 3 /* BiPairedEncoderLoss (bi_encoder_losses.py:140-168): (CE over rows + CE over columns) / 2,
+                                   square matrix, d_q == NULL */
 
 typedef struct cpb_loss_desc {
   uint32_t struct_size;
@@ -111,9 +115,15 @@ typedef struct cpb_loss_desc {
   float* d_grad_scores;                 /* fp32 [n_queries, n_docs] out or NULL: d loss / d raw score */
   float* d_grad_neg_scores;             /* fp32 [n_queries, n_queries * n_neg] out or NULL */
   float* d_bounds;                      /* fp32 [2] out or NULL: min / max of the normalised scores (:64-70) */
+  int32_t neg_pos_offset_delta;         /* with negatives: their term reads its positive from column b + offset + this
+                                           (BiPairwiseNegativeCELoss, bi_encoder_losses.py:350 vs :299: the in-batch term of
+                                           that class ignores `offset`, the explicit term does not).  Normally 0 */
 } cpb_loss_desc;
 
-/* Stand-alone launch of the loss kernel on an existing score matrix.  d_q: bf16 [n_queries * nq_pad, dim]. */
+/* Stand-alone launch of the loss kernel on an existing score matrix.  d_q: bf16 [n_queries * nq_pad, dim], or NULL when
+ * the scores are dot products of single vectors (the bi-encoder losses, colpali_engine/loss/bi_encoder_losses.py:64-418:
+ * BiEncoderLoss = CPB_LOSS_CE, BiPairwiseCELoss = CPB_LOSS_PAIRWISE, BiSigmoidLoss, BiPairedEncoderLoss, and the two
+ * explicit-negative classes through d_neg_scores); nq_pad / dim are then ignored and normalize_scores must be 0. */
 int cpb_colbert_loss_launch(const cpb_loss_desc* loss, const float* d_scores, const void* d_q, int n_queries, int nq_pad,
                             int n_docs, int dim, void* stream);
 
@@ -266,6 +276,36 @@ int cpb_exchange_push(cpb_exchange_push_args* args);
 /* Enqueue a one-thread kernel that adds 1 (release, system scope) to word flag_word_offset of every rank's buffer:
  * publishes everything the stream did before (e.g. the peer adds of cpb_maxsim_bwd_launch with d_dd_doc_base). */
 int cpb_signal_peers(const uint64_t* d_peer_bases, uint64_t mc_base, int n_peers, int64_t flag_word_offset, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Dense dot products in fp32 (row f-4):  out[i, j] (+)= alpha * sum_k A[i, k] * B[row(j), k]
+ *   replaces: torch.einsum("bd,cd->bc", qs, ps)        colpali_engine/utils/processing_utils.py:126 (score_single_vector)
+ *             the same einsum of the bi-encoder losses  colpali_engine/loss/bi_encoder_losses.py:105,158,290,396 and
+ *             "bd,bnd->bn" :235, with their backward products through strided operands
+ *             torch.einsum("nk,ijk->nij", q, grid)      colpali_engine/interpretability/similarity_map_utils.py:50-52
+ *             (d_b_rows = the masked patch rows regrouped "(h w) c -> w h c", :41-47)
+ * Operands keep their dtype (bf16 is widened exactly, fp32 stays fp32); strides are in ELEMENTS.
+ * ------------------------------------------------------------------------------------------------------------------ */
+#define CPB_DOT_A_F32 1u      /* A is fp32 (default: bf16) */
+#define CPB_DOT_B_F32 4u      /* B is fp32 (default: bf16) */
+#define CPB_DOT_ACCUMULATE 2u /* out += instead of out = */
+
+typedef struct cpb_dense_dot_args {
+  uint32_t struct_size;
+  uint32_t flags;               /* CPB_DOT_* */
+  void* stream;
+  const void* d_a;              /* element (i, k) at d_a[i * a_row_stride + k * a_k_stride] */
+  int64_t a_row_stride, a_k_stride;
+  const void* d_b;              /* element (j, k) at d_b[row(j) * b_row_stride + k * b_k_stride] */
+  int64_t b_row_stride, b_k_stride;
+  const int32_t* d_b_rows;      /* [n] or NULL: row(j) = d_b_rows[j] (gather), else j */
+  int32_t m, n, k;
+  float* d_out;                 /* fp32, element (i, j) at d_out[i * out_row_stride + j] */
+  int64_t out_row_stride;
+  const float* d_alpha;         /* device scalar or NULL (= 1) */
+} cpb_dense_dot_args;
+
+int cpb_dense_dot_launch(const cpb_dense_dot_args* args);
 
 /* flags for cpb_head_fwd */
 #define CPB_HEAD_CLAMP_NORM 1u      /* norm = max(norm, 1e-12): ColModernVBert variant (modeling_colmodernvbert.py:59) */

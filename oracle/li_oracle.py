@@ -12,6 +12,9 @@ What it restates (reference = illuin-tech/colpali @ 9be8f19, paths relative to /
   <- colpali_engine/loss/late_interaction_losses.py:73-107 (aggregate, filter), :140-164, :284-313;
   ``colbert_negative_ce_loss_port`` :215-252, ``colbert_pairwise_negative_ce_loss_port`` :361-398,
   ``colbert_sigmoid_loss_port`` :431-465.
+* ``bi_loss_port`` <- colpali_engine/loss/bi_encoder_losses.py:64-418 (the six bi-encoder losses, one closed form),
+  ``similarity_maps_port`` <- colpali_engine/interpretability/similarity_map_utils.py:9-56,
+  ``score_single_vector_port`` <- colpali_engine/utils/processing_utils.py:103-130.
 * ``head_port`` <- colpali_engine/models/qwen2/colqwen2/modeling_colqwen2.py:65-74
   (and modernvbert's clamp variant, models/modernvbert/colvbert/modeling_colmodernvbert.py:59).
 * ``maxsim_f64`` -- an independent numpy float64 evaluation of sum_n max_s <q_n, d_s> used to
@@ -190,6 +193,68 @@ def colbert_sigmoid_loss_port(q, d, offset: int = 0, temperature: float = 0.02, 
     pos_mask = -torch.ones(b * b, device=scores.device)
     pos_mask[pos_idx * (b + 1)] = 1.0
     return F.softplus(-(scores.reshape(-1) / temperature) * pos_mask).mean()
+
+
+# ---------------------------------------------------------------------------------------------
+# single-vector (bi-encoder) scorer, losses, similarity maps                      
+# ---------------------------------------------------------------------------------------------
+def score_single_vector_port(qs: torch.Tensor, ps: torch.Tensor) -> torch.Tensor:
+    """processing_utils.py:126-129."""
+    return torch.einsum("bd,cd->bc", qs, ps).to(torch.float32)
+
+
+def bi_loss_port(kind: str, q: torch.Tensor, d: torch.Tensor, neg: Optional[torch.Tensor] = None, offset: int = 0,
+                 temperature: float = 0.02, pos_aware_negative_filtering: bool = False, in_batch_term_weight: float = 0.5,
+                 filter_threshold: float = 0.95, filter_factor: float = 0.5) -> torch.Tensor:
+    """The bi-encoder losses of bi_encoder_losses.py written as ONE closed form over the [B, C] score matrix (what the loss
+    kernel evaluates) instead of the reference's module-by-module code:
+      kind "ce" BiEncoderLoss :103-113, "paired" BiPairedEncoderLoss :157-168, "pairwise" BiPairwiseCELoss :290-302
+      (positives = diagonal, offset ignored), "sigmoid" BiSigmoidLoss :396-418 (all B x C pairs, +1 at b + offset),
+      "negce" BiNegativeCELoss :231-248, "pairneg" BiPairwiseNegativeCELoss :350-358."""
+    t = temperature
+    scores = torch.einsum("bd,cd->bc", q, d)
+    b, c = scores.shape
+    idx = torch.arange(b)
+    ib_offset = 0 if kind in ("pairwise", "pairneg") else offset
+    pos_idx = idx + ib_offset
+    filt = pos_aware_negative_filtering and kind != "pairneg"
+    if filt:
+        scores = _filter_high_negatives_port(scores, pos_idx, filter_threshold, filter_factor)
+
+    def pairwise(sc):
+        pos = sc.diagonal()
+        top2 = sc.topk(2, dim=1).values
+        hard = torch.where(top2[:, 0] == pos, top2[:, 1], top2[:, 0])
+        return F.softplus((hard - pos) / t).mean()
+
+    if kind == "ce":
+        return F.cross_entropy(scores / t, pos_idx)
+    if kind == "paired":
+        return (F.cross_entropy(scores / t, pos_idx) + F.cross_entropy(scores.T / t, idx)) / 2.0
+    if kind == "pairwise":
+        return pairwise(scores)
+    if kind == "sigmoid":
+        labels = -torch.ones(b, c)
+        labels[idx, pos_idx] = 1.0
+        return F.softplus(-(scores / t) * labels).mean()
+    pos = (q * d[offset : offset + b]).sum(dim=1)
+    negs = torch.einsum("bd,bnd->bn", q, neg)
+    loss = F.softplus((negs - pos.unsqueeze(1)) / t).mean()
+    if in_batch_term_weight > 0:
+        ib = F.cross_entropy(scores / t, pos_idx) if kind == "negce" else pairwise(scores)
+        loss = loss * (1 - in_batch_term_weight) + ib * in_batch_term_weight
+    return loss
+
+
+def similarity_maps_port(image_embeddings: torch.Tensor, query_embeddings: torch.Tensor, n_patches, image_mask: torch.Tensor):
+    """similarity_map_utils.py:29-56 with plain indexing instead of einops: map[n, i, j] = <q_n, patch (row j, column i)>."""
+    maps = []
+    for k in range(image_embeddings.size(0)):
+        w, h = n_patches[k] if isinstance(n_patches, list) else n_patches
+        patches = image_embeddings[k][image_mask[k]]           # (h * w, dim), row-major over (h, w)
+        grid = patches.view(h, w, -1).permute(1, 0, 2)         # (w, h, dim)
+        maps.append(torch.einsum("nk,ijk->nij", query_embeddings[k], grid))
+    return maps
 
 
 # ---------------------------------------------------------------------------------------------

@@ -355,10 +355,80 @@ def wide_dims():
     print("wide_dim320 ok")
 
 
+def bi_small():
+    """Row f-4: the six bi-encoder losses (loss + every gradient), score_single_vector and similarity maps, executed by the
+    reference on fp32 inputs: B=6, C=12, D=40, n_neg=3; offsets 0 and 6."""
+    import importlib.util
+
+    from colpali_engine.loss import bi_encoder_losses as RB
+
+    # the package __init__ imports matplotlib / seaborn (absent here): execute the unmodified module file on its own
+    spec = importlib.util.spec_from_file_location(
+        "ref_similarity_map_utils", "/root/reference/colpali_engine/interpretability/similarity_map_utils.py")
+    smu = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(smu)
+    get_similarity_maps_from_embeddings = smu.get_similarity_maps_from_embeddings
+
+    g = torch.Generator().manual_seed(11)
+    rnd = lambda *sh: torch.nn.functional.normalize(torch.randn(*sh, generator=g), dim=-1)  # noqa: E731
+    q, d, neg = rnd(6, 40), rnd(12, 40), rnd(6, 3, 40)
+    d[:6] = torch.nn.functional.normalize(q + 0.6 * rnd(6, 40), dim=-1)      # positives at offset 0 ...
+    d[6:] = torch.nn.functional.normalize(q + 0.6 * rnd(6, 40), dim=-1)      # ... and at offset 6
+    d[3] = torch.nn.functional.normalize(q[1] + 0.05 * rnd(40), dim=-1)      # a negative above 0.95 x the positive (filter)
+    out = {"q": q.numpy().copy(), "d": d.numpy().copy(), "neg": neg.numpy().copy()}
+    kw_f = dict(pos_aware_negative_filtering=True)
+    cases = (
+        # name, module, docs, negatives?, offset, port kind, port kwargs
+        ("ce", RB.BiEncoderLoss(), d, False, 0, "ce", {}),
+        ("ce_off6_filter", RB.BiEncoderLoss(temperature=0.05, **kw_f), d, False, 6, "ce", dict(temperature=0.05, **kw_f)),
+        ("paired", RB.BiPairedEncoderLoss(), d[:6], False, 0, "paired", {}),
+        ("paired_filter", RB.BiPairedEncoderLoss(temperature=0.1, **kw_f), d[:6], False, 0, "paired", dict(temperature=0.1, **kw_f)),
+        ("pairwise", RB.BiPairwiseCELoss(), d, False, 0, "pairwise", {}),
+        ("pairwise_filter_t1", RB.BiPairwiseCELoss(temperature=1.0, **kw_f), d, False, 0, "pairwise", dict(temperature=1.0, **kw_f)),
+        ("sigmoid", RB.BiSigmoidLoss(), d[:6], False, 0, "sigmoid", {}),
+        ("sigmoid_off6_filter", RB.BiSigmoidLoss(temperature=0.5, **kw_f), d, False, 6, "sigmoid", dict(temperature=0.5, **kw_f)),
+        ("negce", RB.BiNegativeCELoss(), d, True, 6, "negce", {}),
+        ("negce_w0", RB.BiNegativeCELoss(in_batch_term_weight=0.0), d, True, 0, "negce", dict(in_batch_term_weight=0.0)),
+        ("negce_filter", RB.BiNegativeCELoss(temperature=0.1, in_batch_term_weight=0.3, **kw_f), d, True, 0, "negce",
+         dict(temperature=0.1, in_batch_term_weight=0.3, **kw_f)),
+        ("pairneg", RB.BiPairwiseNegativeCELoss(), d, True, 0, "pairneg", {}),
+        ("pairneg_off6", RB.BiPairwiseNegativeCELoss(temperature=0.5, in_batch_term_weight=0.7), d, True, 6, "pairneg",
+         dict(temperature=0.5, in_batch_term_weight=0.7)),
+    )
+    for name, mod, docs, with_neg, off, kind, kw in cases:
+        qq, dd = q.clone().requires_grad_(True), docs.clone().requires_grad_(True)
+        nn = neg.clone().requires_grad_(True) if with_neg else None
+        loss = mod(qq, dd, nn, offset=off) if with_neg else mod(qq, dd, offset=off)
+        loss.backward()
+        out[f"{name}_loss"], out[f"{name}_dq"], out[f"{name}_dd"] = loss.detach().numpy(), qq.grad.numpy(), dd.grad.numpy()
+        if with_neg:
+            out[f"{name}_dn"] = nn.grad.numpy()
+        port = O.bi_loss_port(kind, q, docs, neg if with_neg else None, offset=off, **kw)
+        assert torch.allclose(port, loss.detach(), atol=1e-6, rtol=1e-6), (name, float(port), float(loss))
+    # score_single_vector (processing_utils.py:103-130), fp32 and bf16 operands
+    out["single_f32"] = RefProc.score_single_vector(q, d, device="cpu").numpy()
+    out["single_bf16"] = RefProc.score_single_vector(list(q.bfloat16()), list(d.bfloat16()), device="cpu").numpy()
+    assert torch.equal(O.score_single_vector_port(q, d), torch.from_numpy(out["single_f32"]))
+    # similarity maps (similarity_map_utils.py:9-56): 2 images, 3 x 4 and 2 x 5 patch grids inside 14 / 12 tokens
+    img, qe = rnd(2, 14, 16), rnd(2, 5, 16)
+    mask = torch.zeros(2, 14, dtype=torch.bool)
+    mask[0, 1:13] = True
+    mask[1, [0, 2, 3, 4, 6, 7, 9, 10, 11, 13]] = True
+    n_patches = [(3, 4), (2, 5)]
+    maps = get_similarity_maps_from_embeddings(img, qe, n_patches, mask)
+    port = O.similarity_maps_port(img, qe, n_patches, mask)
+    out["map_img"], out["map_q"], out["map_mask"] = img.numpy().copy(), qe.numpy().copy(), mask.numpy().copy()
+    for k, m in enumerate(maps):
+        assert m.shape == (5, *n_patches[k]) and torch.allclose(port[k], m, atol=1e-6)
+        out[f"map_{k}"] = m.numpy()
+    np.savez_compressed(os.path.join(GOLD, "bi_small.npz"), **out)
+    print("bi_small ok")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
     which = set(sys.argv[1:]) or {"scorer_small", "cfg1", "cfg2", "loss_small", "loss_neg_small", "loss_cfg3", "loss_smooth",
-                                  "head_small", "wide"}
+                                  "head_small", "wide", "bi"}
     if "scorer_small" in which:
         scorer_small()
     if "cfg1" in which:
@@ -377,3 +447,5 @@ if __name__ == "__main__":
         head_small()
     if "wide" in which:
         wide_dims()
+    if "bi" in which:
+        bi_small()

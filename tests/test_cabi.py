@@ -63,7 +63,7 @@ def test_every_entry_point_validates_before_touching_cuda(lib):
     """Bad arguments are rejected with CPB_E_INVALID / CPB_E_UNSUPPORTED and a message, without a GPU."""
     import ctypes
 
-    from colpali_b200._lib import LossDesc, MaxSimArgs, MaxSimBwdArgs
+    from colpali_b200._lib import DenseDotArgs, LossDesc, MaxSimArgs, MaxSimBwdArgs
 
     INVALID, UNSUPPORTED = -1, -2
     err = lib.cpb_last_error
@@ -71,7 +71,10 @@ def test_every_entry_point_validates_before_touching_cuda(lib):
     d = LossDesc(mode=0, temperature=0.02, normalize_scores=1, filter_threshold=0.95, filter_factor=0.5)
 
     def loss(n_q, n_docs, dim=128):
-        return lib.cpb_colbert_loss_launch(ctypes.byref(d), None, None, n_q, 32, n_docs, dim, None)
+        return lib.cpb_colbert_loss_launch(ctypes.byref(d), None, 16, n_q, 32, n_docs, dim, None)  # d_q non-null, never read
+
+    def bi_loss(n_q, n_docs):  # d_q == NULL: scores of single vectors (bi-encoder losses)
+        return lib.cpb_colbert_loss_launch(ctypes.byref(d), None, None, n_q, 0, n_docs, 0, None)
 
     assert loss(4, 3) == INVALID and b"positive index out of range" in err()                    # offset + B > C
     d.mode = 7
@@ -82,8 +85,24 @@ def test_every_entry_point_validates_before_touching_cuda(lib):
     assert loss(4, 4) == INVALID and b"temperature" in err()
     d.temperature = 0.02
     assert loss(4, 4, dim=200) == UNSUPPORTED and b"200" in err()
+    assert bi_loss(4, 4) == INVALID and b"normalize_scores" in err()                            # no query rows to count
+    d.normalize_scores, d.mode = 0, 2
+    assert bi_loss(4, 6) == INVALID and b"multiple of n_queries" in err()                       # BiSigmoidLoss block walk
+    d.mode = 3
+    assert bi_loss(4, 8) == INVALID and b"square" in err()                                      # BiPairedEncoderLoss
+    d.mode = 0
+    assert bi_loss(4, 8) == INVALID and b"null device pointer" in err()                         # valid shape, no buffers
     d.struct_size = 8
     assert loss(4, 4) == INVALID and b"struct_size" in err()
+    # dense dot products
+    dd = DenseDotArgs(m=4, n=0, k=8)
+    assert lib.cpb_dense_dot_launch(ctypes.byref(dd)) == INVALID and b"positive" in err()
+    dd.n = 4
+    assert lib.cpb_dense_dot_launch(ctypes.byref(dd)) == INVALID and b"null device pointer" in err()
+    dd.d_a = dd.d_b = dd.d_out = 16
+    dd.out_row_stride = 2
+    assert lib.cpb_dense_dot_launch(ctypes.byref(dd)) == INVALID and b"out_row_stride" in err()
+    assert lib.cpb_dense_dot_launch(None) == INVALID
     # forward
     a = MaxSimArgs(n_queries=1, nq_pad=32, n_docs=1, dim=128)
     assert lib.cpb_maxsim_launch(ctypes.byref(a)) == INVALID and b"null device pointer" in err()

@@ -31,8 +31,20 @@ def _make_stub(tmp_path):
         class ColbertPairwiseCELoss(ColbertModule): pass
         class ColbertSigmoidLoss(ColbertModule): pass
     """))
+    (root / "loss" / "bi_encoder_losses.py").write_text(textwrap.dedent("""
+        class BiEncoderModule: pass
+        class BiEncoderLoss(BiEncoderModule): pass
+        class BiPairedEncoderLoss(BiEncoderModule): pass
+        class BiSigmoidLoss(BiEncoderModule): pass
+    """))
     (root / "loss" / "__init__.py").write_text(
-        "from .late_interaction_losses import ColbertLoss, ColbertModule, ColbertPairwiseCELoss, ColbertSigmoidLoss\n")
+        "from .late_interaction_losses import ColbertLoss, ColbertModule, ColbertPairwiseCELoss, ColbertSigmoidLoss\n"
+        "from .bi_encoder_losses import BiEncoderLoss, BiEncoderModule, BiSigmoidLoss\n")
+    (root / "interpretability").mkdir()
+    (root / "interpretability" / "similarity_map_utils.py").write_text(
+        "def get_similarity_maps_from_embeddings(*a, **k):\n    return 'reference-maps'\n")
+    (root / "interpretability" / "__init__.py").write_text(
+        "from .similarity_map_utils import get_similarity_maps_from_embeddings\n")
 
 
 def test_install_and_uninstall(tmp_path, monkeypatch):
@@ -40,6 +52,7 @@ def test_install_and_uninstall(tmp_path, monkeypatch):
     monkeypatch.syspath_prepend(str(tmp_path))
     for k in [k for k in sys.modules if k.startswith("colpali_engine")]:
         monkeypatch.delitem(sys.modules, k)
+    import colpali_engine.interpretability as I  # noqa: E741
     import colpali_engine.loss as L
     import colpali_engine.utils.processing_utils as pu
 
@@ -53,10 +66,16 @@ def test_install_and_uninstall(tmp_path, monkeypatch):
         assert L.late_interaction_losses.ColbertLoss is cb.ColbertLoss                   # dotted-path configs resolve to it
         assert L.ColbertSigmoidLoss is cb.ColbertSigmoidLoss
         assert L.ColbertModule is not cb.ColbertModule                                   # the helper base class stays the reference's
-        # score_single_vector (Bi* processors, hidden-size fp32 embeddings) is opt-in
-        assert pu.BaseVisualRetrieverProcessor.score_single_vector(1, 2) == "reference-single"
-        cb.install(single_vector=True)
+        # score_single_vector (Bi* processors, hidden-size fp32 embeddings): the dense fp32 kernel, any dim
         assert pu.BaseVisualRetrieverProcessor.score_single_vector is cb.score_single_vector
+        # bi-encoder losses and the similarity-map helper
+        assert L.BiEncoderLoss is cb.BiEncoderLoss and L.BiSigmoidLoss is cb.BiSigmoidLoss
+        assert L.bi_encoder_losses.BiPairedEncoderLoss is cb.BiPairedEncoderLoss      # not re-exported by the package (loss/__init__.py)
+        assert L.BiEncoderModule is not cb.BiEncoderModule
+        assert I.get_similarity_maps_from_embeddings is cb.get_similarity_maps_from_embeddings
+        assert I.similarity_map_utils.get_similarity_maps_from_embeddings is cb.get_similarity_maps_from_embeddings
+        L.BiEncoderLoss(temperature=0.02, pos_aware_negative_filtering=False, max_batch_size=1024, filter_threshold=0.95,
+                        filter_factor=0.5)
         # constructible with the reference's keyword arguments (scripts/configs/**/*.yaml)
         L.ColbertPairwiseCELoss(temperature=0.02, normalize_scores=True, use_smooth_max=False,
                                 pos_aware_negative_filtering=False, max_batch_size=1024, tau=0.1, norm_tol=1e-3,
@@ -65,3 +84,6 @@ def test_install_and_uninstall(tmp_path, monkeypatch):
         cb.uninstall()
     assert proc.score(1, 2) == "reference-multi"
     assert L.ColbertLoss.__module__.startswith("colpali_engine")
+    assert L.BiEncoderLoss.__module__.startswith("colpali_engine")
+    assert I.get_similarity_maps_from_embeddings() == "reference-maps"
+    assert pu.BaseVisualRetrieverProcessor.score_single_vector(1, 2) == "reference-single"

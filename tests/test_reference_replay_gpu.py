@@ -4,7 +4,8 @@ patched attributes:
 
 * tests/utils/test_processing_utils.py:8-35  (scorer shapes, list == tensor equivalence),
 * tests/loss/test_li_losses.py:75-181        (loss KATs: zero embeddings -> ln B / softplus(0), with/without filtering,
-  explicit negatives with and without the in-batch term).
+  explicit negatives with and without the in-batch term),
+* tests/loss/test_bi_losses.py:42-131        (bi-encoder loss KATs, row f-4).
 
 The reference tests build CPU tensors; the B200 losses have no CPU path, so the loss tests run under
 ``torch.device("cuda")`` as the default device (their tensor factories then allocate on the GPU, nothing else changes).
@@ -62,8 +63,8 @@ def test_reference_scorer_tests_through_the_patch(patched_reference):
     mod = _load("test_processing_utils")
     torch.manual_seed(0)
     mod.test_score_multi_vector_embeddings()   # device=None -> cuda:0, returns CPU fp32 (processing_utils.py:161,180)
-    mod.test_score_single_vector_embeddings()  # not patched by default: the reference's own einsum
-    assert _lib.gpu_launches() - before == 2   # the two score_multi_vector calls ran the fused kernel
+    mod.test_score_single_vector_embeddings()  # patched too: the dense fp32 kernel (any dim, operands keep their dtype)
+    assert _lib.gpu_launches() - before == 4   # two score_multi_vector + two score_single_vector calls
 
 
 def test_reference_loss_kats_through_the_patch(patched_reference):
@@ -84,6 +85,28 @@ def test_reference_loss_kats_through_the_patch(patched_reference):
     assert ran == 7
     assert _lib.gpu_launches() > before
     inst = mod.TestColbertModule()  # the reference's own base class and helpers, untouched by install()
+    for name, fn in inspect.getmembers(inst, inspect.ismethod):
+        if name.startswith("test_"):
+            fn()
+
+
+def test_reference_bi_loss_kats_through_the_patch(patched_reference):
+    from colpali_b200 import _lib
+
+    mod = _load("test_bi_losses")
+    assert mod.BiEncoderLoss is cb.BiEncoderLoss and mod.BiPairwiseNegativeCELoss is cb.BiPairwiseNegativeCELoss
+    before = _lib.gpu_launches()
+    ran = 0
+    with torch.device("cuda"):
+        for cname in ("TestBiEncoderLoss", "TestBiNegativeCELoss", "TestBiPairwiseCELoss", "TestBiPairwiseNegativeCELoss"):
+            inst = getattr(mod, cname)()
+            for name, fn in inspect.getmembers(inst, inspect.ismethod):
+                if name.startswith("test_"):
+                    fn()
+                    ran += 1
+    assert ran == 8
+    assert _lib.gpu_launches() > before
+    inst = mod.TestBiEncoderModule()  # the reference's own base class and helpers, untouched by install()
     for name, fn in inspect.getmembers(inst, inspect.ismethod):
         if name.startswith("test_"):
             fn()
