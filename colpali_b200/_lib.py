@@ -40,6 +40,7 @@ CPB_FLAG_INDEPENDENT = 4
 CPB_FLAG_GRAD_BF16 = 8
 CPB_HEAD_CLAMP_NORM = 1
 CPB_HEAD_SINGLE_ROUNDING = 2
+CPB_TOPK_MAX = 16
 CPB_LOSS_CE = 0
 CPB_LOSS_PAIRWISE = 1
 CPB_LOSS_SIGMOID = 2
@@ -84,6 +85,7 @@ class MaxSimArgs(ctypes.Structure):
         ("d_wait_flags", c_vp), ("n_wait", c_i), ("wait_value", c_u32),
         ("loss", ctypes.POINTER(LossDesc)), ("d_done_counter", c_vp),
         ("grid_out", c_i),
+        ("d_topk_scores", c_vp), ("d_topk_idx", c_vp), ("d_topk_counters", c_vp), ("topk_k", c_i),
     ]
 
     def __init__(self, **kw):

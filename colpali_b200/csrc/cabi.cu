@@ -290,6 +290,8 @@ int cpb_maxsim_launch(cpb_maxsim_args* a) {
   const cpb_loss_desc* loss = CPB_HAS(a, cpb_maxsim_args, loss) ? a->loss : nullptr;
   uint32_t* d_done_counter = CPB_HAS(a, cpb_maxsim_args, d_done_counter) ? a->d_done_counter : nullptr;
 
+  float* d_topk_scores = CPB_HAS(a, cpb_maxsim_args, d_topk_scores) ? a->d_topk_scores : nullptr;
+
   cudaStream_t stream = static_cast<cudaStream_t>(a->stream);
   const int n_queries = a->n_queries, nq_pad = a->nq_pad, n_docs = a->n_docs, dim = a->dim;
   const uint32_t flags = a->flags;
@@ -362,6 +364,16 @@ int cpb_maxsim_launch(cpb_maxsim_args* a) {
     if (rc != CPB_OK) return rc;
     p.done_counter = d_done_counter;
   }
+  if (d_topk_scores) {
+    if (!CPB_HAS(a, cpb_maxsim_args, topk_k) || !a->d_topk_idx || !a->d_topk_counters || a->topk_k < 1 || a->topk_k > CPB_TOPK_MAX)
+      return fail(CPB_E_INVALID, "fused top-k needs d_topk_idx, d_topk_counters and 1 <= topk_k <= %d", CPB_TOPK_MAX);
+    if (dim != 128 || nseg != 1 || !a->d_scores || d_peer_bases || (flags & CPB_FLAG_INDEPENDENT))
+      return fail(CPB_E_UNSUPPORTED, "fused top-k needs dim 128, nq_pad == 32, d_scores, no fused all-gather and no CPB_FLAG_INDEPENDENT");
+    p.topk_scores = d_topk_scores;
+    p.topk_idx = a->d_topk_idx;
+    p.topk_counters = a->d_topk_counters;
+    p.topk_k = a->topk_k;
+  }
   const int mode = smooth ? 2 : (a->d_argmax ? 1 : 0);
   p.pdl = g_opt_pdl.load() ? ((flags & CPB_FLAG_INDEPENDENT) ? 2 : 1) : 0;
   p.boundary_mode = g_opt_boundary_mode.load();
@@ -383,7 +395,7 @@ int cpb_maxsim_launch(cpb_maxsim_args* a) {
     if (opt_cluster == 1 || opt_cluster == 2 || opt_cluster == 4) cluster = opt_cluster;
     // CTA pairs: one M = 256 MMA per two query tiles (one per CTA), half of every document tile per CTA.  Needs every
     // CTA to own all R query tiles and a bank that can be read past the end of a partition (contiguous).
-    bool use_pair = g_opt_pair.load() != 0 && cluster == 2 && (flags & CPB_FLAG_CONTIGUOUS) != 0 &&
+    bool use_pair = g_opt_pair.load() != 0 && cluster == 2 && !d_topk_scores && (flags & CPB_FLAG_CONTIGUOUS) != 0 &&
                     p.num_qtiles % (2 * R) == 0 && !(p.flags & CPB_DBG_NO_TMA);
     int max_clusters = use_pair ? max_clusters_cached(dev, 5 + R, 2) : 0;
     if (max_clusters <= 0) {

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include "loss_body.cuh"
+#include "topk_tail.cuh"
 #include "maxsim_params.h"
 #include "sm100_ptx.cuh"
 
@@ -822,10 +823,13 @@ __device__ __forceinline__ void maxsim_pdl_entry(const MaxSimParams& p) {
 
 // End of the kernel, called by ALL threads of the CTA after their role code: makes the CTA's results visible, signals
 // the fused all-gather's consumers, and lets the last CTA of the grid turn the score matrix into the loss.
-__device__ __forceinline__ void maxsim_finish(const MaxSimParams& p, const LossParams& lp, int cluster, int warp) {
+// `group` / `q_first` / `q_count`: this CTA's query-tile group and its queries, for the fused top-k (0 queries = none).
+__device__ __forceinline__ void maxsim_finish(const MaxSimParams& p, const LossParams& lp, int cluster, int warp,
+                                              int group = 0, int q_first = 0, int q_count = 0) {
   __shared__ int s_last;
   const bool fused_loss = lp.loss != nullptr && p.done_counter != nullptr;
-  if (fused_loss && warp >= 2) __threadfence();  // this warp's score stores are visible device-wide before the count
+  const bool fused_topk = p.topk_scores != nullptr;
+  if ((fused_loss || fused_topk) && warp >= 2) __threadfence();  // this warp's score stores are visible device-wide before the count
   tc_fence_before();
   // no CTA may exit while a peer can still multicast into its shared memory or signal its barriers
   if (cluster > 1) cluster_sync_all(); else __syncthreads();
@@ -854,6 +858,9 @@ __device__ __forceinline__ void maxsim_finish(const MaxSimParams& p, const LossP
       colbert_loss_body(lp);  // reads the [B, C] scores through L2 (__ldcg)
     }
   }
+  if (fused_topk && group < p.q_groups)  // uniform over the CTA (groups past q_groups are cluster padding: no queries)
+    topk_group_tail(p.scores, p.n_docs, p.topk_k, p.topk_scores, p.topk_idx, p.topk_counters, group, p.doc_parts, q_first,
+                    q_count);
 }
 
 }  // namespace cpb

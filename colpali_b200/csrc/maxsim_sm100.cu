@@ -383,7 +383,9 @@ maxsim_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   }
 
   // ---- teardown ---------------------------------------------------------------------------
-  maxsim_finish(p, lp, C, warp);
+  // fused top-k (nq_pad == 32 there): this group's queries are g * R * 4 ... (4 per 128-row query tile)
+  const int tk_q0 = g * R * (kTileM / 32);
+  maxsim_finish(p, lp, C, warp, g, tk_q0, max(0, min(r_cnt * (kTileM / 32), p.n_queries - tk_q0)));
   if ((p.flags & CPB_DBG_CLOCKS) && threadIdx.x == 0) {
     p.scores[2 * blockIdx.x] = static_cast<float>(clock64() - dbg_c0);
     p.scores[2 * blockIdx.x + 1] = static_cast<float>(global_timer_ns() - dbg_t0);

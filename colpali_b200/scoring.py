@@ -218,7 +218,7 @@ def launch_maxsim(q: "QueryBlock", bank: "DocBank", *, scores: Optional[torch.Te
                   lse: Optional[torch.Tensor] = None, round_bf16: bool = False, independent: bool = False,
                   smooth_tau: float = 0.0, nq_real: int = 0, loss: Optional[_lib.LossDesc] = None,
                   done_counter: Optional[torch.Tensor] = None, gather: Optional[dict] = None,
-                  wait: Optional[tuple] = None) -> int:
+                  wait: Optional[tuple] = None, topk: Optional[tuple] = None) -> int:
     """Fill a ``cpb_maxsim_args`` and enqueue the fused kernel on the current stream of ``bank.device``.
     Returns the number of CTAs launched (the fused all-gather's consumers count completions in CTAs)."""
     lib = _lib.load()
@@ -259,6 +259,9 @@ def launch_maxsim(q: "QueryBlock", bank: "DocBank", *, scores: Optional[torch.Te
         if loss is not None:
             a.loss = ctypes.pointer(loss)
             a.d_done_counter = done_counter.data_ptr()
+        if topk is not None:  # (scores [n, k] fp32, idx [n, k] int32, counters, k): selection fused into the kernel's tail
+            a.d_topk_scores, a.d_topk_idx, a.d_topk_counters, a.topk_k = (topk[0].data_ptr(), topk[1].data_ptr(),
+                                                                          topk[2].data_ptr(), int(topk[3]))
         rc = lib.cpb_maxsim_launch(ctypes.byref(a))
     _lib.check(rc, "cpb_maxsim_launch")
     _lib.count_launches(2 if ws is not None else 1)
@@ -276,6 +279,35 @@ def maxsim(q: QueryBlock, bank: DocBank, *, round_bf16: bool = False, want_argma
     argmax = torch.empty(bank.n_docs, q.n * q.nq_pad, dtype=torch.int32, device=dev) if want_argmax else None
     launch_maxsim(q, bank, scores=scores, argmax=argmax, round_bf16=round_bf16, independent=independent)
     return (scores, argmax) if want_argmax else scores
+
+
+_TOPK_COUNTERS: dict = {}
+
+
+def maxsim_topk(q: QueryBlock, bank: DocBank, k: int, *, round_bf16: bool = False):
+    """Scores AND the per-query top-``k`` in ONE launch: the last CTA of every query-tile group selects the ``k`` best
+    documents of its queries from the score rows still in L2 (csrc/topk_tail.cuh) -- larger score first, smaller document
+    index on ties.  Returns ``(scores [n, n_docs] fp32, top_scores [n, k'] fp32, top_idx [n, k'] int64)`` with
+    ``k' = min(k, n_docs)``.  ``fused_topk_supported`` tells whether this shape can take the fused path."""
+    if not fused_topk_supported(q, bank, k):
+        raise _lib.ColpaliB200Error("fused top-k needs dim 128, queries of at most 32 tokens and k <= %d" % _lib.CPB_TOPK_MAX)
+    dev = bank.device
+    key = (str(dev), torch.cuda.current_stream(dev).cuda_stream)
+    words = (q.n * q.nq_pad + 127) // 128
+    ctr = _TOPK_COUNTERS.get(key)
+    if ctr is None or ctr.numel() < words:
+        ctr = torch.zeros(max(words, 64), dtype=torch.int32, device=dev)  # zero once; the kernel resets what it used
+        _TOPK_COUNTERS[key] = ctr
+    scores = torch.empty(q.n, bank.n_docs, dtype=torch.float32, device=dev)
+    top_s = torch.empty(q.n, k, dtype=torch.float32, device=dev)
+    top_i = torch.empty(q.n, k, dtype=torch.int32, device=dev)
+    launch_maxsim(q, bank, scores=scores, round_bf16=round_bf16, topk=(top_s, top_i, ctr, k))
+    kk = min(k, bank.n_docs)
+    return scores, top_s[:, :kk], top_i[:, :kk].to(torch.int64)
+
+
+def fused_topk_supported(q: QueryBlock, bank: DocBank, k: int) -> bool:
+    return 1 <= k <= _lib.CPB_TOPK_MAX and q.nq_pad == 32 and int(bank.flat.shape[1]) == EMBED_DIM
 
 
 def score_multi_vector(

@@ -8,7 +8,9 @@ one all-gather of per-shard results over NVLink:
 * full slabs  -- every rank contributes its ``[n_queries, n_local]`` fp32 scores (padded to the largest shard
                  with -inf), all ranks end with ``[n_queries, n_docs_total]``;
 * top-k       -- every rank contributes its local top-k ``(score, global doc id)`` per query (KBs), all ranks
-                 merge to the global top-k.  Ties are broken by the smaller document id, deterministically.
+                 merge to the global top-k.  Ties are broken by the smaller document id, deterministically.  The local
+                 selection is fused into the scoring kernel's tail (``scoring.maxsim_topk``, csrc/topk_tail.cuh) for
+                 k <= 16, dim 128 and queries of at most 32 tokens; ``torch.topk`` on the slab otherwise.
 
 ``local_scorer`` is the function that scores the local shard; it defaults to the fused sm_100a kernel and exists
 so the host-side logic (sharding, padding, id offsets, merge) can be exercised under ``gloo`` on CPU in tests.
@@ -37,6 +39,23 @@ def _default_local_scorer(qs, bank) -> torch.Tensor:
     from .scoring import QueryBlock, maxsim
 
     return maxsim(QueryBlock(qs, bank.device), bank)
+
+
+def _local_topk(qs, bank, k: int, scorer: Optional[Callable]) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(scores [n_q, k'], local document index [n_q, k'] int64, n_local), k' = min(k, n_local); order: score desc, index asc."""
+    if scorer is None:
+        from .scoring import QueryBlock, fused_topk_supported, maxsim_topk
+
+        q = QueryBlock(qs, bank.device)
+        if fused_topk_supported(q, bank, k):
+            _, s, i = maxsim_topk(q, bank, k)
+            return s, i, bank.n_docs
+        local = _default_local_scorer(qs, bank)
+    else:
+        local = scorer(qs, bank).to(torch.float32)
+    n_local = local.shape[1]
+    ids = torch.arange(n_local, device=local.device).expand(local.shape[0], n_local)
+    return (*merge_topk(local, ids, min(k, n_local)), n_local)
 
 
 def _world(group) -> Tuple[int, int]:
@@ -72,14 +91,15 @@ def score_sharded(
     ``(scores [n_queries, k], doc_ids [n_queries, k])`` -- identical on every rank.
     """
     rank, world = _world(group)
-    scorer = local_scorer or _default_local_scorer
-    local = scorer(qs, local_bank).to(torch.float32)
-    nq, n_local = local.shape
+    if top_k is not None:
+        top_k = min(top_k, n_docs_total)  # never return (-inf, INT64_MAX) filler candidates
+        s, i, n_local = _local_topk(qs, local_bank, top_k, local_scorer)
+        nq, dev = s.shape[0], s.device
+    else:
+        local = (local_scorer or _default_local_scorer)(qs, local_bank).to(torch.float32)
+        nq, n_local = local.shape
     if world == 1:
-        if top_k is None:
-            return local
-        ids = torch.arange(doc_offset, doc_offset + n_local, device=local.device).expand(nq, n_local)
-        return merge_topk(local, ids, top_k)
+        return local if top_k is None else (s, i + doc_offset)
 
     bounds = shard_bounds(n_docs_total, world)
     if (doc_offset, doc_offset + n_local) != bounds[rank]:
@@ -93,15 +113,13 @@ def score_sharded(
         dist.all_gather_into_tensor(gathered.view(world * nq, width), slab, group=group)
         return torch.cat([gathered[r, :, : hi - lo] for r, (lo, hi) in enumerate(bounds)], dim=1)
 
-    top_k = min(top_k, n_docs_total)  # never return (-inf, INT64_MAX) filler candidates
-    k_local = min(top_k, n_local)
-    s, i = torch.topk(local, k_local, dim=1)
-    cand_s = torch.full((nq, top_k), float("-inf"), dtype=torch.float32, device=local.device)
-    cand_i = torch.full((nq, top_k), torch.iinfo(torch.int64).max, dtype=torch.int64, device=local.device)
+    k_local = s.shape[1]
+    cand_s = torch.full((nq, top_k), float("-inf"), dtype=torch.float32, device=dev)
+    cand_i = torch.full((nq, top_k), torch.iinfo(torch.int64).max, dtype=torch.int64, device=dev)
     cand_s[:, :k_local] = s
     cand_i[:, :k_local] = i + doc_offset
-    all_s = torch.empty(world, nq, top_k, dtype=torch.float32, device=local.device)
-    all_i = torch.empty(world, nq, top_k, dtype=torch.int64, device=local.device)
+    all_s = torch.empty(world, nq, top_k, dtype=torch.float32, device=dev)
+    all_i = torch.empty(world, nq, top_k, dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(all_s.view(world * nq, top_k), cand_s, group=group)
     dist.all_gather_into_tensor(all_i.view(world * nq, top_k), cand_i, group=group)
     return merge_topk(all_s.permute(1, 0, 2).reshape(nq, world * top_k), all_i.permute(1, 0, 2).reshape(nq, world * top_k), top_k)

@@ -192,7 +192,17 @@ typedef struct cpb_maxsim_args {
   uint32_t* d_done_counter;     /* device uint32, zero before the first launch (the kernel resets it), needed with `loss` */
   /* written by the call */
   int32_t grid_out;             /* CTAs launched */
+  /* top-k selection fused into the kernel's tail (the sharded scorer's local top-k; replaces torch.topk on the
+     [n_queries, n_docs] slab): the last CTA of every query-tile group selects, per query, the topk_k best documents from
+     the score rows still in L2 -- larger score first, smaller document index on ties; fewer than topk_k documents leave
+     (-inf, INT32_MAX) filler.  Needs dim 128, nq_pad == 32, d_scores, no CPB_FLAG_INDEPENDENT. */
+  float* d_topk_scores;         /* fp32 [n_queries, topk_k] out, or NULL */
+  int32_t* d_topk_idx;          /* int32 [n_queries, topk_k] out: document index in this bank */
+  uint32_t* d_topk_counters;    /* ceil(n_queries * nq_pad / 128) device words, zero before the first launch (the kernel
+                                   resets them); not shared by launches that can overlap */
+  int32_t topk_k;               /* 1 .. CPB_TOPK_MAX */
 } cpb_maxsim_args;
+#define CPB_TOPK_MAX 16
 
 int cpb_maxsim_launch(cpb_maxsim_args* args);
 

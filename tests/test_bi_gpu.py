@@ -52,7 +52,7 @@ def test_losses_at_training_shapes_against_the_port(kind, dtype, shape):
     g = torch.Generator().manual_seed(b + c)
     unit = lambda *sh: torch.nn.functional.normalize(torch.randn(*sh, generator=g), dim=-1)  # noqa: E731
     q, d = unit(b, dim), unit(c, dim)
-    d[off : off + b] = torch.nn.functional.normalize(q + 0.8 * unit(b, dim), dim=-1)
+    d[off : off + b] = torch.nn.functional.normalize(q + 3.0 * unit(b, dim), dim=-1)  # cos ~ 0.3: softmax not saturated
     neg = unit(b, 5, dim) if kind in ("negce", "pairneg") else None
     q, d = q.to(dtype), d.to(dtype)
     neg = neg.to(dtype) if neg is not None else None
@@ -65,8 +65,8 @@ def test_losses_at_training_shapes_against_the_port(kind, dtype, shape):
     nf = neg.float().requires_grad_(True) if neg is not None else None
     want = O.bi_loss_port(kind, qf, df, nf, offset=off, **kw)
     want.backward()
-    assert abs(float(loss) - float(want)) < 1e-4 * max(1.0, abs(float(want))), (float(loss), float(want))
-    tol = 1e-2 if dtype == torch.bfloat16 else 1e-4  # gradients are returned in the embedding dtype
+    assert abs(float(loss) - float(want.detach())) < 1e-4 * max(1.0, abs(float(want.detach()))), (float(loss), float(want.detach()))
+    tol = 1e-2 if dtype == torch.bfloat16 else 2e-4  # gradients are returned in the embedding dtype
     for got, ref in ((dq, qf.grad), (dd, df.grad), (dn, nf.grad if nf is not None else None)):
         if got is None:
             continue
