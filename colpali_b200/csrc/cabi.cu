@@ -671,9 +671,14 @@ int cpb_head_fwd(const void* d_hidden, int64_t n_tokens, int hidden, const void*
     CPB_CUDA(cpb::head_wide_launch(th, tw, p, grid, static_cast<cudaStream_t>(stream_)));
     return CPB_OK;
   }
-  const int64_t pairs = (n_tokens + 255) / 256;
-  const int grid = static_cast<int>(pairs < di.sm_count ? pairs : di.sm_count);
-  CPB_CUDA(cpb::head_launch(th, tw, p, grid, static_cast<cudaStream_t>(stream_)));
+  // one CTA per SM, each an equal share of the 64-token units (at least two units = one tile per CTA)
+  CUtensorMap th64;
+  rc = make_bf16_rowmajor_map(&th64, d_hidden, n_tokens, hidden, 64);
+  if (rc != CPB_OK) return rc;
+  const int64_t units = (n_tokens + 63) / 64;
+  const int64_t want = (units + 1) / 2;
+  const int grid = static_cast<int>(want < di.sm_count ? want : di.sm_count);
+  CPB_CUDA(cpb::head_launch(th, th64, tw, p, grid, static_cast<cudaStream_t>(stream_)));
   return CPB_OK;
 }
 

@@ -19,7 +19,9 @@ struct HeadParams {
   int dim, stages, cluster;
 };
 
-cudaError_t head_launch(const CUtensorMap& th, const CUtensorMap& tw, const HeadParams& p, int grid, cudaStream_t stream);
+// th / th64: the hidden states with 128-row and 64-row boxes (a CTA's share may end in half a tile)
+cudaError_t head_launch(const CUtensorMap& th, const CUtensorMap& th64, const CUtensorMap& tw, const HeadParams& p, int grid,
+                        cudaStream_t stream);
 int head_wide_stages(int dim);  // 0: does not fit
 cudaError_t head_wide_launch(const CUtensorMap& th, const CUtensorMap& tw, const HeadParams& p, int grid, cudaStream_t stream);
 

@@ -10,6 +10,10 @@
 // HBM-bound (AI ~ 118 FLOP/B at H = 1536): the design goal is to stream h at HBM rate.
 //   * tokens on M (TMEM lanes), the 128 output dims on N, K = hidden size in blocks of 64.
 //   * a CTA works on PAIRS of 128-token tiles so that every 16 KiB block of W fetched from L2 is used twice.
+//   * the token range is cut into equal shares of 64-token UNITS per CTA (one contiguous range each), not into whole
+//     pairs: 65 920 tokens are 258 pairs = 1.74 rounds of 148 CTAs, i.e. 2 rounds (0.68 of the HBM peak measured), but
+//     1030 units = 6.96 per CTA; a range that ends in half a tile loads 64 rows (its own TMA box) and multiplies a
+//     128-row tile whose upper half is stale -- wasted tensor work is free in an HBM-bound kernel, wasted bytes are not.
 //   * 4-stage TMA ring (2 x 16 KiB of h + 16 KiB of W per stage), tcgen05.mma 128x128x16 into two pairs of
 //     128-column fp32 accumulators (ping-pong across token-tile pairs), 4 epilogue warps.
 //   * epilogue: one thread owns one token row (128 fp32 in registers): bias, the reference's three bf16
@@ -43,11 +47,13 @@ struct HeadSmem {
   static constexpr int kAlloc = kBytes + 1024;
 };
 
+__device__ __forceinline__ int64_t imin64(int64_t a, int64_t b) { return a < b ? a : b; }
+__device__ __forceinline__ int64_t imax64(int64_t a, int64_t b) { return a > b ? a : b; }
 __device__ __forceinline__ float rbf(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 __global__ void __launch_bounds__(kHThreads, 1)
-head_fwd_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant__ CUtensorMap tmap_w,
-                const HeadParams p) {
+head_fwd_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant__ CUtensorMap tmap_h64,
+                const __grid_constant__ CUtensorMap tmap_w, const HeadParams p) {
   using L = HeadSmem;
   constexpr int S = kHStages;
   extern __shared__ uint8_t smem_raw[];
@@ -62,12 +68,16 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = p.hidden / kHBK;
-  const int64_t num_pairs = (p.n_tokens + 2 * kHBM - 1) / (2 * kHBM);
+  // this CTA's tokens [t_begin, t_end): an equal share of the 64-token units; walked in steps of 256 rows (a pair)
+  const int64_t units = (p.n_tokens + 63) / 64;
+  const int64_t t_begin = 64 * ((units * blockIdx.x) / gridDim.x);
+  const int64_t t_end = imin64(p.n_tokens, 64 * ((units * (static_cast<int64_t>(blockIdx.x) + 1)) / gridDim.x));
 
   if (threadIdx.x < kHDim)
     s_bias[threadIdx.x] = p.bias ? __bfloat162float(p.bias[threadIdx.x]) : 0.f;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_h);
+    tma_prefetch_desc(&tmap_h64);
     tma_prefetch_desc(&tmap_w);
     for (int s = 0; s < S; ++s) {
       mbar_init(&full[s], 1);
@@ -92,14 +102,20 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constan
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int64_t pi = blockIdx.x; pi < num_pairs; pi += gridDim.x) {
-        const int row0 = static_cast<int>(pi * 2 * kHBM);
+      for (int64_t row = t_begin; row < t_end; row += 2 * kHBM) {
+        const int row0 = static_cast<int>(row);
+        // rows of the two tiles that belong to this CTA: 128 or 64 (0 for an absent second tile); a tile of at most 64
+        // rows is fetched with the 64-row box so that no byte of the neighbour's range is read twice
+        const int n0 = static_cast<int>(imin64(kHBM, t_end - row));
+        const int n1 = static_cast<int>(imax64(0, imin64(kHBM, t_end - row - kHBM)));
+        const uint32_t bytes = kHTileBytes + (n0 > 64 ? kHTileBytes : kHTileBytes / 2) +
+                               (n1 > 64 ? kHTileBytes : (n1 > 0 ? kHTileBytes / 2 : 0));
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1u);
-          mbar_expect_tx(&full[stage], kHStageBytes);
+          mbar_expect_tx(&full[stage], bytes);
           uint8_t* dst = smem + stage * kHStageBytes;
-          tma_load_2d(dst, &tmap_h, kb * kHBK, row0, &full[stage]);
-          tma_load_2d(dst + kHTileBytes, &tmap_h, kb * kHBK, row0 + kHBM, &full[stage]);
+          tma_load_2d(dst, n0 > 64 ? &tmap_h : &tmap_h64, kb * kHBK, row0, &full[stage]);
+          if (n1 > 0) tma_load_2d(dst + kHTileBytes, n1 > 64 ? &tmap_h : &tmap_h64, kb * kHBK, row0 + kHBM, &full[stage]);
           tma_load_2d(dst + 2 * kHTileBytes, &tmap_w, kb * kHBK, 0, &full[stage]);
           if (++stage == S) {
             stage = 0;
@@ -115,8 +131,9 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       uint32_t it = 0;
-      for (int64_t pi = blockIdx.x; pi < num_pairs; pi += gridDim.x, ++it) {
+      for (int64_t row = t_begin; row < t_end; row += 2 * kHBM, ++it) {
         const uint32_t a = it & 1u;
+        const int n_tiles = (t_end - row > kHBM) ? 2 : 1;
         mbar_wait(&tmem_empty[a], ((it >> 1) & 1u) ^ 1u);
         tc_fence_after();
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -125,6 +142,7 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constan
           const uint32_t base = s_addr + stage * kHStageBytes;
 #pragma unroll
           for (int r = 0; r < 2; ++r) {
+            if (r >= n_tiles) break;  // (rows past a tile's share are stale shared memory: computed, never stored)
 #pragma unroll
             for (int k = 0; k < kHBK / 16; ++k) {
               const uint64_t adesc = make_sw128_kmajor_desc(base + r * kHTileBytes) + static_cast<uint64_t>(k * 2);
@@ -147,13 +165,14 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constan
     const bool single = (p.flags & CPB_HEAD_SINGLE_ROUNDING) != 0;
     const bool clamp = (p.flags & CPB_HEAD_CLAMP_NORM) != 0;
     uint32_t it = 0;
-    for (int64_t pi = blockIdx.x; pi < num_pairs; pi += gridDim.x, ++it) {
+    for (int64_t prow = t_begin; prow < t_end; prow += 2 * kHBM, ++it) {
       const uint32_t a = it & 1u;
+      const int n_tiles = (t_end - prow > kHBM) ? 2 : 1;
       mbar_wait(&tmem_full[a], (it >> 1) & 1u);
       tc_fence_after();
 #pragma unroll 1
-      for (int r = 0; r < 2; ++r) {
-        const int64_t row = pi * 2 * kHBM + r * kHBM + quad * 32 + lane;
+      for (int r = 0; r < n_tiles; ++r) {
+        const int64_t row = prow + r * kHBM + quad * 32 + lane;
         const uint32_t taddr = tmem_base + lane_base + (a * 2 + r) * kHDim;
         uint32_t v0[32], v1[32], v2[32], v3[32];
         tmem_ld_x32(taddr, v0);
@@ -165,7 +184,7 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constan
         reg_fence32(v1);
         reg_fence32(v2);
         reg_fence32(v3);
-        if (r == 1) {  // both tiles of this accumulator pair are now in registers
+        if (r == n_tiles - 1) {  // every tile of this accumulator pair is now in registers
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty[a]);
@@ -188,11 +207,11 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constan
         if (!single) nrm = rbf(nrm);      // proj.norm(...) is a bf16 tensor           (:68)
         if (clamp) nrm = fmaxf(nrm, 1e-12f);
         float mk = 1.f;
-        if (row < p.n_tokens) {
+        if (row < t_end) {
           if (p.attention_mask) mk = static_cast<float>(p.attention_mask[row]);        // (:69)
           if (p.extra_mask) mk *= (p.extra_mask[row] != 0) ? 1.f : 0.f;                // (:71-74)
         }
-        if (row < p.n_tokens) {
+        if (row < t_end) {  // rows past this CTA's share belong to the next CTA (or lie past the last token)
           uint4* dst = reinterpret_cast<uint4*>(p.out + row * kHDim);
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -222,10 +241,11 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constan
   }
 }
 
-cudaError_t head_launch(const CUtensorMap& th, const CUtensorMap& tw, const HeadParams& p, int grid, cudaStream_t stream) {
+cudaError_t head_launch(const CUtensorMap& th, const CUtensorMap& th64, const CUtensorMap& tw, const HeadParams& p, int grid,
+                        cudaStream_t stream) {
   cudaError_t e = cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HeadSmem::kAlloc);
   if (e != cudaSuccess) return e;
-  head_fwd_kernel<<<grid, kHThreads, HeadSmem::kAlloc, stream>>>(th, tw, p);
+  head_fwd_kernel<<<grid, kHThreads, HeadSmem::kAlloc, stream>>>(th, th64, tw, p);
   return cudaGetLastError();
 }
 

@@ -32,7 +32,11 @@ def test_reference_model_forward_golden():
     assert ((rows - 1).abs() < 8e-3).all()
 
 
-@pytest.mark.parametrize("tokens,hidden", [(5000, 1536), (777, 2048), (256, 64)])
+@pytest.mark.parametrize("tokens,hidden", [
+    (5000, 1536), (777, 2048), (256, 64),
+    # shares of 64-token units per CTA: 6 or 7 units (three tiles + half a tile), 4 or 5, a single short tile, 64 + 1 rows
+    (65920, 256), (38000, 512), (63, 64), (65, 128), (129, 64),
+])
 def test_production_widths_against_oracle(tokens, hidden):
     gen = torch.Generator().manual_seed(hidden)
     h = (torch.randn(tokens, hidden, generator=gen) * 2).bfloat16()
