@@ -26,15 +26,51 @@ def cuda_time(fn, n=20, warm=3):
     return e0.elapsed_time(e1) / n
 
 
+def graph_time(fn, n=20, reps=5):
+    """GPU time per call from CUDA-graph replays of n calls (no host launch path between the kernels)."""
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        for _ in range(3): fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(n): fn()
+    g.replay(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): g.replay()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / (n * reps)
+
+
+def interleaved(fns, rounds=12, per=4):
+    """Median over rounds of each variant's time, the variants taking turns inside every round (the SM clock drifts by
+    several percent within seconds: blocks measured one after the other are not comparable)."""
+    for f in fns:
+        for _ in range(2): f()
+    torch.cuda.synchronize()
+    ts = [[] for _ in fns]
+    for _ in range(rounds):
+        for i, f in enumerate(fns):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(per): f()
+            e1.record(); torch.cuda.synchronize()
+            ts[i].append(e0.elapsed_time(e1) / per)
+    return [sorted(t)[len(t) // 2] for t in ts]
+
+
 which = set(sys.argv[1:]) or {"head", "topk", "bi"}
 if "head" in which:
     for tokens, hidden in ((275 * 1000, 1536), (1030 * 64, 2048), (1030 * 64, 1536), (34125, 1536)):
         h = torch.randn(tokens, hidden, device=dev).bfloat16()
         lin = torch.nn.Linear(hidden, 128).to(dev, torch.bfloat16)
         mask = torch.ones(tokens, dtype=torch.long, device=dev)
-        t = cuda_time(lambda: cb.fused_head(h, lin.weight, lin.bias, mask), n=50, warm=5)
+        t_host = cuda_time(lambda: cb.fused_head(h, lin.weight, lin.bias, mask), n=50, warm=5)
+        t = graph_time(lambda: cb.fused_head(h, lin.weight, lin.bias, mask))
         bytes_alg = 2 * tokens * (hidden + 128) + 2 * hidden * 128
-        print(json.dumps({"what": f"fused_head T={tokens} H={hidden} (64-token unit shares)", "ms": t, "gbs": bytes_alg / t / 1e6,
+        print(json.dumps({"what": f"fused_head T={tokens} H={hidden} (64-token unit shares)", "gpu_ms_graph": t,
+                          "ms_with_python_launch_path": t_host, "gbs": bytes_alg / t / 1e6,
                           "frac_hbm": bytes_alg / t / 1e6 / PEAK_HBM, "tokens_per_s": tokens / t * 1e3}), flush=True)
         del h
 
@@ -44,9 +80,8 @@ if "topk" in which:
     for n_q, n_docs in ((128, 12500), (32, 1000)):
         qs, ps = unit(n_q, 32, 128), unit(n_docs, 1030, 128)
         q, bank = QueryBlock(qs, dev), DocBank.from_passages(ps, dev)
-        t0 = cuda_time(lambda: maxsim(q, bank), n=10)
-        t1 = cuda_time(lambda: maxsim_topk(q, bank, 10), n=10)
-        t2 = cuda_time(lambda: torch.topk(maxsim(q, bank), 10, dim=1), n=10)
+        t0, t1, t2 = interleaved([lambda: maxsim(q, bank), lambda: maxsim_topk(q, bank, 10),
+                                  lambda: torch.topk(maxsim(q, bank), 10, dim=1)])
         print(json.dumps({"what": f"local top-10 of {n_q} q x {n_docs} docs x 1030 x 128", "scores_only_ms": t0,
                           "fused_topk_ms": t1, "scores_then_torch_topk_ms": t2, "tail_us": (t1 - t0) * 1e3,
                           "torch_topk_us": (t2 - t0) * 1e3}), flush=True)
