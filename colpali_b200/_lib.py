@@ -25,6 +25,7 @@ EXPORTED_SYMBOLS = (
     "cpb_maxsim_fwd",
     "cpb_maxsim_workspace_bytes",
     "cpb_maxsim_split_workspace_bytes",
+    "cpb_maxsim_topk_workspace_bytes",
     "cpb_wait_flags",
     "cpb_maxsim_bwd_launch",
     "cpb_exchange_push",
@@ -85,7 +86,7 @@ class MaxSimArgs(ctypes.Structure):
         ("d_wait_flags", c_vp), ("n_wait", c_i), ("wait_value", c_u32),
         ("loss", ctypes.POINTER(LossDesc)), ("d_done_counter", c_vp),
         ("grid_out", c_i),
-        ("d_topk_scores", c_vp), ("d_topk_idx", c_vp), ("d_topk_counters", c_vp), ("topk_k", c_i),
+        ("d_topk_scores", c_vp), ("d_topk_idx", c_vp), ("d_topk_ws", c_vp), ("topk_k", c_i),
     ]
 
     def __init__(self, **kw):
@@ -176,6 +177,8 @@ def load() -> ctypes.CDLL:
     lib.cpb_maxsim_workspace_bytes.argtypes = [ci, ci, ci]
     lib.cpb_maxsim_split_workspace_bytes.restype = c_i64
     lib.cpb_maxsim_split_workspace_bytes.argtypes = [ci, ci]
+    lib.cpb_maxsim_topk_workspace_bytes.restype = c_i64
+    lib.cpb_maxsim_topk_workspace_bytes.argtypes = []
     lib.cpb_maxsim_launch.restype = ci
     lib.cpb_maxsim_launch.argtypes = [ctypes.POINTER(MaxSimArgs)]
     lib.cpb_maxsim_fwd.restype = ci

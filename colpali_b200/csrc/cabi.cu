@@ -23,6 +23,8 @@ cudaError_t maxsim_launch(const CUtensorMap& tq, const CUtensorMap& td, const CU
                           const LossParams& lp, int r, int mode, int grid, cudaStream_t stream);
 int maxsim_max_clusters(int r, int cluster);
 int maxsim_tile_n();
+int64_t maxsim_topk_workspace_bytes();
+int maxsim_topk_slots();
 cudaError_t maxsim_kpipe_launch(const CUtensorMap& tq, const CUtensorMap& td, const CUtensorMap& tt, const MaxSimParams& p,
                                 const LossParams& lp, int dim_panels, int mode, int grid, cudaStream_t stream);
 int maxsim_kpipe_max_clusters(int dim_panels, int cluster);
@@ -271,6 +273,8 @@ int64_t cpb_maxsim_split_workspace_bytes(int n_queries, int nq_pad) {
   return groups * 160 * 2 * (128 * 8 + 16);
 }
 
+int64_t cpb_maxsim_topk_workspace_bytes(void) { return cpb::maxsim_topk_workspace_bytes(); }
+
 int cpb_maxsim_launch(cpb_maxsim_args* a) {
   if (!a || a->struct_size < offsetof(cpb_maxsim_args, d_workspace) + sizeof(float*))
     return fail(CPB_E_INVALID, "cpb_maxsim_args is null or its struct_size is too small");
@@ -365,13 +369,13 @@ int cpb_maxsim_launch(cpb_maxsim_args* a) {
     p.done_counter = d_done_counter;
   }
   if (d_topk_scores) {
-    if (!CPB_HAS(a, cpb_maxsim_args, topk_k) || !a->d_topk_idx || !a->d_topk_counters || a->topk_k < 1 || a->topk_k > CPB_TOPK_MAX)
-      return fail(CPB_E_INVALID, "fused top-k needs d_topk_idx, d_topk_counters and 1 <= topk_k <= %d", CPB_TOPK_MAX);
+    if (!CPB_HAS(a, cpb_maxsim_args, topk_k) || !a->d_topk_idx || !a->d_topk_ws || a->topk_k < 1 || a->topk_k > CPB_TOPK_MAX)
+      return fail(CPB_E_INVALID, "fused top-k needs d_topk_idx, d_topk_ws and 1 <= topk_k <= %d", CPB_TOPK_MAX);
     if (dim != 128 || nseg != 1 || !a->d_scores || d_peer_bases || (flags & CPB_FLAG_INDEPENDENT))
       return fail(CPB_E_UNSUPPORTED, "fused top-k needs dim 128, nq_pad == 32, d_scores, no fused all-gather and no CPB_FLAG_INDEPENDENT");
     p.topk_scores = d_topk_scores;
     p.topk_idx = a->d_topk_idx;
-    p.topk_counters = a->d_topk_counters;
+    p.topk_ws = a->d_topk_ws;
     p.topk_k = a->topk_k;
   }
   const int mode = smooth ? 2 : (a->d_argmax ? 1 : 0);
@@ -439,6 +443,8 @@ int cpb_maxsim_launch(cpb_maxsim_args* a) {
     }
     p.doc_parts = parts;
     grid = p.group_sets * p.doc_parts * cluster;
+    if (d_topk_scores && (grid > cpb::maxsim_topk_slots() || R * 4 > 8))
+      return fail(CPB_E_UNSUPPORTED, "fused top-k: grid of %d CTAs exceeds the candidate workspace", grid);
     rc = make_bf16_rowmajor_map(&tq, a->d_q, q_rows64, 128, 128);
     if (rc != CPB_OK) return rc;
     rc = make_bf16_rowmajor_map(&td, a->d_docs, a->doc_rows, 128, cpb::maxsim_tile_n() / cluster);

@@ -10,9 +10,9 @@
 #include <cuda_runtime.h>
 
 #include "loss_body.cuh"
-#include "topk_tail.cuh"
 #include "maxsim_params.h"
 #include "sm100_ptx.cuh"
+#include "topk_tail.cuh"
 
 namespace cpb {
 
@@ -823,9 +823,9 @@ __device__ __forceinline__ void maxsim_pdl_entry(const MaxSimParams& p) {
 
 // End of the kernel, called by ALL threads of the CTA after their role code: makes the CTA's results visible, signals
 // the fused all-gather's consumers, and lets the last CTA of the grid turn the score matrix into the loss.
-// `group` / `q_first` / `q_count`: this CTA's query-tile group and its queries, for the fused top-k (0 queries = none).
+// `group` / `part` / `q_first` / `q_count`: this CTA's query-tile group, document partition and queries (fused top-k).
 __device__ __forceinline__ void maxsim_finish(const MaxSimParams& p, const LossParams& lp, int cluster, int warp,
-                                              int group = 0, int q_first = 0, int q_count = 0) {
+                                              int group = 0, int part = 0, int q_first = 0, int q_count = 0) {
   __shared__ int s_last;
   const bool fused_loss = lp.loss != nullptr && p.done_counter != nullptr;
   const bool fused_topk = p.topk_scores != nullptr;
@@ -859,8 +859,8 @@ __device__ __forceinline__ void maxsim_finish(const MaxSimParams& p, const LossP
     }
   }
   if (fused_topk && group < p.q_groups)  // uniform over the CTA (groups past q_groups are cluster padding: no queries)
-    topk_group_tail(p.scores, p.n_docs, p.topk_k, p.topk_scores, p.topk_idx, p.topk_counters, group, p.doc_parts, q_first,
-                    q_count);
+    topk_group_tail(p.scores, p.n_docs, p.topk_k, p.topk_scores, p.topk_idx, p.topk_ws, group, part, p.doc_parts, q_first,
+                    q_count, static_cast<uint64_t>(p.wait_timeout_ms) * 1000000ull);
 }
 
 }  // namespace cpb

@@ -57,10 +57,10 @@ struct MaxSimParams {
   uint32_t wait_timeout_ms;
   // fused loss: the last CTA to finish (this counter, reset by it) turns the score matrix into the loss + gradient
   uint32_t* done_counter;       // local device word, zero before the first launch
-  // fused top-k (topk_tail.cuh): the last CTA of every query-tile group selects the k best documents of its queries
+  // fused top-k (topk_tail.cuh): the CTAs of every query-tile group select the k best documents of its queries
   float* topk_scores;           // [n_queries, topk_k] or nullptr
   int32_t* topk_idx;            // [n_queries, topk_k] document index inside this bank
-  uint32_t* topk_counters;      // [q_groups (padded to the cluster size)] local device words, zero before the first launch
+  void* topk_ws;                // kTopkWorkspaceBytes: group counters (zero before the first launch) + candidate lists
   int topk_k;                   // 1 .. kTopkMax
   // smooth-max aggregation (late_interaction_losses.py:40-44): tau * logsumexp(raw / tau) instead of the max
   float smooth_c;               // log2(e) / tau (0 = hard max)

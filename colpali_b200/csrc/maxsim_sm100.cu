@@ -385,7 +385,7 @@ maxsim_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   // ---- teardown ---------------------------------------------------------------------------
   // fused top-k (nq_pad == 32 there): this group's queries are g * R * 4 ... (4 per 128-row query tile)
   const int tk_q0 = g * R * (kTileM / 32);
-  maxsim_finish(p, lp, C, warp, g, tk_q0, max(0, min(r_cnt * (kTileM / 32), p.n_queries - tk_q0)));
+  maxsim_finish(p, lp, C, warp, g, part, tk_q0, max(0, min(r_cnt * (kTileM / 32), p.n_queries - tk_q0)));
   if ((p.flags & CPB_DBG_CLOCKS) && threadIdx.x == 0) {
     p.scores[2 * blockIdx.x] = static_cast<float>(clock64() - dbg_c0);
     p.scores[2 * blockIdx.x + 1] = static_cast<float>(global_timer_ns() - dbg_t0);
@@ -503,6 +503,8 @@ int maxsim_max_clusters(int r, int cluster) {
   return r == 1 ? max_clusters_variant<1>(cluster) : max_clusters_variant<2>(cluster);
 }
 
+int64_t maxsim_topk_workspace_bytes() { return kTopkWorkspaceBytes; }
+int maxsim_topk_slots() { return kTopkSlots; }
 int maxsim_tile_n() { return kTileN; }
 
 cudaError_t maxsim_reduce_segments(const float* partial, float* out, int64_t plane, int nseg, int round_ref,

@@ -259,9 +259,9 @@ def launch_maxsim(q: "QueryBlock", bank: "DocBank", *, scores: Optional[torch.Te
         if loss is not None:
             a.loss = ctypes.pointer(loss)
             a.d_done_counter = done_counter.data_ptr()
-        if topk is not None:  # (scores [n, k] fp32, idx [n, k] int32, counters, k): selection fused into the kernel's tail
-            a.d_topk_scores, a.d_topk_idx, a.d_topk_counters, a.topk_k = (topk[0].data_ptr(), topk[1].data_ptr(),
-                                                                          topk[2].data_ptr(), int(topk[3]))
+        if topk is not None:  # (scores [n, k] fp32, idx [n, k] int32, workspace, k): selection fused into the kernel's tail
+            a.d_topk_scores, a.d_topk_idx, a.d_topk_ws, a.topk_k = (topk[0].data_ptr(), topk[1].data_ptr(),
+                                                                    topk[2].data_ptr(), int(topk[3]))
         rc = lib.cpb_maxsim_launch(ctypes.byref(a))
     _lib.check(rc, "cpb_maxsim_launch")
     _lib.count_launches(2 if ws is not None else 1)
@@ -281,23 +281,22 @@ def maxsim(q: QueryBlock, bank: DocBank, *, round_bf16: bool = False, want_argma
     return (scores, argmax) if want_argmax else scores
 
 
-_TOPK_COUNTERS: dict = {}
+_TOPK_WS: dict = {}
 
 
 def maxsim_topk(q: QueryBlock, bank: DocBank, k: int, *, round_bf16: bool = False):
-    """Scores AND the per-query top-``k`` in ONE launch: the last CTA of every query-tile group selects the ``k`` best
-    documents of its queries from the score rows still in L2 (csrc/topk_tail.cuh) -- larger score first, smaller document
-    index on ties.  Returns ``(scores [n, n_docs] fp32, top_scores [n, k'] fp32, top_idx [n, k'] int64)`` with
+    """Scores AND the per-query top-``k`` in ONE launch: the CTAs of every query-tile group select the ``k`` best
+    documents of its queries from the score rows still in L2, each in its own slice, and the last one merges
+    (csrc/topk_tail.cuh) -- larger score first, smaller document index on ties.  Returns ``(scores [n, n_docs] fp32, top_scores [n, k'] fp32, top_idx [n, k'] int64)`` with
     ``k' = min(k, n_docs)``.  ``fused_topk_supported`` tells whether this shape can take the fused path."""
     if not fused_topk_supported(q, bank, k):
         raise _lib.ColpaliB200Error("fused top-k needs dim 128, queries of at most 32 tokens and k <= %d" % _lib.CPB_TOPK_MAX)
     dev = bank.device
     key = (str(dev), torch.cuda.current_stream(dev).cuda_stream)
-    words = (q.n * q.nq_pad + 127) // 128
-    ctr = _TOPK_COUNTERS.get(key)
-    if ctr is None or ctr.numel() < words:
-        ctr = torch.zeros(max(words, 64), dtype=torch.int32, device=dev)  # zero once; the kernel resets what it used
-        _TOPK_COUNTERS[key] = ctr
+    ctr = _TOPK_WS.get(key)
+    if ctr is None:  # group counters + candidate lists: zero once, the kernel leaves the counters at zero
+        ctr = torch.zeros(int(_lib.load().cpb_maxsim_topk_workspace_bytes()), dtype=torch.uint8, device=dev)
+        _TOPK_WS[key] = ctr
     scores = torch.empty(q.n, bank.n_docs, dtype=torch.float32, device=dev)
     top_s = torch.empty(q.n, k, dtype=torch.float32, device=dev)
     top_i = torch.empty(q.n, k, dtype=torch.int32, device=dev)

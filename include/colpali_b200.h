@@ -193,13 +193,14 @@ typedef struct cpb_maxsim_args {
   /* written by the call */
   int32_t grid_out;             /* CTAs launched */
   /* top-k selection fused into the kernel's tail (the sharded scorer's local top-k; replaces torch.topk on the
-     [n_queries, n_docs] slab): the last CTA of every query-tile group selects, per query, the topk_k best documents from
-     the score rows still in L2 -- larger score first, smaller document index on ties; fewer than topk_k documents leave
-     (-inf, INT32_MAX) filler.  Needs dim 128, nq_pad == 32, d_scores, no CPB_FLAG_INDEPENDENT. */
+     [n_queries, n_docs] slab): once a query-tile group's scores are out, each of its CTAs selects the topk_k best documents
+     of the group's queries inside its own slice of the score rows (still in L2) and the last one merges the lists -- larger
+     score first, smaller document index on ties; fewer than topk_k documents (and scores of -inf) leave (-inf, INT32_MAX)
+     filler.  Needs dim 128, nq_pad == 32, d_scores, no CPB_FLAG_INDEPENDENT. */
   float* d_topk_scores;         /* fp32 [n_queries, topk_k] out, or NULL */
   int32_t* d_topk_idx;          /* int32 [n_queries, topk_k] out: document index in this bank */
-  uint32_t* d_topk_counters;    /* ceil(n_queries * nq_pad / 128) device words, zero before the first launch (the kernel
-                                   resets them); not shared by launches that can overlap */
+  void* d_topk_ws;              /* cpb_maxsim_topk_workspace_bytes() bytes, ZERO-INITIALISED ONCE by the caller (the kernel
+                                   leaves its counters at zero); not shared by launches that can overlap */
   int32_t topk_k;               /* 1 .. CPB_TOPK_MAX */
 } cpb_maxsim_args;
 #define CPB_TOPK_MAX 16
@@ -216,6 +217,7 @@ int cpb_maxsim_fwd(const void* d_q, int n_queries, int nq_pad,
 /* Bytes of d_workspace for this shape (0 when nq_pad == 32) / of d_split_ws. */
 int64_t cpb_maxsim_workspace_bytes(int n_queries, int nq_pad, int n_docs);
 int64_t cpb_maxsim_split_workspace_bytes(int n_queries, int nq_pad);
+int64_t cpb_maxsim_topk_workspace_bytes(void);
 
 /* Enqueue a wait on `stream` until d_flags[i] has reached `value` for every i < n (wrap-safe: counters only grow) --
  * the consumer side of the fused all-gather.  A peer that is late is waited for up to "wait_timeout_ms"; on time-out bit

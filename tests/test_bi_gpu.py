@@ -114,6 +114,30 @@ def test_dense_dot_strides_gather_accumulate():
     assert torch.allclose(out.double(), 1 + 0.5 * want[:, rows.long()], atol=1e-4)
 
 
+@pytest.mark.parametrize("m,n,k", [(37, 53, 72), (64, 512, 1536), (130, 300, 256), (8, 8, 2048), (256, 2304, 64), (40, 24, 1056)])
+@pytest.mark.parametrize("dta,dtb", [(torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16),
+                                     (torch.float32, torch.bfloat16)], ids=["f32", "bf16", "f32xbf16"])
+def test_dense_dot_tiled_paths(m, n, k, dta, dtb):
+    """The vectorised kernels (64-tile with the K range split over a cluster, 128-tile) and the generic fallback, for
+    k-contiguous operands and for transposed views (what the backward products pass), against fp64."""
+    gen = torch.Generator(device=DEV).manual_seed(m * n + k)
+    a = torch.randn(m, k, generator=gen, device=DEV).to(dta)
+    b = torch.randn(n, k, generator=gen, device=DEV).to(dtb)
+    want = a.double() @ b.double().t()
+    tol = dict(rtol=1e-5, atol=2e-5 * k ** 0.5)
+    at, bt = a.t().contiguous().t(), b.t().contiguous().t()   # same values, row-contiguous storage
+    for x in (a, at):
+        for y in (b, bt):
+            assert torch.allclose(cb.dense_dot(x, y).double(), want, **tol), (x.stride(), y.stride())
+    rows = torch.randint(0, n, (n + 3,), generator=gen, device=DEV).to(torch.int32)
+    assert torch.allclose(cb.dense_dot(a, b, b_rows=rows).double(), want[:, rows.long()], **tol)
+    # a retrieval-shaped launch takes the 128-tile kernel (more tiles than SMs)
+    if (m, n, k) == (256, 2304, 64):
+        big = torch.randn(1500, k, generator=gen, device=DEV).to(dta)
+        huge = torch.randn(4000, k, generator=gen, device=DEV).to(dtb)
+        assert torch.allclose(cb.dense_dot(big, huge).double(), big.double() @ huge.double().t(), **tol)
+
+
 def test_similarity_maps_against_reference_golden():
     g = load_golden("bi_small.npz")
     img, qe, mask = (torch.from_numpy(g[k]).to(DEV) for k in ("map_img", "map_q", "map_mask"))
