@@ -40,19 +40,20 @@ __device__ __forceinline__ void topk_row_warp(const float* __restrict__ row, int
     for (int u = 0; u < kTopkLoads; ++u) {
       // candidates must beat the lane's current last entry; NaN and -inf never enter (the comparison is false)
       if (v[u] > s[kTopkMax - 1]) {
-        float cv = v[u];
-        int ci = base + 32 * u;
-        bool shifting = false;
+        // insert behind equal scores and shift the rest down by one.  The list is sorted, so (cv > s[j]) is monotone in
+        // j: every slot decides on its own from two comparisons -- 16 independent selects instead of a 16-step carry
+        // chain of dependent compare / select pairs (a lone warp cannot hide that latency)
+        const float cv = v[u];
+        const int ci = base + 32 * u;
 #pragma unroll
-        for (int j = 0; j < kTopkMax; ++j) {  // insert behind equal scores, then shift the rest down by one
-          shifting = shifting || (cv > s[j]);
-          const float ts = s[j];
-          const int ti = id[j];
-          s[j] = shifting ? cv : ts;
-          id[j] = shifting ? ci : ti;
-          cv = shifting ? ts : cv;
-          ci = shifting ? ti : ci;
+        for (int j = kTopkMax - 1; j > 0; --j) {  // high to low: s[j - 1] is still the old value
+          const bool here = cv > s[j], above = cv > s[j - 1];
+          s[j] = here ? (above ? s[j - 1] : cv) : s[j];
+          id[j] = here ? (above ? id[j - 1] : ci) : id[j];
         }
+        const bool first = cv > s[0];
+        s[0] = first ? cv : s[0];
+        id[0] = first ? ci : id[0];
       }
     }
   }

@@ -89,10 +89,14 @@ class QueryBlock:
         self.device = device
         raw_dim = qs.shape[2] if isinstance(qs, torch.Tensor) else int(qs[0].shape[-1])
         self.dim = _padded_dim(raw_dim)
-        if (isinstance(qs, torch.Tensor) and qs.device == device and qs.dtype == torch.bfloat16 and qs.is_contiguous()
-                and nq == self.nq_pad and qs.shape[2] == self.dim and qs.data_ptr() % 16 == 0):
-            self.flat = qs.view(n * nq, self.dim)  # already in kernel layout: zero copy
-            return
+        if (isinstance(qs, torch.Tensor) and qs.dtype == torch.bfloat16 and qs.is_contiguous()
+                and nq == self.nq_pad and qs.shape[2] == self.dim):
+            if qs.device == device and qs.data_ptr() % 16 == 0:
+                self.flat = qs.view(n * nq, self.dim)  # already in kernel layout: zero copy
+                return
+            if qs.device != device:  # kernel layout on another device (the host): one upload, no zero-fill / re-pad pass
+                self.flat = qs.to(device, non_blocking=True).view(n * nq, self.dim)
+                return
         flat = torch.zeros(n, self.nq_pad, self.dim, dtype=torch.bfloat16, device=device)
         if isinstance(qs, torch.Tensor):
             flat[:, :nq] = _pad_dim(qs.to(device, non_blocking=True))
@@ -287,8 +291,8 @@ _TOPK_WS: dict = {}
 def maxsim_topk(q: QueryBlock, bank: DocBank, k: int, *, round_bf16: bool = False):
     """Scores AND the per-query top-``k`` in ONE launch: the CTAs of every query-tile group select the ``k`` best
     documents of its queries from the score rows still in L2, each in its own slice, and the last one merges
-    (csrc/topk_tail.cuh) -- larger score first, smaller document index on ties.  Returns ``(scores [n, n_docs] fp32, top_scores [n, k'] fp32, top_idx [n, k'] int64)`` with
-    ``k' = min(k, n_docs)``.  ``fused_topk_supported`` tells whether this shape can take the fused path."""
+    (csrc/topk_tail.cuh) -- larger score first, smaller document index on ties.  Returns ``(scores [n, n_docs] fp32, top_scores [n, k'] fp32, top_idx [n, k'] int32)`` with
+    ``k' = min(k, n_docs)`` (views of the kernel's outputs: no kernel runs after the launch).  ``fused_topk_supported`` tells whether this shape can take the fused path."""
     if not fused_topk_supported(q, bank, k):
         raise _lib.ColpaliB200Error("fused top-k needs dim 128, queries of at most 32 tokens and k <= %d" % _lib.CPB_TOPK_MAX)
     dev = bank.device
@@ -302,7 +306,7 @@ def maxsim_topk(q: QueryBlock, bank: DocBank, k: int, *, round_bf16: bool = Fals
     top_i = torch.empty(q.n, k, dtype=torch.int32, device=dev)
     launch_maxsim(q, bank, scores=scores, round_bf16=round_bf16, topk=(top_s, top_i, ctr, k))
     kk = min(k, bank.n_docs)
-    return scores, top_s[:, :kk], top_i[:, :kk].to(torch.int64)
+    return scores, top_s[:, :kk], top_i[:, :kk]
 
 
 def fused_topk_supported(q: QueryBlock, bank: DocBank, k: int) -> bool:

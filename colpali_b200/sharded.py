@@ -49,7 +49,7 @@ def _local_topk(qs, bank, k: int, scorer: Optional[Callable]) -> Tuple[torch.Ten
         q = QueryBlock(qs, bank.device)
         if fused_topk_supported(q, bank, k):
             _, s, i = maxsim_topk(q, bank, k)
-            return s, i, bank.n_docs
+            return s, i.to(torch.int64), bank.n_docs
         local = _default_local_scorer(qs, bank)
     else:
         local = scorer(qs, bank).to(torch.float32)

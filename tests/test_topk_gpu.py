@@ -47,7 +47,7 @@ def test_fused_topk_equals_sorted_scores(n_q, n_docs, doc_len, k):
         assert torch.equal(scores, maxsim(q, bank))
         want_s, want_i = _expect(scores, k)
         assert top_s.shape == want_s.shape == (n_q, min(k, n_docs))
-        assert torch.equal(top_s, want_s) and torch.equal(top_i, want_i), rep
+        assert top_i.dtype == torch.int32 and torch.equal(top_s, want_s) and torch.equal(top_i.long(), want_i), rep
     if doc_len:
         hit = (top_i == 1).nonzero()
         for qi, pos in hit.tolist():        # the duplicate of document 1 directly follows it
