@@ -242,7 +242,11 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    numa = bind_to_gpu_numa_node(local) if world > 1 else {"node": None, "why": "single rank: not bound"}
+    # every rank runs on (and first-touches its pinned buffers on) its GPU's NUMA node -- at N = 1 too: an unbound
+    # process may sit on the other socket and push its 264 MB across the inter-socket link (5.8-6.3 ms per cold step
+    # against 5.0 ms for a bound rank of the N = 2 run).  The affinity is restored before the CPU baseline is timed.
+    orig_affinity = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -429,6 +433,7 @@ def run_b200(args):
         if selftest:
             line["selftest"] = selftest
         if not args.no_cpu and world == 1:
+            os.sched_setaffinity(0, orig_affinity)  # the CPU arm gets every core the container may use, not one node's
             fn, kind = reference_scorer()
             threads = pick_cpu_threads(fn)
             qps, sec, sample = cpu_reference_arm(fn, 5, 1, threads)
