@@ -524,7 +524,8 @@ int cpb_dense_dot_launch(const cpb_dense_dot_args* a) {
   if (a->m <= 0 || a->n <= 0 || a->k <= 0) return fail(CPB_E_INVALID, "m=%d, n=%d, k=%d must be positive", a->m, a->n, a->k);
   if (!a->d_a || !a->d_b || !a->d_out) return fail(CPB_E_INVALID, "null device pointer");
   if (a->out_row_stride < a->n) return fail(CPB_E_INVALID, "out_row_stride=%lld < n=%d", static_cast<long long>(a->out_row_stride), a->n);
-  if ((a->m + 31) / 32 > 65535) return fail(CPB_E_UNSUPPORTED, "m=%d: more than 65535 row tiles (put the long side in n)", a->m);
+  if (((static_cast<int64_t>(a->m) + 31) / 32) * ((static_cast<int64_t>(a->n) + 31) / 32) > 0x7fffffffLL)
+    return fail(CPB_E_UNSUPPORTED, "m=%d x n=%d: more than 2^31 output tiles", a->m, a->n);
   cpb::DenseDotParams p{};
   p.a = a->d_a;
   p.b = a->d_b;

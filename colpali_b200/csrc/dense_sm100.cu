@@ -118,7 +118,11 @@ __global__ void __launch_bounds__(kThreads) dense_tile_kernel(const DenseDotPara
   __shared__ __align__(16) float sa[2][BK][LD];
   __shared__ __align__(16) float sb[2][BK][LD];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int i0 = blockIdx.y * TILE, j0 = blockIdx.x * TILE;
+  // Linear tile index, ROW tiles fastest: the CTAs in flight at any time share a few B tiles (documents) and sweep all
+  // of A (queries), so B -- the big operand of a retrieval call, larger than L2 -- leaves DRAM once.  (Column tiles
+  // fastest re-read B once per row tile: 4.9 GB of DRAM reads for 0.62 GB of operands at 1000 x 100 000 x 1536.)
+  const int m_tiles = (p.m + TILE - 1) / TILE;
+  const int i0 = static_cast<int>(blockIdx.x % m_tiles) * TILE, j0 = static_cast<int>(blockIdx.x / m_tiles) * TILE;
   const TA* a = static_cast<const TA*>(p.a);
   const TB* b = static_cast<const TB*>(p.b);
   const bool a_kc = (p.a_ks == 1), b_kc = (p.b_ks == 1);
@@ -241,7 +245,8 @@ __global__ void __launch_bounds__(kThreads) dense_generic_kernel(const DenseDotP
   __shared__ float sa[kGenKC][33];
   __shared__ float sb[kGenKC][33];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  const int m_tiles = (p.m + 31) / 32;  // linear tile index, row tiles fastest (see dense_tile_kernel)
+  const int i0 = static_cast<int>(blockIdx.x % m_tiles) * 32, j0 = static_cast<int>(blockIdx.x / m_tiles) * 32;
   float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
   for (int k0 = 0; k0 < p.k; k0 += kGenKC) {
     generic_load_tile<TA>(sa, static_cast<const TA*>(p.a), nullptr, p.a_rs, p.a_ks, i0, p.m, k0, p.k);
@@ -283,7 +288,7 @@ bool operand_vectorisable(const void* base, int64_t rs, int64_t ks, int n_rows, 
 template <int TILE, int BK, typename TA, typename TB>
 cudaError_t launch_tile(const DenseDotParams& p, int split_k, cudaStream_t stream) {
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((p.n + TILE - 1) / TILE, (p.m + TILE - 1) / TILE, split_k);
+  cfg.gridDim = dim3(static_cast<unsigned>(((p.n + TILE - 1) / TILE) * static_cast<int64_t>((p.m + TILE - 1) / TILE)), 1, split_k);
   cfg.blockDim = dim3(kThreads);
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -301,7 +306,7 @@ cudaError_t launch_typed(const DenseDotParams& p, int sm_count, cudaStream_t str
   const bool fast = operand_vectorisable<TA>(p.a, p.a_rs, p.a_ks, p.m, p.k, false) &&
                     operand_vectorisable<TB>(p.b, p.b_rs, p.b_ks, p.n, p.k, p.b_rows != nullptr);
   if (!fast) {
-    const dim3 grid((p.n + 31) / 32, (p.m + 31) / 32);
+    const dim3 grid(static_cast<unsigned>(((p.n + 31) / 32) * static_cast<int64_t>((p.m + 31) / 32)));
     dense_generic_kernel<TA, TB><<<grid, kThreads, 0, stream>>>(p);
     return cudaGetLastError();
   }

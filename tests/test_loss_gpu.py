@@ -236,6 +236,52 @@ def test_sigmoid_loss_matches_reference(name, make):
         cb.ColbertSigmoidLoss()(q.to(DEV), torch.from_numpy(g["d"]).to(DEV))  # non-square score matrix
 
 
+@pytest.mark.parametrize("kind", ("negce", "negce_filter", "pairneg", "sigmoid"))
+def test_explicit_negative_and_sigmoid_losses_at_training_shapes(kind):
+    """the a5 losses were only checked at B = 4.  B = 32 queries of 32 tokens, C = 64 gathered
+    documents (offset 32) of 200..300 tokens left-padded with zero rows, 3 negatives per query, bf16 -- against the
+    pinned oracle port evaluated in fp32 on copies of the same bf16 values (losses) and through autograd (gradients)."""
+    gen = torch.Generator().manual_seed(31)
+    b, c, n_neg, nq, nd, off = 32, 64, 3, 32, 300, 32
+    unit = lambda *sh: torch.nn.functional.normalize(torch.randn(*sh, generator=gen), dim=-1)  # noqa: E731
+    q, d, neg = unit(b, nq, 128), unit(c, nd, 128), unit(b, n_neg, nd, 128)
+    q[:, 24:] = 0                                                   # 24 real query tokens (the rest is padding)
+    d[off:off + b, -nq:] = torch.nn.functional.normalize(q + 0.5 * unit(b, nq, 128), dim=-1)  # planted positives
+    d[off:off + b, -nq:][:, 24:] = unit(b, 8, 128)
+    lens = torch.randint(200, nd + 1, (c,), generator=gen)
+    for j in range(c):
+        d[j, : nd - int(lens[j])] = 0
+    neg[:, :, :40] = 0
+    q, d, neg = q.bfloat16(), d.bfloat16(), neg.bfloat16()
+    if kind == "sigmoid":
+        d, off = d[off:off + b].contiguous(), 0
+        mod, port, kw = cb.ColbertSigmoidLoss(), O.colbert_sigmoid_loss_port, {}
+    elif kind == "pairneg":
+        mod, port, kw = cb.ColbertPairwiseNegativeCELoss(in_batch_term_weight=0.4), O.colbert_pairwise_negative_ce_loss_port, dict(in_batch_term_weight=0.4)
+    else:
+        kw = dict(pos_aware_negative_filtering=True, in_batch_term_weight=0.3) if kind == "negce_filter" else {}
+        mod, port = cb.ColbertNegativeCELoss(**kw), O.colbert_negative_ce_loss_port
+    qq, dd = q.to(DEV).requires_grad_(True), d.to(DEV).requires_grad_(True)
+    qo, do = q.float().requires_grad_(True), d.float().requires_grad_(True)
+    if kind == "sigmoid":
+        loss, want = mod(qq, dd), port(qo, do)
+        nn = no = None
+    else:
+        nn, no = neg.to(DEV).requires_grad_(True), neg.float().requires_grad_(True)
+        loss, want = mod(qq, dd, nn, offset=off), port(qo, do, no, offset=off, **kw)
+    loss.backward()
+    want.backward()
+    assert abs(float(loss) - float(want.detach())) < LOSS_TOL, (kind, float(loss), float(want.detach()))
+    for got, ref, src in ((qq.grad, qo.grad, q), (dd.grad, do.grad, d), (nn.grad if nn is not None else None, no.grad if no is not None else None, neg)):
+        if got is None:
+            continue
+        real = (src.float().abs().sum(-1) > 0)  # zero (padding) rows tie everywhere: amax splits, the kernel picks one (a8)
+        g_, r_ = got.float().cpu()[real], ref[real]
+        cos = torch.nn.functional.cosine_similarity(g_.flatten(), r_.flatten(), dim=0)
+        assert cos > 0.999, (kind, float(cos))
+        assert torch.allclose(g_, r_, rtol=3e-2, atol=r_.abs().max().item() * 2e-2), kind
+
+
 def test_reference_kats_for_negative_losses():
     """tests/loss/test_li_losses.py:103-181: all-zero embeddings -> softplus(0) = ln 2 (with and without in-batch term)."""
     b, nq, dim, nneg = 2, 1, 3, 1
