@@ -53,6 +53,7 @@ std::atomic<int> g_opt_boundary_mode{1};
 std::atomic<int> g_opt_pair{0};  // CTA-pair MMAs (maxsim_pair_sm100.cu) where the shape allows
 std::atomic<int> g_opt_early_spin{0};  // MMA issuer pacing (MaxSimParams::early_spin)
 std::atomic<int> g_opt_wait_timeout_ms{120000};
+std::atomic<int> g_opt_dense_raster{4};  // DenseDotParams::raster_group
 std::mutex g_cache_mu;  // guards the device-property / occupancy caches below
 
 int fail(int code, const char* fmt, ...) {
@@ -248,6 +249,9 @@ int cpb_set_option(const char* name, int value) {
   } else if (!strcmp(name, "head_cluster")) {
     if (value < 0 || value > 2) return fail(CPB_E_INVALID, "head_cluster must be 0, 1 or 2");
     g_head_cluster = value;
+  } else if (!strcmp(name, "dense_raster")) {
+    if (value < 1) return fail(CPB_E_INVALID, "dense_raster must be >= 1");
+    g_opt_dense_raster = value;
   } else if (!strcmp(name, "wait_timeout_ms")) {
     if (value <= 0) return fail(CPB_E_INVALID, "wait_timeout_ms must be positive");
     g_opt_wait_timeout_ms = value;
@@ -541,6 +545,7 @@ int cpb_dense_dot_launch(const cpb_dense_dot_args* a) {
   p.out_rs = a->out_row_stride;
   p.alpha = CPB_HAS(a, cpb_dense_dot_args, d_alpha) ? a->d_alpha : nullptr;
   p.accumulate = (a->flags & CPB_DOT_ACCUMULATE) ? 1 : 0;
+  p.raster_group = g_opt_dense_raster.load();
   p.a_f32 = (a->flags & CPB_DOT_A_F32) ? 1 : 0;
   p.b_f32 = (a->flags & CPB_DOT_B_F32) ? 1 : 0;
   CPB_CUDA(cpb::dense_dot_launch(p, static_cast<cudaStream_t>(a->stream)));

@@ -16,6 +16,7 @@ struct DenseDotParams {
   const float* alpha;       // device scalar or nullptr (= 1)
   int accumulate;           // out += alpha * dot instead of out = alpha * dot
   int a_f32, b_f32;         // operand element type: float, else __nv_bfloat16
+  int raster_group;         // output tiles are walked in blocks of this many column tiles x all row tiles (>= 1)
 };
 
 cudaError_t dense_dot_launch(const DenseDotParams& p, cudaStream_t stream);

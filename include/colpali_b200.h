@@ -77,6 +77,8 @@ int cpb_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
  *                     job first; a huge value restores round 1's blocking wait
  *   "head_cluster"    0 = auto, 1 / 2: CTAs sharing the projection weight block (wide head)
  *   "wait_timeout_ms" time-out of cpb_wait_flags (default 120000)
+ *   "dense_raster"    cpb_dense_dot_launch walks the output tiles in blocks of this many column tiles x all row tiles
+ *                     (default 4; 1 = row tiles fastest, a huge value = column tiles fastest)
  *   "debug_delay", "debug_flags"  profiling only
  */
 int cpb_set_option(const char* name, int value);

@@ -256,10 +256,14 @@ def test_explicit_negative_and_sigmoid_losses_at_training_shapes(kind):
     if kind == "sigmoid":
         d, off = d[off:off + b].contiguous(), 0
         mod, port, kw = cb.ColbertSigmoidLoss(), O.colbert_sigmoid_loss_port, {}
-    elif kind == "pairneg":
-        mod, port, kw = cb.ColbertPairwiseNegativeCELoss(in_batch_term_weight=0.4), O.colbert_pairwise_negative_ce_loss_port, dict(in_batch_term_weight=0.4)
+    elif kind == "pairneg":  # (temperatures at which the planted positives do not saturate the softplus / softmax:
+        # at the default 0.02 every gradient of this batch is ~1e-12 and a comparison of directions is noise)
+        kw = dict(temperature=0.5, in_batch_term_weight=0.4)
+        mod, port = cb.ColbertPairwiseNegativeCELoss(**kw), O.colbert_pairwise_negative_ce_loss_port
     else:
-        kw = dict(pos_aware_negative_filtering=True, in_batch_term_weight=0.3) if kind == "negce_filter" else {}
+        kw = dict(temperature=0.3)
+        if kind == "negce_filter":
+            kw.update(pos_aware_negative_filtering=True, in_batch_term_weight=0.3)
         mod, port = cb.ColbertNegativeCELoss(**kw), O.colbert_negative_ce_loss_port
     qq, dd = q.to(DEV).requires_grad_(True), d.to(DEV).requires_grad_(True)
     qo, do = q.float().requires_grad_(True), d.float().requires_grad_(True)
