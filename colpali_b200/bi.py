@@ -50,6 +50,12 @@ def dense_dot(a: torch.Tensor, b: torch.Tensor, *, b_rows: Optional[torch.Tensor
         raise _lib.ColpaliB200Error("dense_dot operands live on different devices")
     a, b = _as_dot_operand(a), _as_dot_operand(b)
     m, k = a.shape
+    if b_rows is not None and (b_rows.device != dev or b_rows.dtype != torch.int32 or not b_rows.is_contiguous()):
+        raise ValueError("b_rows must be a contiguous int32 tensor on the operands' device")
+    if alpha is not None and (alpha.device != dev or alpha.dtype != torch.float32 or alpha.numel() != 1):
+        raise ValueError("alpha must be a one-element fp32 tensor on the operands' device")
+    if out is not None and out.device != dev:
+        raise ValueError("the output tensor lives on another device")
     n = int(b_rows.numel()) if b_rows is not None else b.shape[0]
     if out is None:
         if accumulate:
@@ -120,7 +126,7 @@ def get_similarity_maps_from_embeddings(image_embeddings: torch.Tensor, query_em
                 f"does not match the number of non-padded image tokens ({counts[idx]})."
             )
         rows = torch.nonzero(image_mask[idx], as_tuple=False).flatten()      # masked tokens, row-major "(h w)"
-        rows = rows.view(h, w).t().contiguous().view(-1).to(torch.int32)     # output order: i = w index, j = h index
+        rows = rows.view(h, w).t().contiguous().view(-1).to(device=dev, dtype=torch.int32)  # output order: i = w index, j = h index
         sim = dense_dot(query_embeddings[idx].to(dev), image_embeddings[idx], b_rows=rows)
         maps.append(sim.view(query_embeddings.shape[1], w, h))
     return maps
