@@ -34,7 +34,7 @@ EXPORTED_SYMBOLS = (
     "cpb_dense_dot_launch",
 )
 
-CPB_ABI_VERSION = 2
+CPB_ABI_VERSION = 3
 CPB_FLAG_ROUND_BF16 = 1
 CPB_FLAG_CONTIGUOUS = 2
 CPB_FLAG_INDEPENDENT = 4

@@ -294,4 +294,63 @@ __device__ __forceinline__ void colbert_loss_body(const LossParams& p) {
   }
 }
 
+// Rows [b0, b1) only: their loss sum and the min / max of their normalised scores -> partial3[0..2] (written by one
+// thread).  Whole-CTA function like colbert_loss_body.  The fused MaxSim kernels call it from the last CTA of every
+// query-tile GROUP (the CTAs that produced those rows' scores), so the row work of a batch runs on q_groups SMs at once
+// instead of on the single last CTA of the grid; colbert_loss_combine then folds the partials.
+__device__ __forceinline__ void colbert_loss_rows_partial(const LossParams& p, int b0, int b1, float* partial3) {
+  __shared__ float s_loss[32];
+  __shared__ float s_min[32];
+  __shared__ float s_max[32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = blockDim.x >> 5;
+  float loss_acc = 0.f, mn = INFINITY, mx = -INFINITY;
+  if (p.C <= 32 * kLossCols) {
+    for (int b = b0 + warp; b < b1; b += nwarps) loss_acc += colbert_loss_row<true>(p, b, lane, mn, mx);
+  } else {
+    for (int b = b0 + warp; b < b1; b += nwarps) loss_acc += colbert_loss_row<false>(p, b, lane, mn, mx);
+  }
+  mn = warp_min_f(mn);
+  mx = warp_max_f(mx);
+  if (lane == 0) {
+    s_loss[warp] = loss_acc;
+    s_min[warp] = mn;
+    s_max[warp] = mx;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float l = (lane < nwarps) ? s_loss[lane] : 0.f;
+    float a = (lane < nwarps) ? s_min[lane] : INFINITY;
+    float z = (lane < nwarps) ? s_max[lane] : -INFINITY;
+    l = warp_sum_f(l);
+    a = warp_min_f(a);
+    z = warp_max_f(z);
+    if (lane == 0) {
+      partial3[0] = l;
+      partial3[1] = a;
+      partial3[2] = z;
+    }
+  }
+}
+
+// One warp: loss = (sum of the n_groups partial sums, in group order within each lane, fixed butterfly across lanes) / B.
+__device__ __forceinline__ void colbert_loss_combine(const LossParams& p, const float* partials, int n_groups, int lane) {
+  float l = 0.f, a = INFINITY, z = -INFINITY;
+  for (int g = lane; g < n_groups; g += 32) {
+    l += __ldcg(partials + 3 * g);
+    a = fminf(a, __ldcg(partials + 3 * g + 1));
+    z = fmaxf(z, __ldcg(partials + 3 * g + 2));
+  }
+  l = warp_sum_f(l);
+  a = warp_min_f(a);
+  z = warp_max_f(z);
+  if (lane == 0) {
+    p.loss[0] = l / static_cast<float>(p.B);
+    if (p.bounds != nullptr) {
+      p.bounds[0] = a;
+      p.bounds[1] = z;
+    }
+  }
+}
+
 }  // namespace cpb

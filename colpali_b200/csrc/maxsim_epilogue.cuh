@@ -823,9 +823,14 @@ __device__ __forceinline__ void maxsim_pdl_entry(const MaxSimParams& p) {
 
 // End of the kernel, called by ALL threads of the CTA after their role code: makes the CTA's results visible, signals
 // the fused all-gather's consumers, and lets the last CTA of the grid turn the score matrix into the loss.
-// `group` / `part` / `q_first` / `q_count`: this CTA's query-tile group, document partition and queries (fused top-k).
+// `group` / `part` / `q_first` / `q_count`: this CTA's query-tile group, document partition and queries.  With them
+// (q_count >= 0: the dim-128 kernel) the fused loss runs per group -- the last CTA of every group turns the group's rows
+// of the score matrix into their loss terms and gradients, the last group to finish folds the partial sums -- and the
+// fused top-k can run; without them (K-pipelined and pair kernels) the last CTA of the grid does all rows.
+// Counter workspace (d_done_counter): word 0 = groups (or CTAs) done, words [1, 1 + G) = per-group CTA counters, then
+// 3 G floats of partial (sum, min, max); G = q_groups.  All zero between launches.
 __device__ __forceinline__ void maxsim_finish(const MaxSimParams& p, const LossParams& lp, int cluster, int warp,
-                                              int group = 0, int part = 0, int q_first = 0, int q_count = 0) {
+                                              int group = 0, int part = 0, int q_first = 0, int q_count = -1) {
   __shared__ int s_last;
   const bool fused_loss = lp.loss != nullptr && p.done_counter != nullptr;
   const bool fused_topk = p.topk_scores != nullptr;
@@ -845,7 +850,7 @@ __device__ __forceinline__ void maxsim_finish(const MaxSimParams& p, const LossP
       }
     }
   }
-  if (fused_loss) {
+  if (fused_loss && q_count < 0) {
     if (threadIdx.x == 0) {
       __threadfence();
       const unsigned prev = atomicAdd(p.done_counter, 1u);
@@ -856,6 +861,32 @@ __device__ __forceinline__ void maxsim_finish(const MaxSimParams& p, const LossP
     if (s_last) {
       __threadfence();
       colbert_loss_body(lp);  // reads the [B, C] scores through L2 (__ldcg)
+    }
+  } else if (fused_loss && group < p.q_groups) {  // uniform over the CTA (groups past q_groups are cluster padding)
+    uint32_t* group_ctr = p.done_counter + 1 + group;
+    float* partials = reinterpret_cast<float*>(p.done_counter + 1 + p.q_groups);
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned prev = atomicAdd(group_ctr, 1u);
+      s_last = (prev + 1u == static_cast<unsigned>(p.doc_parts)) ? 1 : 0;
+      if (s_last) *group_ctr = 0u;
+    }
+    __syncthreads();
+    if (s_last) {  // this group's rows of the score matrix are complete
+      __threadfence();
+      colbert_loss_rows_partial(lp, q_first, q_first + q_count, partials + 3 * group);
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        __threadfence();  // partial + gradient rows before the count
+        const unsigned prev = atomicAdd(p.done_counter, 1u);
+        s_last = (prev + 1u == static_cast<unsigned>(p.q_groups)) ? 1 : 0;
+        if (s_last) *p.done_counter = 0u;
+      }
+      __syncthreads();
+      if (s_last && warp == 0) {  // every group has published its partial
+        __threadfence();
+        colbert_loss_combine(lp, partials, p.q_groups, threadIdx.x & 31);
+      }
     }
   }
   if (fused_topk && group < p.q_groups)  // uniform over the CTA (groups past q_groups are cluster padding: no queries)

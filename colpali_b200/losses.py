@@ -41,14 +41,17 @@ from .scoring import DocBank, QueryBlock, _on_device, launch_maxsim
 
 
 _DONE_COUNTERS: dict = {}
+_DONE_WORDS = 4096
 
 
 def _done_counter(dev: torch.device) -> torch.Tensor:
-    """Device word the fused loss uses to find the last CTA, one per (device, stream) (the kernel resets it)."""
+    """Counter workspace of the fused loss (``cpb_maxsim_args.d_done_counter``: completion counters per query-tile group
+    and their partial sums, ``1 + 4 * ceil(B * 32 / 128)`` words), one per (device, stream); zero once, the kernel leaves
+    it zero.  4096 words cover batches of 8184 queries."""
     key = (str(dev), torch.cuda.current_stream(dev).cuda_stream)
     t = _DONE_COUNTERS.get(key)
     if t is None:
-        t = torch.zeros(1, dtype=torch.int32, device=dev)
+        t = torch.zeros(_DONE_WORDS, dtype=torch.int32, device=dev)
         _DONE_COUNTERS[key] = t
     return t
 

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define CPB_ABI_VERSION 2
+#define CPB_ABI_VERSION 3
 
 /* error codes */
 #define CPB_OK 0
@@ -191,7 +191,9 @@ typedef struct cpb_maxsim_args {
   uint32_t wait_value;
   /* the in-batch loss "emitted directly": the last CTA of the grid turns d_scores into the loss (+ gradient) */
   const cpb_loss_desc* loss;    /* NULL = scores only */
-  uint32_t* d_done_counter;     /* device uint32, zero before the first launch (the kernel resets it), needed with `loss` */
+  uint32_t* d_done_counter;     /* needed with `loss`: 1 + 4 * ceil(n_queries * nq_pad / 128) device words (completion
+                                   counters of the query-tile groups + their partial sums), ZERO before the first launch;
+                                   the kernel leaves them zero.  (ABI 2: one word) */
   /* written by the call */
   int32_t grid_out;             /* CTAs launched */
   /* top-k selection fused into the kernel's tail (the sharded scorer's local top-k; replaces torch.topk on the

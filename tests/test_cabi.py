@@ -32,7 +32,7 @@ def test_exports_match_header(lib):
 
 
 def test_abi_version(lib):
-    assert lib.cpb_abi_version() == 2
+    assert lib.cpb_abi_version() == 3
 
 
 def test_argument_validation_needs_no_gpu(lib):
