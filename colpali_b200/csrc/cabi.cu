@@ -447,6 +447,8 @@ int cpb_maxsim_launch(cpb_maxsim_args* a) {
     }
     p.doc_parts = parts;
     grid = p.group_sets * p.doc_parts * cluster;
+    if (loss && p.q_groups >= cpb::kLossWsGroups)
+      return fail(CPB_E_UNSUPPORTED, "the fused loss handles at most %d query tiles groups (%d)", cpb::kLossWsGroups - 1, p.q_groups);
     if (d_topk_scores && (grid > cpb::maxsim_topk_slots() || R * 4 > 8))
       return fail(CPB_E_UNSUPPORTED, "fused top-k: grid of %d CTAs exceeds the candidate workspace", grid);
     rc = make_bf16_rowmajor_map(&tq, a->d_q, q_rows64, 128, 128);

@@ -827,10 +827,13 @@ __device__ __forceinline__ void maxsim_pdl_entry(const MaxSimParams& p) {
 // (q_count >= 0: the dim-128 kernel) the fused loss runs per group -- the last CTA of every group turns the group's rows
 // of the score matrix into their loss terms and gradients, the last group to finish folds the partial sums -- and the
 // fused top-k can run; without them (K-pipelined and pair kernels) the last CTA of the grid does all rows.
-// Counter workspace (d_done_counter): word 0 = groups (or CTAs) done, words [1, 1 + G) = per-group CTA counters, then
-// 3 G floats of partial (sum, min, max); G = q_groups.  All zero between launches.
+// Counter workspace (d_done_counter, kLossWsWords words): word 0 = groups (or CTAs) done, words [1, 1 + G) = per-group
+// CTA counters (G = q_groups < kLossWsGroups), and from word kLossWsGroups on 3 floats of partial (sum, min, max) per
+// group.  The counters are zero between launches; the partial region is FIXED, not packed behind the G counters -- a
+// launch with more groups would otherwise find an earlier launch's partial sums where it expects zeroed counters.
 __device__ __forceinline__ void maxsim_finish(const MaxSimParams& p, const LossParams& lp, int cluster, int warp,
                                               int group = 0, int part = 0, int q_first = 0, int q_count = -1) {
+  static_assert(kLossWsWords >= 4 * kLossWsGroups, "partials of every group fit behind the counters");
   __shared__ int s_last;
   const bool fused_loss = lp.loss != nullptr && p.done_counter != nullptr;
   const bool fused_topk = p.topk_scores != nullptr;
@@ -864,7 +867,7 @@ __device__ __forceinline__ void maxsim_finish(const MaxSimParams& p, const LossP
     }
   } else if (fused_loss && group < p.q_groups) {  // uniform over the CTA (groups past q_groups are cluster padding)
     uint32_t* group_ctr = p.done_counter + 1 + group;
-    float* partials = reinterpret_cast<float*>(p.done_counter + 1 + p.q_groups);
+    float* partials = reinterpret_cast<float*>(p.done_counter + kLossWsGroups);
     if (threadIdx.x == 0) {
       __threadfence();
       const unsigned prev = atomicAdd(group_ctr, 1u);

@@ -11,6 +11,10 @@
 
 namespace cpb {
 
+// layout of the fused loss's counter workspace (cpb_maxsim_args.d_done_counter): see maxsim_finish
+constexpr int kLossWsGroups = 1024;  // counters in words [0, 1024): word 0 + one per query-tile group (at most 1023)
+constexpr int kLossWsWords = 4096;   // + 3 floats per group from word 1024 on
+
 struct MaxSimParams {
   const void* q;             // bf16 [q_rows, 128] padded queries
   const int32_t* doc_start;  // [n_docs] first bank row of each document

@@ -46,8 +46,8 @@ _DONE_WORDS = 4096
 
 def _done_counter(dev: torch.device) -> torch.Tensor:
     """Counter workspace of the fused loss (``cpb_maxsim_args.d_done_counter``: completion counters per query-tile group
-    and their partial sums, ``1 + 4 * ceil(B * 32 / 128)`` words), one per (device, stream); zero once, the kernel leaves
-    it zero.  4096 words cover batches of 8184 queries."""
+    and their partial sums, ``CPB_LOSS_WORKSPACE_WORDS`` = 4096 words: up to 1023 groups = 8184 queries), one per
+    (device, stream); zero once, the kernel leaves the counters zero."""
     key = (str(dev), torch.cuda.current_stream(dev).cuda_stream)
     t = _DONE_COUNTERS.get(key)
     if t is None:

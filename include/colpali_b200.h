@@ -191,9 +191,9 @@ typedef struct cpb_maxsim_args {
   uint32_t wait_value;
   /* the in-batch loss "emitted directly": the last CTA of the grid turns d_scores into the loss (+ gradient) */
   const cpb_loss_desc* loss;    /* NULL = scores only */
-  uint32_t* d_done_counter;     /* needed with `loss`: 1 + 4 * ceil(n_queries * nq_pad / 128) device words (completion
-                                   counters of the query-tile groups + their partial sums), ZERO before the first launch;
-                                   the kernel leaves them zero.  (ABI 2: one word) */
+  uint32_t* d_done_counter;     /* needed with `loss`: CPB_LOSS_WORKSPACE_WORDS device words (completion counters of the
+                                   query-tile groups + their partial sums), ZERO before the first launch; the kernel leaves
+                                   the counters zero.  Not shared by launches that can overlap.  (ABI 2: one word) */
   /* written by the call */
   int32_t grid_out;             /* CTAs launched */
   /* top-k selection fused into the kernel's tail (the sharded scorer's local top-k; replaces torch.topk on the
@@ -208,6 +208,7 @@ typedef struct cpb_maxsim_args {
   int32_t topk_k;               /* 1 .. CPB_TOPK_MAX */
 } cpb_maxsim_args;
 #define CPB_TOPK_MAX 16
+#define CPB_LOSS_WORKSPACE_WORDS 4096
 
 int cpb_maxsim_launch(cpb_maxsim_args* args);
 
