@@ -363,6 +363,23 @@ def test_bf16_gradient_rows_are_the_cast_of_the_fp32_rows():
     assert torch.equal(grads[True][0], grads[False][0]) and torch.equal(grads[True][1], grads[False][1])
 
 
+def test_fused_loss_workspace_survives_changing_batch_sizes():
+    """The per-stream counter workspace of the fused loss is shared by launches of different shapes: 1, 5, 2 and 8
+    query-tile groups in turn (a first version packed the groups' partial sums behind the counters, so a launch with more
+    groups than its predecessor started from non-zero counters and never emitted its loss)."""
+    gen = torch.Generator().manual_seed(77)
+    unit = lambda *sh: torch.nn.functional.normalize(torch.randn(*sh, generator=gen), dim=-1).bfloat16()  # noqa: E731
+    for rep in range(2):
+        for b in (4, 40, 12, 64, 3):
+            q, d = unit(b, 32, 128), unit(b + 5, 90, 128)
+            for mod, port in ((cb.ColbertLoss(), O.colbert_loss_port), (cb.ColbertPairwiseCELoss(), O.colbert_pairwise_ce_loss_port)):
+                got = mod(q.to(DEV).requires_grad_(True), d.to(DEV))      # argmax kernel + per-group loss tail
+                got_ng = mod(q.to(DEV), d.to(DEV))                         # max kernel, no gradient
+                want = port(q.float(), d.float())
+                assert abs(float(got) - float(want)) < 1e-4, (rep, b, float(got), float(want))
+                assert abs(float(got_ng) - float(want)) < 1e-4, (rep, b, float(got_ng), float(want))
+
+
 def test_back_to_back_training_forwards_do_not_deadlock():
     """400 argmax-mode forwards without host synchronisation (a training loop): the epilogue warpgroups of every CTA must
     get their registers (setmaxnreg) in every launch -- a race there killed one launch in a few hundred."""
