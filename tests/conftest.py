@@ -11,6 +11,28 @@ if ROOT not in sys.path:
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+def _usable_cores() -> int:
+    """min(cpu_count, affinity, cgroup quota).  The GPU boxes show 128 logical CPUs but cap the container at 16
+    (cpu.max); the CPU oracle (torch einsum / autograd on the host) is ~80x slower when oneDNN oversubscribes them --
+    the GPU suite went from 50 s to 12 minutes when four more oracle-backed tests were added."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        pass
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        pass
+    return n
+
+
+torch.set_num_threads(_usable_cores())
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA sm_100 device (run on the B200 box)")
 

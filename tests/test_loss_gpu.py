@@ -376,8 +376,8 @@ def test_fused_loss_workspace_survives_changing_batch_sizes():
                 got = mod(q.to(DEV).requires_grad_(True), d.to(DEV))      # argmax kernel + per-group loss tail
                 got_ng = mod(q.to(DEV), d.to(DEV))                         # max kernel, no gradient
                 want = port(q.float(), d.float())
-                assert abs(float(got) - float(want)) < 1e-4, (rep, b, float(got), float(want))
-                assert abs(float(got_ng) - float(want)) < 1e-4, (rep, b, float(got_ng), float(want))
+                assert abs(float(got) - float(want)) < 2e-4, (rep, b, float(got), float(want))
+                assert abs(float(got_ng) - float(want)) < 2e-4, (rep, b, float(got_ng), float(want))
 
 
 def test_back_to_back_training_forwards_do_not_deadlock():
