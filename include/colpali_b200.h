@@ -21,7 +21,19 @@
  *     idempotent and guarded, and (b) the tuning knobs of cpb_set_option, which are atomics read
  *     once per launch -- change them only for experiments.  Device scratch that a caller shares
  *     between launches (d_split_ws, d_done_counter) must not be shared by launches that can run
- *     at the same time: give every stream its own.
+ *     at the same time: give every stream its own;
+ *   - forward progress: the MaxSim kernels are persistent.  Whenever the documents are split
+ *     into more than one partition per query-tile group, the grid is sized from the occupancy
+ *     query so that ALL of its CTAs are resident at once on an otherwise idle device, and some
+ *     CTAs then wait for a neighbour inside the kernel (a document cut by a partition boundary
+ *     -- option "balanced" --, the fused top-k's per-group rendezvous, the fused all-gather's
+ *     write-after-read guard; the fused loss never waits: the last CTA to arrive does the work).
+ *     Kernels of other streams or processes that occupy SMs only delay those waits, as long as
+ *     they finish on their own.  What breaks the assumption is a context that cannot use every
+ *     SM the occupancy query counted (MPS with an active-thread percentage, green contexts):
+ *     there, set cpb_set_option("balanced", 0) and do not pass d_topk_* / d_peer_bases.
+ *     A wait that outlives "wait_timeout_ms" traps (in-kernel) or sets the status word
+ *     (cpb_wait_flags) instead of hanging the device.
  */
 #ifndef COLPALI_B200_H_
 #define COLPALI_B200_H_
