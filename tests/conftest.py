@@ -1,9 +1,15 @@
 import os
 import sys
 
-import numpy as np
-import pytest
-import torch
+# The GPU boxes have no network: the replay test imports the real colpali_engine (hence transformers / huggingface_hub);
+# nothing in the suite downloads anything, and nothing should wait on a resolver time-out to find that out.
+os.environ.setdefault("HF_HUB_OFFLINE", "1")
+os.environ.setdefault("TRANSFORMERS_OFFLINE", "1")
+os.environ.setdefault("HF_HUB_DISABLE_TELEMETRY", "1")
+
+import numpy as np  # noqa: E402
+import pytest  # noqa: E402
+import torch  # noqa: E402
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
