@@ -25,6 +25,9 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# the reference arm imports the real colpali_engine (transformers / huggingface_hub) on a box without network
+for _k in ("HF_HUB_OFFLINE", "TRANSFORMERS_OFFLINE", "HF_HUB_DISABLE_TELEMETRY"):
+    os.environ.setdefault(_k, "1")
 
 N_QUERIES, N_Q, N_DOCS, N_D, DIM = 32, 32, 1000, 1030, 128
 FLOPS_PER_STEP = 2.0 * N_QUERIES * N_Q * N_DOCS * N_D * DIM  # 2*Bq*Nq*Bd*Nd*D
