@@ -4,7 +4,7 @@
  * The reference (illuin-tech/colpali, `colpali_engine`) is pure Python and has no FFI of its own:
  * the seams this library sits behind are three Python attributes.  Each
  * entry point below names the reference code it replaces.  The Python host side
- * (colpali_b200/*.py) binds these symbols with ctypes and keeps the reference signatures.
+ * (the .py files of colpali_b200/) binds these symbols with ctypes and keeps the reference signatures.
  *
  * Conventions
  *   - every pointer named `d_*` is a DEVICE pointer owned by the caller (PyTorch's caching
