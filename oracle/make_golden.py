@@ -35,7 +35,9 @@ from colpali_engine.utils.processing_utils import BaseVisualRetrieverProcessor a
 
 from oracle import li_oracle as O  # noqa: E402
 
-GOLD = os.path.join(ROOT, "tests", "golden")
+# CPB_GOLDEN_OUT=/tmp/somewhere regenerates into another directory (oracle/compare_golden.py then diffs it against the
+# committed fixtures: how reproducible the reference's CPU outputs are on THIS host)
+GOLD = os.environ.get("CPB_GOLDEN_OUT") or os.path.join(ROOT, "tests", "golden")
 os.makedirs(GOLD, exist_ok=True)
 
 
