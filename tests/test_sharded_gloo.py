@@ -65,3 +65,34 @@ def test_sharded_equals_single_process(tmp_path, world, n_docs):
         assert np.array_equal(got["full"], want.numpy())           # every rank holds the full score matrix
         assert np.array_equal(got["ts"], want_s.numpy())
         assert np.array_equal(got["ti"], want_i.numpy())           # recall@k = 1 against the single-process pass
+
+
+def test_merge_topk_and_shard_bounds_properties():
+    """Randomised: merge_topk == a plain sort by (score desc, id asc), ties included (scores drawn from 4 values);
+    shard_bounds is a partition into contiguous ranges whose sizes differ by at most one, larger shards first."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 4), st.integers(1, 40), st.integers(1, 45), st.integers(0, 2**31 - 1))
+    def merge(nq, m, k, seed):
+        g = torch.Generator().manual_seed(seed)
+        s = torch.randint(0, 4, (nq, m), generator=g).float()
+        s[torch.rand(nq, m, generator=g) < 0.1] = float("-inf")            # the filler of short shards
+        ids = torch.stack([torch.randperm(1000, generator=g)[:m] for _ in range(nq)])
+        ts, ti = merge_topk(s, ids, k)
+        kk = min(k, m)
+        assert ts.shape == ti.shape == (nq, kk)
+        for r in range(nq):
+            want = sorted(zip(s[r].tolist(), ids[r].tolist()), key=lambda p: (-p[0], p[1]))[:kk]
+            assert list(zip(ts[r].tolist(), ti[r].tolist())) == want
+
+    @settings(max_examples=100, deadline=None)
+    @given(st.integers(0, 10**6), st.integers(1, 64))
+    def bounds(n, w):
+        b = shard_bounds(n, w)
+        sizes = [hi - lo for lo, hi in b]
+        assert len(b) == w and b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+        assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+
+    merge()
+    bounds()
