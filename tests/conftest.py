@@ -27,12 +27,20 @@ def _usable_cores() -> int:
     except AttributeError:
         pass
     try:
-        with open("/sys/fs/cgroup/cpu.max") as f:
+        with open("/sys/fs/cgroup/cpu.max") as f:  # cgroup v2
             quota, period = f.read().split()
         if quota != "max":
             n = min(n, max(1, int(int(quota) / int(period))))
     except (OSError, ValueError):
-        pass
+        try:  # cgroup v1
+            with open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us") as f:
+                quota = int(f.read())
+            with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as f:
+                period = int(f.read())
+            if quota > 0 and period > 0:
+                n = min(n, max(1, quota // period))
+        except (OSError, ValueError):
+            pass
     return n
 
 
