@@ -7,15 +7,6 @@ os.environ.setdefault("HF_HUB_OFFLINE", "1")
 os.environ.setdefault("TRANSFORMERS_OFFLINE", "1")
 os.environ.setdefault("HF_HUB_DISABLE_TELEMETRY", "1")
 
-import numpy as np  # noqa: E402
-import pytest  # noqa: E402
-import torch  # noqa: E402
-
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-if ROOT not in sys.path:
-    sys.path.insert(0, ROOT)
-GOLDEN = os.path.join(ROOT, "tests", "golden")
-
 
 def _usable_cores() -> int:
     """min(cpu_count, affinity, cgroup quota).  The GPU boxes show 128 logical CPUs but cap the container at 16
@@ -44,7 +35,27 @@ def _usable_cores() -> int:
     return n
 
 
+# numpy's BLAS (oracle.maxsim_f64) and every OpenMP runtime size their pools from the 128 visible CPUs unless told
+# otherwise; torch.set_num_threads below only covers ATen.  Set before numpy / torch are imported.
+for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+    os.environ.setdefault(_k, str(_usable_cores()))
+
+import numpy as np  # noqa: E402
+import pytest  # noqa: E402
+import torch  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
 torch.set_num_threads(_usable_cores())
+try:  # pools that were already created before this file was imported (a plugin importing numpy first)
+    from threadpoolctl import threadpool_limits
+
+    threadpool_limits(limits=_usable_cores())
+except Exception:  # noqa: BLE001 - best effort
+    pass
 
 
 def pytest_configure(config):
